@@ -1,0 +1,120 @@
+"""ctypes binding of libb200engine.so (include/b200engine.h).  No compute lives in Python."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+_LIB = None
+LIB_PATH = Path(__file__).resolve().parent / "lib" / "libb200engine.so"
+
+
+class B200Error(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"b200engine error {code}: {msg}")
+        self.code = code
+
+
+class Config(C.Structure):
+    _fields_ = [
+        ("device", C.c_int32),
+        ("num_layers", C.c_int32), ("hidden", C.c_int32), ("q_heads", C.c_int32), ("kv_heads", C.c_int32),
+        ("intermediate", C.c_int32), ("vocab", C.c_int32),
+        ("rms_eps", C.c_float), ("rope_theta", C.c_float),
+        ("max_model_len", C.c_int32), ("max_num_seqs", C.c_int32), ("max_batched_tokens", C.c_int32),
+        ("num_kv_blocks", C.c_int64), ("kv_fraction", C.c_float),
+        ("enable_prefix_caching", C.c_int32), ("eos_token_id", C.c_int32),
+        ("seed", C.c_uint64), ("init_scale", C.c_float),
+        ("manual_step", C.c_int32), ("record_steps", C.c_int32),
+    ]
+
+
+class Sampling(C.Structure):
+    _fields_ = [("max_tokens", C.c_int32), ("temperature", C.c_float), ("ignore_eos", C.c_int32),
+                ("num_stop_ids", C.c_int32), ("stop_ids", C.POINTER(C.c_int32))]
+
+
+class Usage(C.Structure):
+    _fields_ = [("prompt_tokens", C.c_int32), ("cached_tokens", C.c_int32), ("completion_tokens", C.c_int32)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("steps", C.c_int64), ("running", C.c_int32), ("waiting", C.c_int32),
+                ("kv_blocks_total", C.c_int64), ("kv_blocks_free", C.c_int64),
+                ("prompt_tokens", C.c_int64), ("cached_prompt_tokens", C.c_int64), ("generated_tokens", C.c_int64),
+                ("preemptions", C.c_int64), ("last_step_device_us", C.c_double), ("total_device_us", C.c_double),
+                ("last_step_tokens", C.c_int64), ("kernel_launches", C.c_int64)]
+
+
+class StepInfo(C.Structure):
+    _fields_ = [("tokens", C.c_int32), ("decode_seqs", C.c_int32), ("prefill_seqs", C.c_int32),
+                ("sampled", C.c_int32), ("kv_tokens_read", C.c_int64), ("device_us", C.c_double)]
+
+
+# every symbol include/b200engine.h declares: name -> (restype, argtypes)
+_vp, _i32, _i64, _u64, _f = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64, C.c_float
+_pi32 = C.POINTER(C.c_int32)
+SYMBOLS = {
+    "b200_last_error": (C.c_char_p, []),
+    "b200_version": (C.c_char_p, []),
+    "b200_config_default": (None, [C.POINTER(Config)]),
+    "b200_engine_create": (C.c_int, [C.POINTER(Config), C.POINTER(_vp)]),
+    "b200_engine_destroy": (None, [_vp]),
+    "b200_submit": (C.c_int, [_vp, _pi32, _i32, C.POINTER(Sampling), C.POINTER(_u64)]),
+    "b200_poll": (C.c_int, [_vp, _u64, _pi32, _i32, _pi32, _pi32, C.POINTER(Usage)]),
+    "b200_wait": (C.c_int, [_vp, _u64, _i64]),
+    "b200_abort": (C.c_int, [_vp, _u64]),
+    "b200_release": (C.c_int, [_vp, _u64]),
+    "b200_stats_get": (C.c_int, [_vp, C.POINTER(Stats)]),
+    "b200_engine_step": (C.c_int, [_vp, C.POINTER(StepInfo)]),
+    "b200_engine_replay": (C.c_int, [_vp, _i32, _i32, C.POINTER(C.c_double), C.POINTER(_i64), C.POINTER(_i64),
+                                      C.POINTER(_i64), C.POINTER(_i64)]),
+    "b200_engine_reset_prefix_cache": (C.c_int, [_vp]),
+    "b200_engine_tensor_info": (C.c_int, [_vp, C.c_char_p, C.POINTER(_u64), C.POINTER(_vp)]),
+    "b200_engine_tensor_read": (C.c_int, [_vp, C.c_char_p, _vp, _u64]),
+    "b200_engine_tensor_write": (C.c_int, [_vp, C.c_char_p, _vp, _u64]),
+    "b200_engine_forward_logits": (C.c_int, [_vp, _pi32, _i32, _vp]),
+    "b200_router_create": (C.c_int, [_i32, C.POINTER(_vp)]),
+    "b200_router_destroy": (None, [_vp]),
+    "b200_router_set_endpoints": (C.c_int, [_vp, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p),
+                                             C.POINTER(C.c_char_p), _i32]),
+    "b200_router_pick": (C.c_int, [_vp, _i32, C.c_char_p, C.c_char_p, _i32, _i32, _i64, C.c_char_p, _i32,
+                                    C.POINTER(_u64)]),
+    "b200_router_done": (C.c_int, [_vp, _u64]),
+    "b200_router_add_inflight": (C.c_int, [_vp, C.c_char_p, _i64]),
+    "b200_router_inflight": (C.c_int, [_vp, C.c_char_p, C.POINTER(_i64), C.POINTER(_i64)]),
+    "b200_xxh64": (_u64, [_vp, C.c_size_t]),
+    "b200_op_gemm": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp]),
+    "b200_op_embed": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp]),
+    "b200_op_rmsnorm": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _f, _vp]),
+    "b200_op_rope_kvwrite": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
+    "b200_op_silu_mul": (C.c_int, [_vp, _vp, _i32, _i32, _vp]),
+    "b200_op_argmax": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp]),
+    "b200_op_paged_attn": (C.c_int, [_vp, _i32, _vp, _i32, _vp, _vp, _i32, _vp, _i32, _i32, _i32, _f, _i32, _vp]),
+    "b200_op_init_uniform": (C.c_int, [_vp, _u64, C.c_uint32, _f, _f, _vp]),
+}
+
+
+def lib() -> C.CDLL:
+    """Load the engine library, building it in-tree first if it is missing.  Fails loudly."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not LIB_PATH.exists():
+        from . import _build
+        _build.build()
+    if not LIB_PATH.exists():
+        raise ImportError(f"{LIB_PATH} is missing and could not be built: the CUDA engine is required")
+    l = C.CDLL(str(LIB_PATH), mode=os.RTLD_GLOBAL if hasattr(os, "RTLD_GLOBAL") else C.DEFAULT_MODE)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(l, name)  # AttributeError if the .so does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    _LIB = l
+    return l
+
+
+def check(rc: int) -> int:
+    if rc < 0:
+        raise B200Error(rc, lib().b200_last_error().decode("utf-8", "replace"))
+    return rc

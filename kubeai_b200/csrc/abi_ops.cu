@@ -1,0 +1,150 @@
+// Op-level C-ABI entry points (include/b200engine.h "op-level entry points") + error plumbing.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <mutex>
+
+#include "../../include/b200engine.h"
+#include "errors.h"
+#include "gemm.h"
+#include "kernels.h"
+
+namespace b200 {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int require_device() {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0) {
+    set_error("no CUDA device available (%s): the B200 path has no CPU fallback",
+              e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    return B200_ERR_NO_DEVICE;
+  }
+  return 0;
+}
+
+int cuda_fail(const char* what, int rc) {
+  cudaError_t e = cudaGetLastError();
+  set_error("%s failed (rc=%d, cuda=%s)", what, rc, cudaGetErrorString(e));
+  return rc == -1 ? B200_ERR_INVALID : B200_ERR_CUDA;
+}
+
+namespace {
+// scratch for b200_op_gemm (the engine owns its own)
+std::mutex g_mu;
+float* g_ws = nullptr;
+int* g_counters = nullptr;
+constexpr int kCounterInts = 1 << 20;
+
+int ensure_scratch() {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (g_ws) return 0;
+  int sms = 0, dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (cudaMalloc(&g_ws, gemm_workspace_bytes(sms)) != cudaSuccess) return -1;
+  if (cudaMalloc(&g_counters, kCounterInts * sizeof(int)) != cudaSuccess) return -1;
+  cudaMemset(g_counters, 0, kCounterInts * sizeof(int));
+  return 0;
+}
+}  // namespace
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" {
+
+const char* b200_last_error(void) { return g_err; }
+const char* b200_version(void) { return "kubeai-b200 0.1.0 sm_100a"; }
+
+int b200_op_gemm(const void* w, const void* x, void* out, int32_t N, int32_t T, int32_t K, void* stream) {
+  if (int rc = require_device()) return rc;
+  if (!w || !x || !out || N <= 0 || T < 0 || K <= 0 || K % 8) {
+    set_error("b200_op_gemm: bad arguments N=%d T=%d K=%d", N, T, K);
+    return B200_ERR_INVALID;
+  }
+  if (T == 0) return 0;
+  if (ensure_scratch()) {
+    set_error("b200_op_gemm: workspace allocation failed");
+    return B200_ERR_OOM;
+  }
+  GemmPlan plan;
+  int rc = gemm_plan_init(&plan, w, N, K, K, g_ws, g_counters, 0);
+  if (rc) return cuda_fail("gemm_plan_init", rc);
+  const int bn = gemm_block_n_for(T);
+  const int slabs = (N + 127) / 128, ntt = (T + bn - 1) / bn;
+  if (2ll * slabs * ntt > kCounterInts) {
+    set_error("b200_op_gemm: problem too large for the op-level scratch");
+    return B200_ERR_INVALID;
+  }
+  CUtensorMap tmx;
+  rc = gemm_make_x_map(&tmx, x, T, K, K, bn);
+  if (rc) return cuda_fail("gemm_make_x_map", rc);
+  rc = gemm_run(plan, tmx, bn, out, N, T, static_cast<cudaStream_t>(stream));
+  if (rc) return cuda_fail("gemm_run", rc);
+  return 0;
+}
+
+int b200_op_embed(const void* table, const int32_t* ids, void* out, int32_t T, int32_t H, int32_t vocab,
+                  void* stream) {
+  if (int rc = require_device()) return rc;
+  int rc = embed_gather(table, ids, out, T, H, vocab, static_cast<cudaStream_t>(stream));
+  return rc ? cuda_fail("embed_gather", rc) : 0;
+}
+
+int b200_op_rmsnorm(const void* x, void* residual, const void* w, void* out, const int32_t* row_index,
+                    int32_t rows, int32_t H, float eps, void* stream) {
+  if (int rc = require_device()) return rc;
+  int rc = rmsnorm(x, residual, w, out, row_index, rows, H, eps, static_cast<cudaStream_t>(stream));
+  return rc ? cuda_fail("rmsnorm", rc) : 0;
+}
+
+int b200_op_rope_kvwrite(void* qkv, const int32_t* positions, const int32_t* slots, const void* cos_sin,
+                         void* kv_layer, int32_t T, int32_t q_heads, int32_t kv_heads, int32_t max_pos,
+                         void* stream) {
+  if (int rc = require_device()) return rc;
+  int rc = rope_kv_write(qkv, positions, slots, cos_sin, kv_layer, T, q_heads, kv_heads, max_pos,
+                         static_cast<cudaStream_t>(stream));
+  return rc ? cuda_fail("rope_kv_write", rc) : 0;
+}
+
+int b200_op_silu_mul(const void* gate_up, void* out, int32_t T, int32_t I, void* stream) {
+  if (int rc = require_device()) return rc;
+  int rc = silu_mul(gate_up, out, T, I, static_cast<cudaStream_t>(stream));
+  return rc ? cuda_fail("silu_mul", rc) : 0;
+}
+
+int b200_op_argmax(const void* logits, int32_t* out, int32_t S, int32_t V, int32_t ld, void* stream) {
+  if (int rc = require_device()) return rc;
+  int rc = argmax_rows(logits, out, S, V, ld, static_cast<cudaStream_t>(stream));
+  return rc ? cuda_fail("argmax_rows", rc) : 0;
+}
+
+int b200_op_paged_attn(const void* q, int32_t ldq, void* out, int32_t ldo, const void* kv_layer,
+                       const int32_t* block_tables, int32_t max_blocks, const int32_t* work, int32_t num_work,
+                       int32_t q_heads, int32_t kv_heads, float scale, int32_t decode, void* stream) {
+  if (int rc = require_device()) return rc;
+  static_assert(sizeof(AttnWork) == 16, "AttnWork is int32[4] on the wire");
+  int rc = paged_attention(q, ldq, out, ldo, kv_layer, block_tables, max_blocks,
+                           reinterpret_cast<const AttnWork*>(work), num_work, q_heads, kv_heads, scale, decode,
+                           static_cast<cudaStream_t>(stream));
+  return rc ? cuda_fail("paged_attention", rc) : 0;
+}
+
+int b200_op_init_uniform(void* p, uint64_t n, uint32_t seed, float scale, float offset, void* stream) {
+  if (int rc = require_device()) return rc;
+  int rc = init_uniform(p, n, seed, scale, offset, static_cast<cudaStream_t>(stream));
+  return rc ? cuda_fail("init_uniform", rc) : 0;
+}
+
+}  // extern "C"

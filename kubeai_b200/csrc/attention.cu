@@ -1,0 +1,282 @@
+// Paged causal attention for the per-step hot path (SURVEY.md §8a K6 decode, K7 chunked prefill).
+// Computes softmax(q . K^T / sqrt(128)) . V over the tokens reachable through a sequence's block
+// table, GQA 4:1 — the operation the reference backend delegates to FlashInfer/FlashAttention
+// (vllm/model_executor/models/llama.py:223-233, vllm/v1/attention/backends/flashinfer.py).
+//
+// B200 design: this op is an HBM stream (decode reads 4 KiB of K+V per context token per layer),
+// so the kernel is organised around the page gather, not around the math:
+//   * KV layout is [block][K|V][kv_head][16 tokens][128] so one (page, head) is a contiguous 4 KiB
+//     run; 128 threads pull a 64-token tile (4 pages) with 16-byte cp.async into an XOR-swizzled,
+//     double-buffered smem tile (32 KiB per stage, 3 CTAs/SM => ~96 KiB in flight per SM).
+//   * the 4 query heads of a KV head ride in one m16n8k16 tensor-core tile so K/V bytes are read
+//     once per group (fp32 softmax, warp-shuffle row reductions, P rounded to bf16 for P.V).
+//   * decode: the CTA's 4 warps each own a 16-token strip of every tile and merge their
+//     (max, sum, acc) through smem at the end; prefill: a CTA owns 16 query tokens x 4 heads, one
+//     head per warp, and walks the causal prefix.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace b200 {
+
+namespace {
+
+constexpr int kD = 128;
+constexpr int kTile = 64;                       // tokens per smem tile
+constexpr int kTileBytes = kTile * kD * 2;      // 16 KiB for K, same for V
+constexpr int kStageBytes = 2 * kTileBytes;     // K + V
+constexpr int kAttnSmem = 2 * kStageBytes;      // double buffered: 64 KiB
+
+template <bool DECODE>
+__global__ void __launch_bounds__(128)
+paged_attn_kernel(const __nv_bfloat16* __restrict__ q, int ldq, __nv_bfloat16* __restrict__ out, int ldo,
+                  const __nv_bfloat16* __restrict__ kv, const int* __restrict__ block_tables, int max_blocks,
+                  const AttnWork* __restrict__ work, int Hkv, float scale_log2) {
+  constexpr int WT = DECODE ? 16 : 64;  // tokens of each tile handled by one warp
+  constexpr int NT = WT / 8;
+  extern __shared__ __align__(128) uint8_t smem[];
+  const uint32_t sbase = smem_u32(smem);
+
+  const AttnWork wk = work[blockIdx.x];
+  const int kvh = blockIdx.y;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, tq = lane & 3;
+
+  const int kv_end = wk.q_pos0 + wk.q_count;  // tokens [0, kv_end) are visible to the last query
+  const int ntiles = (kv_end + kTile - 1) / kTile;
+  const int* btab = block_tables + static_cast<size_t>(wk.seq) * max_blocks;
+  const size_t head_page = static_cast<size_t>(16) * kD;            // elements per (page, head)
+  const size_t kv_page = static_cast<size_t>(Hkv) * head_page;      // elements per K (or V) page
+
+  // ---- Q fragments (A operand, 16 rows x 128 d as 8 k-steps)
+  uint32_t qf[8][4];
+  {
+    const __nv_bfloat16* r0p = nullptr;
+    const __nv_bfloat16* r1p = nullptr;
+    if (DECODE) {
+      if (g < 4) r0p = q + static_cast<size_t>(wk.q_tok0) * ldq + (kvh * 4 + g) * kD;
+    } else {
+      const int head = kvh * 4 + warp;
+      if (g < wk.q_count) r0p = q + static_cast<size_t>(wk.q_tok0 + g) * ldq + head * kD;
+      if (g + 8 < wk.q_count) r1p = q + static_cast<size_t>(wk.q_tok0 + g + 8) * ldq + head * kD;
+    }
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks) {
+      const int d = ks * 16 + tq * 2;
+      qf[ks][0] = r0p ? *reinterpret_cast<const uint32_t*>(r0p + d) : 0u;
+      qf[ks][1] = r1p ? *reinterpret_cast<const uint32_t*>(r1p + d) : 0u;
+      qf[ks][2] = r0p ? *reinterpret_cast<const uint32_t*>(r0p + d + 8) : 0u;
+      qf[ks][3] = r1p ? *reinterpret_cast<const uint32_t*>(r1p + d + 8) : 0u;
+    }
+  }
+
+  auto load_tile = [&](int tile, int stage) {
+    const uint32_t kdst = sbase + stage * kStageBytes;
+    const uint32_t vdst = kdst + kTileBytes;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int r = j * 8 + (tid >> 4);  // token row inside the tile
+      const int cc = tid & 15;           // 16-byte chunk inside the 256-byte row
+      const int tok = tile * kTile + r;
+      const bool valid = tok < kv_end;
+      const int blk = valid ? __ldg(btab + (tok >> 4)) : 0;
+      const __nv_bfloat16* ksrc =
+          kv + (static_cast<size_t>(blk) * 2) * kv_page + kvh * head_page + (tok & 15) * kD + cc * 8;
+      const uint32_t off = r * 256 + ((cc ^ (r & 7)) << 4);
+      cp_async_16(kdst + off, ksrc, valid);
+      cp_async_16(vdst + off, ksrc + kv_page, valid);
+    }
+  };
+
+  float o[16][4];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+  const int wo = DECODE ? warp * 16 : 0;  // this warp's token offset inside a tile
+
+  load_tile(0, 0);
+  cp_async_commit();
+  for (int t = 0; t < ntiles; ++t) {
+    if (t + 1 < ntiles) load_tile(t + 1, (t + 1) & 1);
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();
+
+    const int tok_base = t * kTile + wo;
+    if (tok_base < kv_end) {
+      const uint32_t kb = sbase + (t & 1) * kStageBytes;
+      const uint32_t vb = kb + kTileBytes;
+      float s[NT][4];
+#pragma unroll
+      for (int i = 0; i < NT; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
+      const int mi = lane >> 3, ri = lane & 7;
+      // ---- S = Q K^T
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks) {
+#pragma unroll
+        for (int tp = 0; tp < WT / 16; ++tp) {
+          const int tok = wo + tp * 16 + (mi >> 1) * 8 + ri;
+          const int chunk = ks * 2 + (mi & 1);
+          uint32_t b0, b1, b2, b3;
+          ldmatrix_x4(kb + tok * 256 + ((chunk ^ (tok & 7)) << 4), b0, b1, b2, b3);
+          mma_bf16_16816(s[tp * 2], qf[ks], b0, b1);
+          mma_bf16_16816(s[tp * 2 + 1], qf[ks], b2, b3);
+        }
+      }
+      // ---- causal mask, online softmax (fp32, base-2)
+      const int qp0 = DECODE ? wk.q_pos0 : wk.q_pos0 + g;
+      const int qp1 = DECODE ? wk.q_pos0 : wk.q_pos0 + g + 8;
+      float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        const int kp = tok_base + nt * 8 + tq * 2;
+        if (kp > qp0) s[nt][0] = -INFINITY;
+        if (kp + 1 > qp0) s[nt][1] = -INFINITY;
+        if (kp > qp1) s[nt][2] = -INFINITY;
+        if (kp + 1 > qp1) s[nt][3] = -INFINITY;
+        mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
+        mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
+      }
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+      const float mn0 = fmaxf(m0, mx0 * scale_log2), mn1 = fmaxf(m1, mx1 * scale_log2);
+      const float mu0 = mn0 == -INFINITY ? 0.f : mn0, mu1 = mn1 == -INFINITY ? 0.f : mn1;
+      const float a0 = exp2f(m0 - mu0), a1 = exp2f(m1 - mu1);
+      m0 = mn0;
+      m1 = mn1;
+      float ps0 = 0.f, ps1 = 0.f;
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        s[nt][0] = exp2f(s[nt][0] * scale_log2 - mu0);
+        s[nt][1] = exp2f(s[nt][1] * scale_log2 - mu0);
+        s[nt][2] = exp2f(s[nt][2] * scale_log2 - mu1);
+        s[nt][3] = exp2f(s[nt][3] * scale_log2 - mu1);
+        ps0 += s[nt][0] + s[nt][1];
+        ps1 += s[nt][2] + s[nt][3];
+      }
+      l0 = l0 * a0 + ps0;
+      l1 = l1 * a1 + ps1;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        o[i][0] *= a0;
+        o[i][1] *= a0;
+        o[i][2] *= a1;
+        o[i][3] *= a1;
+      }
+      // ---- O += P V
+#pragma unroll
+      for (int kk = 0; kk < WT / 16; ++kk) {
+        uint32_t pa[4];
+        pa[0] = pack_bf16x2(s[2 * kk][0], s[2 * kk][1]);
+        pa[1] = pack_bf16x2(s[2 * kk][2], s[2 * kk][3]);
+        pa[2] = pack_bf16x2(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+        pa[3] = pack_bf16x2(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+#pragma unroll
+        for (int dp = 0; dp < 8; ++dp) {
+          const int tok = wo + kk * 16 + (mi & 1) * 8 + ri;
+          const int chunk = dp * 2 + (mi >> 1);
+          uint32_t b0, b1, b2, b3;
+          ldmatrix_x4_trans(vb + tok * 256 + ((chunk ^ (tok & 7)) << 4), b0, b1, b2, b3);
+          mma_bf16_16816(o[dp * 2], pa, b0, b1);
+          mma_bf16_16816(o[dp * 2 + 1], pa, b2, b3);
+        }
+      }
+    }
+    __syncthreads();
+  }
+  cp_async_wait<0>();
+
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+
+  if (!DECODE) {
+    const int head = kvh * 4 + warp;
+    const float i0 = l0 > 0.f ? 1.f / l0 : 0.f, i1 = l1 > 0.f ? 1.f / l1 : 0.f;
+    if (g < wk.q_count) {
+      __nv_bfloat16* dst = out + static_cast<size_t>(wk.q_tok0 + g) * ldo + head * kD + tq * 2;
+#pragma unroll
+      for (int dn = 0; dn < 16; ++dn)
+        *reinterpret_cast<uint32_t*>(dst + dn * 8) = pack_bf16x2(o[dn][0] * i0, o[dn][1] * i0);
+    }
+    if (g + 8 < wk.q_count) {
+      __nv_bfloat16* dst = out + static_cast<size_t>(wk.q_tok0 + g + 8) * ldo + head * kD + tq * 2;
+#pragma unroll
+      for (int dn = 0; dn < 16; ++dn)
+        *reinterpret_cast<uint32_t*>(dst + dn * 8) = pack_bf16x2(o[dn][2] * i1, o[dn][3] * i1);
+    }
+  } else {
+    // merge the 4 warps' partial softmax states: rows 0..3 of each warp tile are the 4 heads
+    float* so = reinterpret_cast<float*>(smem);            // [4 warps][4 heads][128]
+    float* sm = so + 4 * 4 * kD;                           // [4][4]
+    float* sl = sm + 16;                                   // [4][4]
+    if (g < 4) {
+#pragma unroll
+      for (int dn = 0; dn < 16; ++dn) {
+        float2 v = make_float2(o[dn][0], o[dn][1]);
+        *reinterpret_cast<float2*>(so + (warp * 4 + g) * kD + dn * 8 + tq * 2) = v;
+      }
+      if (tq == 0) {
+        sm[warp * 4 + g] = m0;
+        sl[warp * 4 + g] = l0;
+      }
+    }
+    __syncthreads();
+    const int d = tid;
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+      float mm = -INFINITY;
+#pragma unroll
+      for (int w = 0; w < 4; ++w) mm = fmaxf(mm, sm[w * 4 + h]);
+      float num = 0.f, den = 0.f;
+#pragma unroll
+      for (int w = 0; w < 4; ++w) {
+        const float mw = sm[w * 4 + h];
+        const float wgt = (mw == -INFINITY) ? 0.f : exp2f(mw - mm);
+        num += so[(w * 4 + h) * kD + d] * wgt;
+        den += sl[w * 4 + h] * wgt;
+      }
+      out[static_cast<size_t>(wk.q_tok0) * ldo + (kvh * 4 + h) * kD + d] =
+          __float2bfloat16_rn(den > 0.f ? num / den : 0.f);
+    }
+  }
+}
+
+}  // namespace
+
+int paged_attention(const void* q, int ldq, void* out, int ldo, const void* kv_layer, const int* block_tables,
+                    int max_blocks, const AttnWork* work, int num_work, int Hq, int Hkv, float scale,
+                    int decode, cudaStream_t st) {
+  if (num_work <= 0) return 0;
+  if (Hq != 4 * Hkv) return -1;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(paged_attn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem) !=
+            cudaSuccess ||
+        cudaFuncSetAttribute(paged_attn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem) !=
+            cudaSuccess)
+      return -3;
+    attr_set = true;
+  }
+  const float scale_log2 = scale * 1.4426950408889634f;
+  dim3 grid(num_work, Hkv);
+  const __nv_bfloat16* qq = static_cast<const __nv_bfloat16*>(q);
+  __nv_bfloat16* oo = static_cast<__nv_bfloat16*>(out);
+  const __nv_bfloat16* kk = static_cast<const __nv_bfloat16*>(kv_layer);
+  if (decode)
+    paged_attn_kernel<true><<<grid, 128, kAttnSmem, st>>>(qq, ldq, oo, ldo, kk, block_tables, max_blocks, work,
+                                                          Hkv, scale_log2);
+  else
+    paged_attn_kernel<false><<<grid, 128, kAttnSmem, st>>>(qq, ldq, oo, ldo, kk, block_tables, max_blocks, work,
+                                                           Hkv, scale_log2);
+  return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+}  // namespace b200

@@ -1,0 +1,334 @@
+// Bandwidth-bound per-step ops of the Llama forward.
+// Rounding points follow the reference backend so greedy tokens match:
+//   RMSNorm / fused add:  vllm/ir/ops/layernorm.py:9-21,42-60
+//   RoPE (neox):          vllm/model_executor/layers/rotary_embedding/base.py:140-198 (bf16 cos/sin cache)
+//   SiLU*mul:             vllm/model_executor/layers/activation.py:138-148 (silu in fp32, rounded, then * up)
+//   greedy sampling:      vllm/v1/sample/sampler.py:91,235-236 (argmax, lowest index wins ties)
+// All kernels: 16-byte vectorised, coalesced, one warp-shuffle + one smem hop for reductions.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "kernels.h"
+
+namespace b200 {
+
+namespace {
+
+union Vec8 {
+  uint4 u;
+  __nv_bfloat16 h[8];
+};
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ------------------------------------------------------------------ embedding gather
+__global__ void embed_kernel(const __nv_bfloat16* __restrict__ table, const int* __restrict__ ids,
+                             __nv_bfloat16* __restrict__ out, int H, int vocab) {
+  const int t = blockIdx.x;
+  int id = ids[t];
+  if (id < 0 || id >= vocab) id = 0;
+  const uint4* src = reinterpret_cast<const uint4*>(table + static_cast<size_t>(id) * H);
+  uint4* dst = reinterpret_cast<uint4*>(out + static_cast<size_t>(t) * H);
+  for (int i = threadIdx.x; i < H / 8; i += blockDim.x) dst[i] = __ldg(src + i);
+}
+
+// ------------------------------------------------------------------ (fused add) RMSNorm
+// x: [rows_in, H] GEMM output (or hidden), residual: in/out [rows_in, H] or null.
+// row_index (optional): output row s reads input row row_index[s]; residual is then NOT written back.
+template <int VPT>  // uint4 vectors per thread (H = VPT * 8 * blockDim)
+__global__ void rmsnorm_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ residual,
+                               const __nv_bfloat16* __restrict__ w, __nv_bfloat16* __restrict__ out,
+                               const int* __restrict__ row_index, int H, float eps) {
+  const int s = blockIdx.x;
+  const int r = row_index ? row_index[s] : s;
+  const uint4* xin = reinterpret_cast<const uint4*>(x + static_cast<size_t>(r) * H);
+  uint4* res = residual ? reinterpret_cast<uint4*>(residual + static_cast<size_t>(r) * H) : nullptr;
+  float v[VPT][8];
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    const int idx = threadIdx.x + i * blockDim.x;
+    Vec8 a;
+    a.u = xin[idx];
+    if (res) {
+      Vec8 b;
+      b.u = res[idx];
+      Vec8 o;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float f = __bfloat162float(a.h[j]) + __bfloat162float(b.h[j]);
+        o.h[j] = __float2bfloat16_rn(f);  // residual stored in input dtype ...
+        v[i][j] = f;                      // ... variance from the fp32 sum (layernorm.py:51-56)
+      }
+      if (!row_index) res[idx] = o.u;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[i][j] = __bfloat162float(a.h[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) ss += v[i][j] * v[i][j];
+  }
+  __shared__ float red[32];
+  ss = warp_sum(ss);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    t = warp_sum(t);
+    if (threadIdx.x == 0) red[0] = t;
+  }
+  __syncthreads();
+  const float inv = rsqrtf(red[0] / static_cast<float>(H) + eps);
+  const uint4* wv = reinterpret_cast<const uint4*>(w);
+  uint4* o4 = reinterpret_cast<uint4*>(out + static_cast<size_t>(s) * H);
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    const int idx = threadIdx.x + i * blockDim.x;
+    Vec8 ww, o;
+    ww.u = __ldg(wv + idx);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      // normalised value rounded to bf16 BEFORE the weight multiply (layernorm.py:19)
+      __nv_bfloat16 nb = __float2bfloat16_rn(v[i][j] * inv);
+      o.h[j] = __float2bfloat16_rn(__bfloat162float(nb) * __bfloat162float(ww.h[j]));
+    }
+    o4[idx] = o.u;
+  }
+}
+
+// ------------------------------------------------------------------ RoPE (neox) + paged KV write
+// qkv: [T, (Hq + 2*Hkv) * 128], q and k rotated in place; k,v rows scattered to the paged cache
+// kv layout per layer: [block][2][Hkv][16][128]  (head-major inside a page: one (page,head) = 4 KiB contiguous)
+__global__ void rope_kv_kernel(__nv_bfloat16* __restrict__ qkv, const int* __restrict__ positions,
+                               const int* __restrict__ slots, const __nv_bfloat16* __restrict__ cos_sin,
+                               __nv_bfloat16* __restrict__ kv, int Hq, int Hkv, int max_pos) {
+  constexpr int D = 128, HALF = 64;
+  const int t = blockIdx.x;
+  int pos = positions[t];
+  pos = pos < 0 ? 0 : (pos >= max_pos ? max_pos - 1 : pos);
+  const int slot = slots[t];
+  const int ld = (Hq + 2 * Hkv) * D;
+  __nv_bfloat16* row = qkv + static_cast<size_t>(t) * ld;
+  const __nv_bfloat16* cs = cos_sin + static_cast<size_t>(pos) * D;  // cos[0:64] | sin[0:64]
+  const int blk = slot >> 4, off = slot & 15;
+  const size_t page_stride = static_cast<size_t>(Hkv) * 16 * D;  // elements per K (or V) page over all heads
+  __nv_bfloat16* kbase = kv + static_cast<size_t>(blk) * 2 * page_stride;
+  __nv_bfloat16* vbase = kbase + page_stride;
+
+  const int rot_tasks = (Hq + Hkv) * (HALF / 8);  // 8 elements of x1 (and the matching 8 of x2) per task
+  for (int task = threadIdx.x; task < rot_tasks; task += blockDim.x) {
+    const int head = task >> 3, c = task & 7;
+    __nv_bfloat16* hp = row + head * D;
+    Vec8 x1, x2, co, si, o1, o2;
+    x1.u = *reinterpret_cast<const uint4*>(hp + c * 8);
+    x2.u = *reinterpret_cast<const uint4*>(hp + HALF + c * 8);
+    co.u = __ldg(reinterpret_cast<const uint4*>(cs + c * 8));
+    si.u = __ldg(reinterpret_cast<const uint4*>(cs + HALF + c * 8));
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float a = __bfloat162float(x1.h[j]), b = __bfloat162float(x2.h[j]);
+      const float cc = __bfloat162float(co.h[j]), sn = __bfloat162float(si.h[j]);
+      // every bf16 op rounds, exactly like the reference kernel's scalar_t arithmetic
+      // (x * cos - y * sin with c10::BFloat16 operators == rotary_embedding/common.py:173-174)
+      const float ac = __bfloat162float(__float2bfloat16_rn(__fmul_rn(a, cc)));
+      const float bs = __bfloat162float(__float2bfloat16_rn(__fmul_rn(b, sn)));
+      const float bc = __bfloat162float(__float2bfloat16_rn(__fmul_rn(b, cc)));
+      const float as = __bfloat162float(__float2bfloat16_rn(__fmul_rn(a, sn)));
+      o1.h[j] = __float2bfloat16_rn(ac - bs);
+      o2.h[j] = __float2bfloat16_rn(bc + as);
+    }
+    *reinterpret_cast<uint4*>(hp + c * 8) = o1.u;
+    *reinterpret_cast<uint4*>(hp + HALF + c * 8) = o2.u;
+    if (head >= Hq && slot >= 0) {
+      __nv_bfloat16* dst = kbase + (static_cast<size_t>(head - Hq) * 16 + off) * D;
+      *reinterpret_cast<uint4*>(dst + c * 8) = o1.u;
+      *reinterpret_cast<uint4*>(dst + HALF + c * 8) = o2.u;
+    }
+  }
+  if (slot >= 0) {
+    const int v_tasks = Hkv * (D / 8);
+    const __nv_bfloat16* vrow = row + (Hq + Hkv) * D;
+    for (int task = threadIdx.x; task < v_tasks; task += blockDim.x) {
+      const int head = task >> 4, c = task & 15;
+      uint4 val = *reinterpret_cast<const uint4*>(vrow + head * D + c * 8);
+      *reinterpret_cast<uint4*>(vbase + (static_cast<size_t>(head) * 16 + off) * D + c * 8) = val;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ SiLU(gate) * up
+__global__ void silu_mul_kernel(const __nv_bfloat16* __restrict__ gu, __nv_bfloat16* __restrict__ out, int I,
+                                int ldi) {
+  const int t = blockIdx.y;
+  const uint4* g = reinterpret_cast<const uint4*>(gu + static_cast<size_t>(t) * ldi);
+  const uint4* u = reinterpret_cast<const uint4*>(gu + static_cast<size_t>(t) * ldi + I);
+  uint4* o = reinterpret_cast<uint4*>(out + static_cast<size_t>(t) * I);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < I / 8; i += gridDim.x * blockDim.x) {
+    Vec8 a, b, r;
+    a.u = g[i];
+    b.u = u[i];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float x = __bfloat162float(a.h[j]);
+      const __nv_bfloat16 s = __float2bfloat16_rn(x / (1.0f + expf(-x)));
+      r.h[j] = __float2bfloat16_rn(__bfloat162float(s) * __bfloat162float(b.h[j]));
+    }
+    o[i] = r.u;
+  }
+}
+
+// ------------------------------------------------------------------ greedy argmax over bf16 logits
+__global__ void argmax_kernel(const __nv_bfloat16* __restrict__ logits, int* __restrict__ out, int V, int ld) {
+  const int s = blockIdx.x;
+  const __nv_bfloat16* row = logits + static_cast<size_t>(s) * ld;
+  float best = -INFINITY;
+  int bi = 0x7fffffff;
+  const int nvec = V / 8;
+  const uint4* r4 = reinterpret_cast<const uint4*>(row);
+  for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
+    Vec8 a;
+    a.u = r4[i];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float f = __bfloat162float(a.h[j]);
+      const int idx = i * 8 + j;
+      if (f > best || (f == best && idx < bi)) {
+        best = f;
+        bi = idx;
+      }
+    }
+  }
+  for (int idx = nvec * 8 + threadIdx.x; idx < V; idx += blockDim.x) {
+    const float f = __bfloat162float(row[idx]);
+    if (f > best || (f == best && idx < bi)) {
+      best = f;
+      bi = idx;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ob > best || (ob == best && oi < bi)) {
+      best = ob;
+      bi = oi;
+    }
+  }
+  __shared__ float sb[32];
+  __shared__ int si[32];
+  if ((threadIdx.x & 31) == 0) {
+    sb[threadIdx.x >> 5] = best;
+    si[threadIdx.x >> 5] = bi;
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const int nw = blockDim.x >> 5;
+    best = threadIdx.x < nw ? sb[threadIdx.x] : -INFINITY;
+    bi = threadIdx.x < nw ? si[threadIdx.x] : 0x7fffffff;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ob > best || (ob == best && oi < bi)) {
+        best = ob;
+        bi = oi;
+      }
+    }
+    if (threadIdx.x == 0) out[s] = bi == 0x7fffffff ? 0 : bi;
+  }
+}
+
+// ------------------------------------------------------------------ seeded weight init (device side)
+__device__ __forceinline__ uint32_t mix32(uint32_t x) {
+  x ^= x >> 16;
+  x *= 0x7feb352du;
+  x ^= x >> 15;
+  x *= 0x846ca68bu;
+  x ^= x >> 16;
+  return x;
+}
+// value(i) = scale * u, u uniform in [-sqrt(3), sqrt(3)) (unit variance), from a counter hash.
+__global__ void init_uniform_kernel(__nv_bfloat16* __restrict__ p, size_t n, uint32_t seed, float scale,
+                                    float offset) {
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    uint32_t h = mix32(static_cast<uint32_t>(i) ^ mix32(seed + static_cast<uint32_t>(i >> 32) * 0x9e3779b9u));
+    // explicit _rn intrinsics: no FMA contraction, so a numpy replica is bit-exact
+    const float u = __fmul_rn(__fadd_rn(__fmul_rn(static_cast<float>(h >> 8), 1.0f / 16777216.0f), -0.5f),
+                              3.4641016151f);
+    p[i] = __float2bfloat16_rn(__fadd_rn(offset, __fmul_rn(scale, u)));
+  }
+}
+
+}  // namespace
+
+int embed_gather(const void* table, const int* ids, void* out, int T, int H, int vocab, cudaStream_t st) {
+  if (T <= 0) return 0;
+  if (H % 8) return -1;
+  embed_kernel<<<T, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(table), ids,
+                                  static_cast<__nv_bfloat16*>(out), H, vocab);
+  return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+int rmsnorm(const void* x, void* residual, const void* w, void* out, const int* row_index, int rows, int H,
+            float eps, cudaStream_t st) {
+  if (rows <= 0) return 0;
+  const __nv_bfloat16* xx = static_cast<const __nv_bfloat16*>(x);
+  __nv_bfloat16* rr = static_cast<__nv_bfloat16*>(residual);
+  const __nv_bfloat16* ww = static_cast<const __nv_bfloat16*>(w);
+  __nv_bfloat16* oo = static_cast<__nv_bfloat16*>(out);
+  if (H % 8) return -1;
+  const int vecs = H / 8;
+  // pick threads so that every thread owns exactly VPT vectors
+  if (vecs % 256 == 0 && vecs / 256 <= 4) {
+    switch (vecs / 256) {
+      case 1: rmsnorm_kernel<1><<<rows, 256, 0, st>>>(xx, rr, ww, oo, row_index, H, eps); break;
+      case 2: rmsnorm_kernel<2><<<rows, 256, 0, st>>>(xx, rr, ww, oo, row_index, H, eps); break;
+      case 3: rmsnorm_kernel<3><<<rows, 256, 0, st>>>(xx, rr, ww, oo, row_index, H, eps); break;
+      default: rmsnorm_kernel<4><<<rows, 256, 0, st>>>(xx, rr, ww, oo, row_index, H, eps); break;
+    }
+  } else if (vecs % 32 == 0 && vecs <= 1024) {
+    rmsnorm_kernel<1><<<rows, vecs, 0, st>>>(xx, rr, ww, oo, row_index, H, eps);
+  } else {
+    return -1;
+  }
+  return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+int rope_kv_write(void* qkv, const int* positions, const int* slots, const void* cos_sin, void* kv_layer,
+                  int T, int Hq, int Hkv, int max_pos, cudaStream_t st) {
+  if (T <= 0) return 0;
+  rope_kv_kernel<<<T, 128, 0, st>>>(static_cast<__nv_bfloat16*>(qkv), positions, slots,
+                                    static_cast<const __nv_bfloat16*>(cos_sin),
+                                    static_cast<__nv_bfloat16*>(kv_layer), Hq, Hkv, max_pos);
+  return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+int silu_mul(const void* gate_up, void* out, int T, int I, cudaStream_t st) {
+  if (T <= 0) return 0;
+  if (I % 8) return -1;
+  dim3 grid((I / 8 + 255) / 256, T);
+  silu_mul_kernel<<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(gate_up),
+                                        static_cast<__nv_bfloat16*>(out), I, 2 * I);
+  return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+int argmax_rows(const void* logits, int* out, int S, int V, int ld, cudaStream_t st) {
+  if (S <= 0) return 0;
+  if (ld % 8) return -1;
+  argmax_kernel<<<S, 1024, 0, st>>>(static_cast<const __nv_bfloat16*>(logits), out, V, ld);
+  return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+int init_uniform(void* p, size_t n, uint32_t seed, float scale, float offset, cudaStream_t st) {
+  if (n == 0) return 0;
+  init_uniform_kernel<<<148 * 8, 256, 0, st>>>(static_cast<__nv_bfloat16*>(p), n, seed, scale, offset);
+  return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+}  // namespace b200

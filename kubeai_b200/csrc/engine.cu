@@ -1,0 +1,1029 @@
+// In-process inference engine: one instance per GPU replica.
+// It stands where the reference launches a backend pod (internal/modelcontroller/engine_vllm.go:82-100)
+// and is reached through the C ABI in include/b200engine.h instead of the HTTP hop at
+// internal/modelproxy/handler.go:158.
+//
+// Host side (this file): paged-KV block pool with hash-chained prefix cache, continuous-batching
+// scheduler with chunked prefill under a per-step token budget (semantics of vLLM's
+// v1/core/sched/scheduler.py: running first, then waiting; preempt-by-recompute on KV exhaustion;
+// 16-token blocks; a prefix hit covers at most len-1 tokens), the Llama forward as a fixed kernel
+// sequence on one CUDA stream, greedy sampling, thread-safe submit/poll/wait/abort.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <deque>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/b200engine.h"
+#include "errors.h"
+#include "gemm.h"
+#include "kernels.h"
+#include "xxh64.h"
+
+namespace b200 {
+
+namespace {
+
+constexpr int kD = 128;
+constexpr int kPage = 16;
+typedef __nv_bfloat16 bf16;
+
+#define CK(call)                                                                      \
+  do {                                                                                \
+    cudaError_t e_ = (call);                                                          \
+    if (e_ != cudaSuccess) {                                                          \
+      set_error("%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_));   \
+      return e_ == cudaErrorMemoryAllocation ? B200_ERR_OOM : B200_ERR_CUDA;          \
+    }                                                                                 \
+  } while (0)
+
+// ------------------------------------------------------------------ KV block pool + prefix cache
+class BlockPool {
+ public:
+  void init(int64_t n, bool caching) {
+    n_ = static_cast<int>(n);
+    caching_ = caching;
+    ref_.assign(n_, 0);
+    prev_.assign(n_, -1);
+    next_.assign(n_, -1);
+    uid_.assign(n_, 0);
+    parent_.assign(n_, 0);
+    hash_.assign(n_, 0);
+    toks_.assign(static_cast<size_t>(n_) * kPage, 0);
+    head_ = tail_ = -1;
+    free_ = 0;
+    for (int b = 0; b < n_; ++b) push_free(b);
+    next_uid_ = 1;
+    map_.clear();
+  }
+  int64_t total() const { return n_; }
+  int64_t free_count() const { return free_; }
+
+  // Take a block for writing (evicts its cached identity if it had one).
+  int alloc() {
+    if (head_ < 0) return -1;
+    int b = head_;
+    unlink(b);
+    drop_identity(b);
+    ref_[b] = 1;
+    return b;
+  }
+  void ref(int b) {
+    if (ref_[b] == 0) unlink(b);
+    ++ref_[b];
+  }
+  void unref(int b) {
+    if (--ref_[b] == 0) push_free(b);
+  }
+  // Cached full block whose parent chain uid is `parent` and content is toks[0..16): id or -1.
+  int lookup(uint64_t parent, const int32_t* toks) const {
+    if (!caching_) return -1;
+    auto it = map_.find(key_hash(parent, toks));
+    if (it == map_.end()) return -1;
+    int b = it->second;
+    if (parent_[b] != parent || memcmp(&toks_[static_cast<size_t>(b) * kPage], toks, kPage * 4) != 0) return -1;
+    return b;
+  }
+  // Give block b (just filled) a cache identity; returns the chain uid children must use.
+  uint64_t publish(int b, uint64_t parent, const int32_t* toks) {
+    if (!caching_) return 0;
+    int existing = lookup(parent, toks);
+    if (existing >= 0) return uid_[existing];  // same content already cached elsewhere: chain to it
+    uint64_t h = key_hash(parent, toks);
+    if (map_.count(h)) return next_uid_++;  // 64-bit collision with different content: leave uncached
+    drop_identity(b);
+    uid_[b] = next_uid_++;
+    parent_[b] = parent;
+    hash_[b] = h;
+    memcpy(&toks_[static_cast<size_t>(b) * kPage], toks, kPage * 4);
+    map_[h] = b;
+    return uid_[b];
+  }
+  uint64_t uid(int b) const { return uid_[b]; }
+  void reset_cache() {
+    for (int b = 0; b < n_; ++b) uid_[b] = 0;
+    map_.clear();
+  }
+
+ private:
+  static uint64_t key_hash(uint64_t parent, const int32_t* toks) {
+    uint8_t buf[8 + kPage * 4];
+    memcpy(buf, &parent, 8);
+    memcpy(buf + 8, toks, kPage * 4);
+    return xxh64(buf, sizeof(buf), 0);
+  }
+  void drop_identity(int b) {
+    if (uid_[b]) {
+      auto it = map_.find(hash_[b]);
+      if (it != map_.end() && it->second == b) map_.erase(it);
+      uid_[b] = 0;
+    }
+  }
+  void push_free(int b) {
+    prev_[b] = tail_;
+    next_[b] = -1;
+    if (tail_ >= 0) next_[tail_] = b; else head_ = b;
+    tail_ = b;
+    ++free_;
+  }
+  void unlink(int b) {
+    if (prev_[b] >= 0) next_[prev_[b]] = next_[b]; else head_ = next_[b];
+    if (next_[b] >= 0) prev_[next_[b]] = prev_[b]; else tail_ = prev_[b];
+    prev_[b] = next_[b] = -1;
+    --free_;
+  }
+  int n_ = 0;
+  bool caching_ = true;
+  std::vector<int> ref_, prev_, next_;
+  std::vector<uint64_t> uid_, parent_, hash_;
+  std::vector<int32_t> toks_;
+  int head_ = -1, tail_ = -1;
+  int64_t free_ = 0;
+  uint64_t next_uid_ = 1;
+  std::unordered_map<uint64_t, int> map_;
+};
+
+// ------------------------------------------------------------------ sequences
+struct Seq {
+  uint64_t id = 0;
+  std::vector<int32_t> toks;  // prompt + generated
+  int n_prompt = 0;
+  int n_computed = 0;    // tokens whose KV is in the cache
+  int n_published = 0;   // leading full blocks with a cache identity
+  uint64_t chain_uid = 0;
+  std::vector<int> blocks;
+  int max_tokens = 16;
+  bool ignore_eos = false;
+  std::vector<int32_t> stop_ids;
+  int n_generated = 0;
+  int n_cached = -1;  // prefix-hit tokens at first admission
+  bool admitted = false;
+  // shared with API threads (guarded by Engine::mu_)
+  std::vector<int32_t> out;
+  size_t drained = 0;
+  int finished = 0;
+  bool abort_requested = false;
+};
+
+struct StepMeta {
+  int T = 0, nd = 0, np = 0, S = 0, nseq = 0;
+  int off_ids = 0, off_pos = 0, off_slots = 0, off_rows = 0, off_dwork = 0, off_pwork = 0, off_btab = 0;
+  int words = 0;
+  int64_t kv_tokens = 0;
+  int out_tokens = 0;  // sampled rows that produce a generated token
+};
+
+struct XMaps {
+  CUtensorMap m[4];  // block_n 32, 64, 128, 256
+};
+
+}  // namespace
+
+// ------------------------------------------------------------------ engine
+struct Engine {
+  b200_config cfg;
+  int L, H, Hq, Hkv, I, V, QKV;
+  int Tcap, Scap, max_blocks_per_seq;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  int sms = 148;
+
+  // weights
+  struct Layer {
+    bf16 *wqkv, *wo, *wgu, *wdown, *norm1, *norm2;
+    GemmPlan p_qkv, p_o, p_gu, p_down;
+  };
+  std::vector<Layer> layers;
+  bf16 *embed = nullptr, *lm_head = nullptr, *final_norm = nullptr, *cos_sin = nullptr;
+  GemmPlan p_lm;
+  bf16* weights_blob = nullptr;
+  size_t weights_bytes = 0;
+  std::unordered_map<std::string, std::pair<void*, size_t>> tensors;
+
+  // activations
+  bf16 *res = nullptr, *x = nullptr, *normed = nullptr, *qkv = nullptr, *attn = nullptr, *gu = nullptr, *act = nullptr,
+       *last_hidden = nullptr, *logits = nullptr;
+  int* sampled = nullptr;
+  int32_t* sampled_host = nullptr;  // pinned
+  XMaps xm_normed, xm_attn, xm_act, xm_last;
+  float* gemm_ws = nullptr;
+  int* gemm_counters = nullptr;
+
+  // KV
+  bf16* kv = nullptr;
+  size_t kv_layer_elems = 0;
+  BlockPool pool;
+
+  // step input staging
+  int step_words_cap = 0;
+  int32_t* stage_host = nullptr;  // pinned, one per ring slot
+  std::vector<int32_t*> stage_dev;
+  std::vector<StepMeta> ring_meta;
+  int ring_n = 2, ring_pos = 0;
+  int64_t recorded = 0;
+
+  // scheduler state (engine thread only)
+  std::deque<std::shared_ptr<Seq>> waiting;
+  std::vector<std::shared_ptr<Seq>> running;
+
+  // shared state
+  std::mutex mu_;
+  std::condition_variable cv_work_, cv_out_;
+  std::deque<std::shared_ptr<Seq>> incoming;
+  std::unordered_map<uint64_t, std::shared_ptr<Seq>> requests;
+  uint64_t next_id = 1;
+  std::atomic<bool> stop{false};
+  std::thread worker;
+  b200_stats stats;
+  bool fatal = false;
+
+  ~Engine();
+  int init(const b200_config& c);
+  int alloc_all();
+  int forward(const StepMeta& m, int32_t* dbuf, bool all_logits, bf16* logits_out);
+  int step(b200_step_info* info);
+  void loop();
+  bool ensure_blocks(Seq& s, int upto);
+  void release_blocks(Seq& s);
+  void preempt(std::shared_ptr<Seq> s);
+  void finish(std::shared_ptr<Seq> s, int code);
+  void admit_prefix(Seq& s);
+  const CUtensorMap& xmap(const XMaps& xm, int bn) const { return xm.m[bn == 32 ? 0 : bn == 64 ? 1 : bn == 128 ? 2 : 3]; }
+  int gemm(const GemmPlan& p, const XMaps& xm, void* out, int ldo, int T) {
+    const int bn = gemm_block_n_for(T);
+    ++stats.kernel_launches;
+    return gemm_run(p, xmap(xm, bn), bn, out, ldo, T, stream);
+  }
+};
+
+Engine::~Engine() {
+  stop = true;
+  cv_work_.notify_all();
+  if (worker.joinable()) worker.join();
+  cudaSetDevice(cfg.device);
+  if (stream) cudaStreamSynchronize(stream);
+  void* frees[] = {weights_blob, res, x, normed, qkv, attn, gu, act, last_hidden, logits, sampled, gemm_ws,
+                   gemm_counters, kv};
+  for (void* p : frees)
+    if (p) cudaFree(p);
+  for (auto p : stage_dev)
+    if (p) cudaFree(p);
+  if (stage_host) cudaFreeHost(stage_host);
+  if (sampled_host) cudaFreeHost(sampled_host);
+  if (ev0) cudaEventDestroy(ev0);
+  if (ev1) cudaEventDestroy(ev1);
+  if (stream) cudaStreamDestroy(stream);
+}
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+int Engine::alloc_all() {
+  // ---- weights: one blob, 1 KiB-aligned tensors
+  struct Item {
+    std::string name;
+    size_t elems;
+    bf16** dst;
+    float scale, offset;
+  };
+  std::vector<Item> items;
+  layers.resize(L);
+  const float s_h = 1.0f / sqrtf(static_cast<float>(H)), s_i = 1.0f / sqrtf(static_cast<float>(I)),
+              s_a = 1.0f / sqrtf(static_cast<float>(Hq * kD));
+  items.push_back({"embed", static_cast<size_t>(V) * H, &embed, 1.0f, 0.f});
+  for (int l = 0; l < L; ++l) {
+    std::string p = "layers." + std::to_string(l) + ".";
+    items.push_back({p + "wqkv", static_cast<size_t>(QKV) * H, &layers[l].wqkv, s_h, 0.f});
+    items.push_back({p + "wo", static_cast<size_t>(H) * Hq * kD, &layers[l].wo, s_a, 0.f});
+    items.push_back({p + "wgu", static_cast<size_t>(2) * I * H, &layers[l].wgu, s_h, 0.f});
+    items.push_back({p + "wdown", static_cast<size_t>(H) * I, &layers[l].wdown, s_i, 0.f});
+    items.push_back({p + "norm1", static_cast<size_t>(H), &layers[l].norm1, 0.1f, 1.0f});
+    items.push_back({p + "norm2", static_cast<size_t>(H), &layers[l].norm2, 0.1f, 1.0f});
+  }
+  items.push_back({"final_norm", static_cast<size_t>(H), &final_norm, 0.1f, 1.0f});
+  items.push_back({"lm_head", static_cast<size_t>(V) * H, &lm_head, s_h * (cfg.init_scale > 0 ? cfg.init_scale : 4.0f), 0.f});
+  size_t total = 0;
+  std::vector<size_t> offs;
+  for (auto& it : items) {
+    offs.push_back(total);
+    total += align_up(it.elems * 2, 1024);
+  }
+  const size_t cs_elems = static_cast<size_t>(cfg.max_model_len) * kD;
+  const size_t cs_off = total;
+  total += align_up(cs_elems * 2, 1024);
+  weights_bytes = total;
+  CK(cudaMalloc(&weights_blob, total));
+  for (size_t i = 0; i < items.size(); ++i) {
+    bf16* p = reinterpret_cast<bf16*>(reinterpret_cast<uint8_t*>(weights_blob) + offs[i]);
+    *items[i].dst = p;
+    tensors[items[i].name] = {p, items[i].elems * 2};
+    uint32_t seed = static_cast<uint32_t>(xxh64(items[i].name.data(), items[i].name.size(), cfg.seed));
+    if (init_uniform(p, items[i].elems, seed, items[i].scale, items[i].offset, stream)) return cuda_fail("init_uniform", -2);
+  }
+  cos_sin = reinterpret_cast<bf16*>(reinterpret_cast<uint8_t*>(weights_blob) + cs_off);
+  tensors["cos_sin"] = {cos_sin, cs_elems * 2};
+  {
+    // vllm rotary_embedding/base.py:70-92: inv_freq = base^(-2i/d); cache = cos(t*f) | sin(t*f), cast to bf16
+    std::vector<bf16> h(cs_elems);
+    std::vector<float> inv(kD / 2);
+    for (int i = 0; i < kD / 2; ++i)
+      inv[i] = 1.0f / powf(cfg.rope_theta, static_cast<float>(2 * i) / static_cast<float>(kD));
+    for (int t = 0; t < cfg.max_model_len; ++t)
+      for (int i = 0; i < kD / 2; ++i) {
+        const float f = static_cast<float>(t) * inv[i];
+        h[static_cast<size_t>(t) * kD + i] = __float2bfloat16_rn(cosf(f));
+        h[static_cast<size_t>(t) * kD + kD / 2 + i] = __float2bfloat16_rn(sinf(f));
+      }
+    CK(cudaMemcpyAsync(cos_sin, h.data(), cs_elems * 2, cudaMemcpyHostToDevice, stream));
+    CK(cudaStreamSynchronize(stream));
+  }
+
+  // ---- activations
+  CK(cudaMalloc(&res, static_cast<size_t>(Tcap) * H * 2));
+  CK(cudaMalloc(&x, static_cast<size_t>(Tcap) * H * 2));
+  CK(cudaMalloc(&normed, static_cast<size_t>(Tcap) * H * 2));
+  CK(cudaMalloc(&qkv, static_cast<size_t>(Tcap) * QKV * 2));
+  CK(cudaMalloc(&attn, static_cast<size_t>(Tcap) * Hq * kD * 2));
+  CK(cudaMalloc(&gu, static_cast<size_t>(Tcap) * 2 * I * 2));
+  CK(cudaMalloc(&act, static_cast<size_t>(Tcap) * I * 2));
+  CK(cudaMalloc(&last_hidden, static_cast<size_t>(Scap) * H * 2));
+  CK(cudaMalloc(&logits, static_cast<size_t>(Scap) * V * 2));
+  CK(cudaMalloc(&sampled, static_cast<size_t>(Scap) * 4));
+  CK(cudaMemset(normed, 0, static_cast<size_t>(Tcap) * H * 2));
+  CK(cudaMemset(attn, 0, static_cast<size_t>(Tcap) * Hq * kD * 2));
+  CK(cudaMemset(act, 0, static_cast<size_t>(Tcap) * I * 2));
+  CK(cudaMemset(last_hidden, 0, static_cast<size_t>(Scap) * H * 2));
+  CK(cudaMallocHost(&sampled_host, static_cast<size_t>(Scap) * 4));
+  CK(cudaMalloc(&gemm_ws, gemm_workspace_bytes(sms)));
+  const int maxN = std::max(std::max(QKV, 2 * I), V);
+  const size_t n_counters = 2ull * (maxN / 128 + 2) * (Tcap / 32 + 2);
+  CK(cudaMalloc(&gemm_counters, n_counters * 4));
+  CK(cudaMemset(gemm_counters, 0, n_counters * 4));
+
+  // ---- GEMM plans + activation tensor maps (encoded once; kernels mask rows >= T)
+  auto plan = [&](GemmPlan* p, const void* W, int N, int K) {
+    return gemm_plan_init(p, W, N, K, K, gemm_ws, gemm_counters, sms);
+  };
+  for (int l = 0; l < L; ++l) {
+    if (plan(&layers[l].p_qkv, layers[l].wqkv, QKV, H) || plan(&layers[l].p_o, layers[l].wo, H, Hq * kD) ||
+        plan(&layers[l].p_gu, layers[l].wgu, 2 * I, H) || plan(&layers[l].p_down, layers[l].wdown, H, I))
+      return cuda_fail("gemm_plan_init", -2);
+  }
+  if (plan(&p_lm, lm_head, V, H)) return cuda_fail("gemm_plan_init(lm_head)", -2);
+  const int bns[4] = {32, 64, 128, 256};
+  for (int i = 0; i < 4; ++i) {
+    if (gemm_make_x_map(&xm_normed.m[i], normed, Tcap, H, H, bns[i]) ||
+        gemm_make_x_map(&xm_attn.m[i], attn, Tcap, Hq * kD, Hq * kD, bns[i]) ||
+        gemm_make_x_map(&xm_act.m[i], act, Tcap, I, I, bns[i]) ||
+        gemm_make_x_map(&xm_last.m[i], last_hidden, Scap, H, H, bns[i]))
+      return cuda_fail("gemm_make_x_map", -2);
+  }
+
+  // ---- KV pool
+  const size_t block_bytes_layer = static_cast<size_t>(2) * Hkv * kPage * kD * 2;
+  int64_t nblocks = cfg.num_kv_blocks;
+  if (nblocks <= 0) {
+    size_t fr = 0, tot = 0;
+    CK(cudaMemGetInfo(&fr, &tot));
+    const float frac = cfg.kv_fraction > 0 ? cfg.kv_fraction : 0.85f;
+    nblocks = static_cast<int64_t>(static_cast<double>(fr) * frac / (static_cast<double>(block_bytes_layer) * L));
+  }
+  if (nblocks < 4) {
+    set_error("KV pool too small (%lld blocks)", static_cast<long long>(nblocks));
+    return B200_ERR_OOM;
+  }
+  if (nblocks > (1 << 27)) nblocks = 1 << 27;
+  kv_layer_elems = static_cast<size_t>(nblocks) * 2 * Hkv * kPage * kD;
+  CK(cudaMalloc(&kv, kv_layer_elems * 2 * L));
+  pool.init(nblocks, cfg.enable_prefix_caching != 0);
+
+  // ---- step input ring
+  max_blocks_per_seq = (cfg.max_model_len + kPage - 1) / kPage;
+  step_words_cap = 3 * Tcap + Scap + 4 * Scap + 4 * (Tcap / 16 + Scap + 1) + Scap * max_blocks_per_seq + 64;
+  ring_n = std::max(2, cfg.record_steps);
+  CK(cudaMallocHost(&stage_host, static_cast<size_t>(step_words_cap) * 4));
+  stage_dev.assign(ring_n, nullptr);
+  ring_meta.assign(ring_n, StepMeta());
+  for (int i = 0; i < ring_n; ++i) CK(cudaMalloc(&stage_dev[i], static_cast<size_t>(step_words_cap) * 4));
+  CK(cudaStreamSynchronize(stream));
+  return 0;
+}
+
+int Engine::init(const b200_config& c) {
+  cfg = c;
+  L = c.num_layers; H = c.hidden; Hq = c.q_heads; Hkv = c.kv_heads; I = c.intermediate; V = c.vocab;
+  QKV = (Hq + 2 * Hkv) * kD;
+  if (L < 1 || H % 64 || Hq != 4 * Hkv || I % 64 || V < 8 || c.max_model_len < 16 || c.max_num_seqs < 1 ||
+      c.max_batched_tokens < 16) {
+    set_error("unsupported model/config (need q_heads == 4*kv_heads, hidden %% 64 == 0, intermediate %% 64 == 0)");
+    return B200_ERR_INVALID;
+  }
+  Tcap = (c.max_batched_tokens + 15) / 16 * 16;
+  Scap = c.max_num_seqs;
+  memset(&stats, 0, sizeof(stats));
+  CK(cudaSetDevice(c.device));
+  CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c.device));
+  CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+  CK(cudaEventCreate(&ev0));
+  CK(cudaEventCreate(&ev1));
+  if (int rc = alloc_all()) return rc;
+  stats.kv_blocks_total = pool.total();
+  stats.kv_blocks_free = pool.free_count();
+  if (!c.manual_step) worker = std::thread([this] { loop(); });
+  return 0;
+}
+
+// ------------------------------------------------------------------ forward pass (fixed kernel sequence)
+int Engine::forward(const StepMeta& m, int32_t* dbuf, bool all_logits, bf16* logits_out) {
+  const int T = m.T;
+  const int* ids = dbuf + m.off_ids;
+  const int* pos = dbuf + m.off_pos;
+  const int* slots = dbuf + m.off_slots;
+  const int* rows = dbuf + m.off_rows;
+  const AttnWork* dwork = reinterpret_cast<const AttnWork*>(dbuf + m.off_dwork);
+  const AttnWork* pwork = reinterpret_cast<const AttnWork*>(dbuf + m.off_pwork);
+  const int* btab = dbuf + m.off_btab;
+  const float scale = 1.0f / sqrtf(static_cast<float>(kD));
+  int rc = 0;
+  auto launched = [&](int n) { stats.kernel_launches += n; };
+  rc |= embed_gather(embed, ids, res, T, H, V, stream); launched(1);
+  for (int l = 0; l < L && !rc; ++l) {
+    Layer& ly = layers[l];
+    bf16* kv_l = kv + static_cast<size_t>(l) * kv_layer_elems;
+    if (l == 0) rc |= rmsnorm(res, nullptr, ly.norm1, normed, nullptr, T, H, cfg.rms_eps, stream);
+    else rc |= rmsnorm(x, res, ly.norm1, normed, nullptr, T, H, cfg.rms_eps, stream);
+    rc |= gemm(ly.p_qkv, xm_normed, qkv, QKV, T);
+    rc |= rope_kv_write(qkv, pos, slots, cos_sin, kv_l, T, Hq, Hkv, cfg.max_model_len, stream);
+    launched(2);
+    if (m.nd) { rc |= paged_attention(qkv, QKV, attn, Hq * kD, kv_l, btab, max_blocks_per_seq, dwork, m.nd, Hq, Hkv, scale, 1, stream); launched(1); }
+    if (m.np) { rc |= paged_attention(qkv, QKV, attn, Hq * kD, kv_l, btab, max_blocks_per_seq, pwork, m.np, Hq, Hkv, scale, 0, stream); launched(1); }
+    rc |= gemm(ly.p_o, xm_attn, x, H, T);
+    rc |= rmsnorm(x, res, ly.norm2, normed, nullptr, T, H, cfg.rms_eps, stream);
+    rc |= gemm(ly.p_gu, xm_normed, gu, 2 * I, T);
+    rc |= silu_mul(gu, act, T, I, stream);
+    rc |= gemm(ly.p_down, xm_act, x, H, T);
+    launched(2);
+  }
+  if (rc) return cuda_fail("forward", -2);
+  if (all_logits) {
+    rc |= rmsnorm(x, res, final_norm, normed, nullptr, T, H, cfg.rms_eps, stream);
+    rc |= gemm(p_lm, xm_normed, logits_out, V, T);
+    launched(1);
+  } else if (m.S > 0) {
+    rc |= rmsnorm(x, res, final_norm, last_hidden, rows, m.S, H, cfg.rms_eps, stream);
+    rc |= gemm(p_lm, xm_last, logits, V, m.S);
+    rc |= argmax_rows(logits, sampled, m.S, V, V, stream);
+    launched(2);
+  }
+  if (rc) return cuda_fail("forward(head)", -2);
+  return 0;
+}
+
+// ------------------------------------------------------------------ scheduler helpers
+bool Engine::ensure_blocks(Seq& s, int upto) {
+  const int need = (upto + kPage - 1) / kPage - static_cast<int>(s.blocks.size());
+  if (need <= 0) return true;
+  if (pool.free_count() < need) return false;
+  for (int i = 0; i < need; ++i) s.blocks.push_back(pool.alloc());
+  return true;
+}
+
+void Engine::release_blocks(Seq& s) {
+  // tail blocks go to the front of the LRU free queue order first (vLLM frees in reverse)
+  for (auto it = s.blocks.rbegin(); it != s.blocks.rend(); ++it) pool.unref(*it);
+  s.blocks.clear();
+  s.n_computed = 0;
+  s.n_published = 0;
+  s.chain_uid = 0;
+}
+
+void Engine::preempt(std::shared_ptr<Seq> s) {
+  release_blocks(*s);
+  s->admitted = false;
+  waiting.push_front(s);
+  ++stats.preemptions;
+}
+
+void Engine::finish(std::shared_ptr<Seq> s, int code) {
+  release_blocks(*s);
+  std::lock_guard<std::mutex> lk(mu_);
+  s->finished = code;
+}
+
+void Engine::admit_prefix(Seq& s) {
+  // hash-chained full-block lookup; a hit may cover at most len-1 tokens (kv_cache_manager.py:210-222)
+  const int len = static_cast<int>(s.toks.size());
+  const int nfull = (len - 1) / kPage;
+  uint64_t parent = 0;
+  int hit = 0;
+  for (int b = 0; b < nfull; ++b) {
+    int blk = pool.lookup(parent, &s.toks[static_cast<size_t>(b) * kPage]);
+    if (blk < 0) break;
+    pool.ref(blk);
+    s.blocks.push_back(blk);
+    parent = pool.uid(blk);
+    ++hit;
+  }
+  s.n_computed = hit * kPage;
+  s.n_published = hit;
+  s.chain_uid = parent;
+  if (s.n_cached < 0) {
+    s.n_cached = s.n_computed;
+    stats.cached_prompt_tokens += s.n_cached;
+    stats.prompt_tokens += s.n_prompt;
+  }
+}
+
+// ------------------------------------------------------------------ one scheduler iteration + forward
+int Engine::step(b200_step_info* info) {
+  if (info) memset(info, 0, sizeof(*info));
+  {
+    std::lock_guard<std::mutex> lk(mu_);
+    while (!incoming.empty()) {
+      waiting.push_back(incoming.front());
+      incoming.pop_front();
+    }
+  }
+  // aborted requests leave first
+  {
+    std::vector<std::shared_ptr<Seq>> keep;
+    for (auto& s : running) {
+      bool ab;
+      { std::lock_guard<std::mutex> lk(mu_); ab = s->abort_requested; }
+      if (ab) finish(s, B200_FINISH_ABORTED); else keep.push_back(s);
+    }
+    running.swap(keep);
+    std::deque<std::shared_ptr<Seq>> wkeep;
+    for (auto& s : waiting) {
+      bool ab;
+      { std::lock_guard<std::mutex> lk(mu_); ab = s->abort_requested; }
+      if (ab) finish(s, B200_FINISH_ABORTED); else wkeep.push_back(s);
+    }
+    waiting.swap(wkeep);
+  }
+
+  struct Sched { std::shared_ptr<Seq> s; int n; };
+  std::vector<Sched> sched;
+  int budget = cfg.max_batched_tokens;
+  bool preempted = false;
+  // 1. running requests first (decodes and in-progress prefills)
+  for (size_t i = 0; i < running.size() && budget > 0;) {
+    auto s = running[i];
+    int n = std::min(static_cast<int>(s->toks.size()) - s->n_computed, budget);
+    if (n <= 0) { ++i; continue; }
+    bool ok = true;
+    while (!ensure_blocks(*s, s->n_computed + n)) {
+      auto victim = running.back();
+      running.pop_back();
+      preempt(victim);
+      preempted = true;
+      if (victim == s) { ok = false; break; }
+    }
+    if (!ok) break;  // s itself was preempted; everything after it is gone too
+    sched.push_back({s, n});
+    budget -= n;
+    ++i;
+  }
+  // 2. admit waiting requests
+  while (!preempted && budget > 0 && !waiting.empty() && static_cast<int>(running.size()) < cfg.max_num_seqs) {
+    auto s = waiting.front();
+    if (!s->admitted) admit_prefix(*s);
+    int n = std::min(static_cast<int>(s->toks.size()) - s->n_computed, budget);
+    if (!ensure_blocks(*s, s->n_computed + n)) {
+      release_blocks(*s);
+      break;
+    }
+    s->admitted = true;
+    waiting.pop_front();
+    running.push_back(s);
+    sched.push_back({s, n});
+    budget -= n;
+  }
+  {
+    std::lock_guard<std::mutex> lk(mu_);
+    stats.running = static_cast<int>(running.size());
+    stats.waiting = static_cast<int>(waiting.size());
+    stats.kv_blocks_free = pool.free_count();
+  }
+  if (sched.empty()) return 0;
+
+  // ---- pack the step's device inputs
+  StepMeta m;
+  m.nseq = static_cast<int>(sched.size());
+  for (auto& sc : sched) m.T += sc.n;
+  std::vector<AttnWork> dwork, pwork;
+  std::vector<int> rows;
+  int32_t* h = stage_host;
+  m.off_ids = 0; m.off_pos = m.T; m.off_slots = 2 * m.T;
+  int tok = 0, ndec_seq = 0, npre_seq = 0;
+  for (int si = 0; si < m.nseq; ++si) {
+    Seq& s = *sched[si].s;
+    const int n = sched[si].n, p0 = s.n_computed;
+    for (int j = 0; j < n; ++j) {
+      const int p = p0 + j;
+      h[m.off_ids + tok + j] = s.toks[p];
+      h[m.off_pos + tok + j] = p;
+      h[m.off_slots + tok + j] = s.blocks[p / kPage] * kPage + (p % kPage);
+    }
+    if (n == 1) {
+      dwork.push_back({tok, 1, p0, si});
+      m.kv_tokens += p0 + 1;
+      ++ndec_seq;
+    } else {
+      for (int j = 0; j < n; j += 16) pwork.push_back({tok + j, std::min(16, n - j), p0 + j, si});
+      m.kv_tokens += static_cast<int64_t>(n) * p0 + static_cast<int64_t>(n) * (n + 1) / 2;
+      ++npre_seq;
+    }
+    if (p0 + n == static_cast<int>(s.toks.size())) rows.push_back(tok + n - 1);
+    tok += n;
+  }
+  m.nd = static_cast<int>(dwork.size());
+  m.np = static_cast<int>(pwork.size());
+  m.S = static_cast<int>(rows.size());
+  m.out_tokens = m.S;
+  int w = 3 * m.T;
+  m.off_rows = w; memcpy(h + w, rows.data(), rows.size() * 4); w += m.S;
+  w = (w + 3) & ~3;
+  m.off_dwork = w; memcpy(h + w, dwork.data(), dwork.size() * 16); w += 4 * m.nd;
+  m.off_pwork = w; memcpy(h + w, pwork.data(), pwork.size() * 16); w += 4 * m.np;
+  m.off_btab = w;
+  for (int si = 0; si < m.nseq; ++si) {
+    Seq& s = *sched[si].s;
+    memcpy(h + w + static_cast<size_t>(si) * max_blocks_per_seq, s.blocks.data(), s.blocks.size() * 4);
+  }
+  w += m.nseq * max_blocks_per_seq;
+  m.words = w;
+  if (w > step_words_cap) {
+    set_error("step staging overflow (%d > %d words)", w, step_words_cap);
+    return B200_ERR_INVALID;
+  }
+
+  const int slot = ring_pos;
+  ring_pos = (ring_pos + 1) % ring_n;
+  ring_meta[slot] = m;
+  ++recorded;
+  int32_t* dbuf = stage_dev[slot];
+  CK(cudaMemcpyAsync(dbuf, h, static_cast<size_t>(w) * 4, cudaMemcpyHostToDevice, stream));
+  CK(cudaEventRecord(ev0, stream));
+  if (int rc = forward(m, dbuf, false, nullptr)) return rc;
+  CK(cudaEventRecord(ev1, stream));
+  if (m.S) CK(cudaMemcpyAsync(sampled_host, sampled, static_cast<size_t>(m.S) * 4, cudaMemcpyDeviceToHost, stream));
+  CK(cudaStreamSynchronize(stream));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, ev0, ev1);
+
+  // ---- apply results
+  int ri = 0;
+  int64_t gen = 0;
+  std::vector<std::pair<std::shared_ptr<Seq>, int>> done;
+  for (int si = 0; si < m.nseq; ++si) {
+    auto sp = sched[si].s;
+    Seq& s = *sp;
+    const int n = sched[si].n;
+    const bool samples = (s.n_computed + n == static_cast<int>(s.toks.size()));
+    s.n_computed += n;
+    // publish newly full blocks to the prefix cache
+    while ((s.n_published + 1) * kPage <= s.n_computed) {
+      const int b = s.n_published;
+      s.chain_uid = pool.publish(s.blocks[b], s.chain_uid, &s.toks[static_cast<size_t>(b) * kPage]);
+      ++s.n_published;
+    }
+    if (!samples) continue;
+    const int32_t t = sampled_host[ri++];
+    s.toks.push_back(t);
+    ++s.n_generated;
+    ++gen;
+    int code = 0;
+    if (!s.ignore_eos && cfg.eos_token_id >= 0 && t == cfg.eos_token_id) code = B200_FINISH_STOP;
+    for (int sid : s.stop_ids) if (t == sid) code = B200_FINISH_STOP;
+    if (!code && s.n_generated >= s.max_tokens) code = B200_FINISH_LENGTH;
+    if (!code && static_cast<int>(s.toks.size()) >= cfg.max_model_len) code = B200_FINISH_LENGTH;
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      s.out.push_back(t);
+    }
+    if (code) done.push_back({sp, code});
+  }
+  for (auto& d : done) {
+    running.erase(std::find(running.begin(), running.end(), d.first));
+    finish(d.first, d.second);
+  }
+  {
+    std::lock_guard<std::mutex> lk(mu_);
+    ++stats.steps;
+    stats.generated_tokens += gen;
+    stats.last_step_device_us = ms * 1000.0;
+    stats.total_device_us += ms * 1000.0;
+    stats.last_step_tokens = m.T;
+    stats.running = static_cast<int>(running.size());
+    stats.waiting = static_cast<int>(waiting.size());
+    stats.kv_blocks_free = pool.free_count();
+  }
+  cv_out_.notify_all();
+  if (info) {
+    info->tokens = m.T;
+    info->decode_seqs = ndec_seq;
+    info->prefill_seqs = npre_seq;
+    info->sampled = m.S;
+    info->kv_tokens_read = m.kv_tokens;
+    info->device_us = ms * 1000.0;
+  }
+  return 1;
+}
+
+void Engine::loop() {
+  cudaSetDevice(cfg.device);
+  while (!stop) {
+    int rc = step(nullptr);
+    if (rc < 0) {
+      // a CUDA failure poisons this replica: fail everything in flight (the router retries elsewhere,
+      // internal/modelproxy/handler.go:127-155)
+      fprintf(stderr, "[b200engine] step failed: %s\n", b200_last_error());
+      std::vector<std::shared_ptr<Seq>> all(running.begin(), running.end());
+      all.insert(all.end(), waiting.begin(), waiting.end());
+      running.clear();
+      waiting.clear();
+      {
+        std::lock_guard<std::mutex> lk(mu_);
+        fatal = true;
+        for (auto& s : all) s->finished = B200_FINISH_ERROR;
+        for (auto& s : incoming) s->finished = B200_FINISH_ERROR;
+        incoming.clear();
+      }
+      cv_out_.notify_all();
+      return;
+    }
+    if (rc == 0) {
+      std::unique_lock<std::mutex> lk(mu_);
+      cv_work_.wait_for(lk, std::chrono::milliseconds(50), [this] { return stop.load() || !incoming.empty(); });
+    }
+  }
+}
+
+}  // namespace b200
+
+// ====================================================================== C ABI
+using namespace b200;
+
+struct b200_engine {
+  Engine impl;
+};
+
+extern "C" {
+
+void b200_config_default(b200_config* c) {
+  memset(c, 0, sizeof(*c));
+  c->device = 0;
+  c->num_layers = 32; c->hidden = 4096; c->q_heads = 32; c->kv_heads = 8; c->intermediate = 14336; c->vocab = 128256;
+  c->rms_eps = 1e-5f;
+  c->rope_theta = 500000.0f;
+  c->max_model_len = 2048;
+  c->max_num_seqs = 128;
+  c->max_batched_tokens = 2048;
+  c->num_kv_blocks = 0;
+  c->kv_fraction = 0.85f;
+  c->enable_prefix_caching = 1;
+  c->eos_token_id = -1;
+  c->seed = 0;
+  c->init_scale = 4.0f;
+  c->manual_step = 0;
+  c->record_steps = 0;
+}
+
+int b200_engine_create(const b200_config* cfg, b200_engine** out) {
+  if (!cfg || !out) { set_error("null argument"); return B200_ERR_INVALID; }
+  if (int rc = require_device()) return rc;
+  b200_engine* e = new (std::nothrow) b200_engine();
+  if (!e) { set_error("host OOM"); return B200_ERR_OOM; }
+  int rc = e->impl.init(*cfg);
+  if (rc) { delete e; return rc; }
+  *out = e;
+  return 0;
+}
+
+void b200_engine_destroy(b200_engine* e) { delete e; }
+
+int b200_submit(b200_engine* e, const int32_t* prompt_ids, int32_t n, const b200_sampling* sp, uint64_t* req_id) {
+  if (!e || !prompt_ids || n <= 0 || !req_id) { set_error("b200_submit: bad arguments"); return B200_ERR_INVALID; }
+  Engine& g = e->impl;
+  const int max_tokens = sp && sp->max_tokens > 0 ? sp->max_tokens : 16;
+  if (n + 1 > g.cfg.max_model_len) { set_error("prompt (%d tokens) exceeds max_model_len %d", n, g.cfg.max_model_len); return B200_ERR_INVALID; }
+  if (sp && sp->temperature >= 1e-5f) { set_error("only greedy sampling (temperature < 1e-5) is implemented"); return B200_ERR_INVALID; }
+  for (int i = 0; i < n; ++i) if (prompt_ids[i] < 0 || prompt_ids[i] >= g.V) { set_error("token id out of range"); return B200_ERR_INVALID; }
+  auto s = std::make_shared<Seq>();
+  s->toks.assign(prompt_ids, prompt_ids + n);
+  s->n_prompt = n;
+  s->max_tokens = max_tokens;
+  s->ignore_eos = sp && sp->ignore_eos;
+  if (sp && sp->num_stop_ids > 0 && sp->stop_ids) s->stop_ids.assign(sp->stop_ids, sp->stop_ids + sp->num_stop_ids);
+  {
+    std::lock_guard<std::mutex> lk(g.mu_);
+    if (g.fatal) { set_error("engine is in a failed state"); return B200_ERR_CUDA; }
+    s->id = g.next_id++;
+    g.requests[s->id] = s;
+    g.incoming.push_back(s);
+    *req_id = s->id;
+  }
+  g.cv_work_.notify_one();
+  return 0;
+}
+
+static std::shared_ptr<Seq> find_req(Engine& g, uint64_t id) {
+  auto it = g.requests.find(id);
+  return it == g.requests.end() ? nullptr : it->second;
+}
+
+int b200_poll(b200_engine* e, uint64_t req_id, int32_t* out_ids, int32_t cap, int32_t* n_out, int32_t* finished,
+              b200_usage* usage) {
+  if (!e || !n_out) { set_error("b200_poll: bad arguments"); return B200_ERR_INVALID; }
+  Engine& g = e->impl;
+  std::lock_guard<std::mutex> lk(g.mu_);
+  auto s = find_req(g, req_id);
+  if (!s) { set_error("unknown request %llu", static_cast<unsigned long long>(req_id)); return B200_ERR_NOT_FOUND; }
+  int n = static_cast<int>(std::min<size_t>(s->out.size() - s->drained, cap > 0 && out_ids ? cap : 0));
+  if (n > 0) memcpy(out_ids, s->out.data() + s->drained, static_cast<size_t>(n) * 4);
+  s->drained += n;
+  *n_out = n;
+  if (finished) *finished = (s->drained == s->out.size()) ? s->finished : 0;
+  if (usage) {
+    usage->prompt_tokens = s->n_prompt;
+    usage->cached_tokens = s->n_cached < 0 ? 0 : s->n_cached;
+    usage->completion_tokens = static_cast<int>(s->out.size());
+  }
+  return 0;
+}
+
+int b200_wait(b200_engine* e, uint64_t req_id, int64_t timeout_us) {
+  if (!e) { set_error("null engine"); return B200_ERR_INVALID; }
+  Engine& g = e->impl;
+  std::unique_lock<std::mutex> lk(g.mu_);
+  auto s = find_req(g, req_id);
+  if (!s) { set_error("unknown request"); return B200_ERR_NOT_FOUND; }
+  auto ready = [&] { return s->out.size() > s->drained || s->finished != 0; };
+  if (timeout_us < 0) { g.cv_out_.wait(lk, ready); return 0; }
+  if (!g.cv_out_.wait_for(lk, std::chrono::microseconds(timeout_us), ready)) { set_error("timeout"); return B200_ERR_TIMEOUT; }
+  return 0;
+}
+
+int b200_abort(b200_engine* e, uint64_t req_id) {
+  if (!e) { set_error("null engine"); return B200_ERR_INVALID; }
+  Engine& g = e->impl;
+  {
+    std::lock_guard<std::mutex> lk(g.mu_);
+    auto s = find_req(g, req_id);
+    if (!s) { set_error("unknown request"); return B200_ERR_NOT_FOUND; }
+    s->abort_requested = true;
+  }
+  g.cv_work_.notify_one();
+  return 0;
+}
+
+int b200_release(b200_engine* e, uint64_t req_id) {
+  if (!e) { set_error("null engine"); return B200_ERR_INVALID; }
+  Engine& g = e->impl;
+  std::lock_guard<std::mutex> lk(g.mu_);
+  auto it = g.requests.find(req_id);
+  if (it == g.requests.end()) { set_error("unknown request"); return B200_ERR_NOT_FOUND; }
+  if (!it->second->finished) it->second->abort_requested = true;
+  g.requests.erase(it);
+  return 0;
+}
+
+int b200_stats_get(b200_engine* e, b200_stats* out) {
+  if (!e || !out) { set_error("null argument"); return B200_ERR_INVALID; }
+  std::lock_guard<std::mutex> lk(e->impl.mu_);
+  *out = e->impl.stats;
+  return 0;
+}
+
+int b200_engine_step(b200_engine* e, b200_step_info* info) {
+  if (!e) { set_error("null engine"); return B200_ERR_INVALID; }
+  if (!e->impl.cfg.manual_step) { set_error("engine was not created with manual_step"); return B200_ERR_INVALID; }
+  cudaSetDevice(e->impl.cfg.device);
+  return e->impl.step(info);
+}
+
+int b200_engine_replay(b200_engine* e, int32_t n, int32_t repeat, double* ms_total, int64_t* tokens, int64_t* sampled,
+                       int64_t* kv_tokens_read, int64_t* launches) {
+  if (!e || n <= 0 || repeat <= 0) { set_error("b200_engine_replay: bad arguments"); return B200_ERR_INVALID; }
+  Engine& g = e->impl;
+  if (!g.cfg.manual_step) { set_error("replay needs manual_step"); return B200_ERR_INVALID; }
+  if (n > g.ring_n || n > g.recorded) { set_error("only %lld steps recorded (ring %d)", static_cast<long long>(g.recorded), g.ring_n); return B200_ERR_INVALID; }
+  cudaSetDevice(g.cfg.device);
+  int64_t tk = 0, sm = 0, kvt = 0;
+  const int64_t l0 = g.stats.kernel_launches;
+  CK(cudaEventRecord(g.ev0, g.stream));
+  for (int r = 0; r < repeat; ++r) {
+    for (int i = n; i >= 1; --i) {
+      const int slot = ((g.ring_pos - i) % g.ring_n + g.ring_n) % g.ring_n;
+      const StepMeta& m = g.ring_meta[slot];
+      if (int rc = g.forward(m, g.stage_dev[slot], false, nullptr)) return rc;
+      tk += m.T; sm += m.S; kvt += m.kv_tokens;
+    }
+  }
+  CK(cudaEventRecord(g.ev1, g.stream));
+  CK(cudaStreamSynchronize(g.stream));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, g.ev0, g.ev1);
+  if (ms_total) *ms_total = ms;
+  if (tokens) *tokens = tk;
+  if (sampled) *sampled = sm;
+  if (kv_tokens_read) *kv_tokens_read = kvt;
+  if (launches) *launches = g.stats.kernel_launches - l0;
+  return 0;
+}
+
+int b200_engine_reset_prefix_cache(b200_engine* e) {
+  if (!e) { set_error("null engine"); return B200_ERR_INVALID; }
+  if (!e->impl.cfg.manual_step) { set_error("reset needs manual_step"); return B200_ERR_INVALID; }
+  e->impl.pool.reset_cache();
+  return 0;
+}
+
+int b200_engine_tensor_info(b200_engine* e, const char* name, uint64_t* num_bytes, void** device_ptr) {
+  if (!e || !name) { set_error("null argument"); return B200_ERR_INVALID; }
+  auto it = e->impl.tensors.find(name);
+  if (it == e->impl.tensors.end()) { set_error("unknown tensor %s", name); return B200_ERR_NOT_FOUND; }
+  if (num_bytes) *num_bytes = it->second.second;
+  if (device_ptr) *device_ptr = it->second.first;
+  return 0;
+}
+
+int b200_engine_tensor_read(b200_engine* e, const char* name, void* host_dst, uint64_t cap) {
+  uint64_t nb = 0; void* p = nullptr;
+  if (int rc = b200_engine_tensor_info(e, name, &nb, &p)) return rc;
+  if (!host_dst || cap < nb) { set_error("buffer too small (%llu < %llu)", (unsigned long long)cap, (unsigned long long)nb); return B200_ERR_INVALID; }
+  cudaSetDevice(e->impl.cfg.device);
+  CK(cudaStreamSynchronize(e->impl.stream));
+  CK(cudaMemcpy(host_dst, p, nb, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int b200_engine_tensor_write(b200_engine* e, const char* name, const void* host_src, uint64_t n) {
+  uint64_t nb = 0; void* p = nullptr;
+  if (int rc = b200_engine_tensor_info(e, name, &nb, &p)) return rc;
+  if (!host_src || n != nb) { set_error("size mismatch (%llu != %llu)", (unsigned long long)n, (unsigned long long)nb); return B200_ERR_INVALID; }
+  cudaSetDevice(e->impl.cfg.device);
+  CK(cudaStreamSynchronize(e->impl.stream));
+  CK(cudaMemcpy(p, host_src, nb, cudaMemcpyHostToDevice));
+  return 0;
+}
+
+int b200_engine_forward_logits(b200_engine* e, const int32_t* ids, int32_t n, void* host_logits_bf16) {
+  if (!e || !ids || n <= 0 || !host_logits_bf16) { set_error("bad arguments"); return B200_ERR_INVALID; }
+  Engine& g = e->impl;
+  if (!g.cfg.manual_step) { set_error("forward_logits needs manual_step"); return B200_ERR_INVALID; }
+  if (n > g.Tcap || n > g.cfg.max_model_len) { set_error("too many tokens"); return B200_ERR_INVALID; }
+  cudaSetDevice(g.cfg.device);
+  Seq s;
+  s.toks.assign(ids, ids + n);
+  if (!g.ensure_blocks(s, n)) { set_error("KV pool exhausted"); return B200_ERR_OOM; }
+  StepMeta m;
+  m.T = n; m.nseq = 1;
+  int32_t* h = g.stage_host;
+  m.off_ids = 0; m.off_pos = n; m.off_slots = 2 * n;
+  for (int j = 0; j < n; ++j) {
+    h[j] = ids[j];
+    h[n + j] = j;
+    h[2 * n + j] = s.blocks[j / kPage] * kPage + j % kPage;
+  }
+  int w = (3 * n + 3) & ~3;
+  m.off_rows = w;
+  m.off_dwork = w;
+  std::vector<AttnWork> pw;
+  if (n == 1) { m.nd = 1; h[w] = 0; h[w + 1] = 1; h[w + 2] = 0; h[w + 3] = 0; w += 4; m.off_pwork = w; }
+  else {
+    m.off_pwork = w;
+    for (int j = 0; j < n; j += 16) { h[w] = j; h[w + 1] = std::min(16, n - j); h[w + 2] = j; h[w + 3] = 0; w += 4; ++m.np; }
+  }
+  m.off_btab = w;
+  memcpy(h + w, s.blocks.data(), s.blocks.size() * 4);
+  w += g.max_blocks_per_seq;
+  m.words = w;
+  bf16* dl = nullptr;
+  CK(cudaMalloc(&dl, static_cast<size_t>(n) * g.V * 2));
+  int32_t* dbuf = g.stage_dev[0];
+  cudaError_t ce = cudaMemcpyAsync(dbuf, h, static_cast<size_t>(w) * 4, cudaMemcpyHostToDevice, g.stream);
+  int rc = ce == cudaSuccess ? g.forward(m, dbuf, true, dl) : B200_ERR_CUDA;
+  if (!rc) {
+    ce = cudaMemcpyAsync(host_logits_bf16, dl, static_cast<size_t>(n) * g.V * 2, cudaMemcpyDeviceToHost, g.stream);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(g.stream);
+    if (ce != cudaSuccess) { set_error("forward_logits: %s", cudaGetErrorString(ce)); rc = B200_ERR_CUDA; }
+  }
+  cudaFree(dl);
+  for (auto it = s.blocks.rbegin(); it != s.blocks.rend(); ++it) g.pool.unref(*it);
+  return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,27 @@
+// Host-side plan for the stream-K tcgen05 projection GEMM (gemm_tcgen05.cu).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stddef.h>
+
+namespace b200 {
+
+struct GemmPlan {
+  CUtensorMap tm_w;  // weight [N, K] bf16, box 128 x 64, 128B swizzle
+  int N, K;
+  float* ws;      // fp32 partial workspace, gemm_workspace_bytes(max_ctas)
+  int* counters;  // 2 ints per output tile, zero-initialised, self-resetting
+  int max_ctas;   // persistent grid size cap (SM count)
+};
+
+int gemm_block_n_for(int T);
+size_t gemm_workspace_bytes(int max_ctas);
+// W row-major [N, K] with leading dimension ldw (elements).
+int gemm_plan_init(GemmPlan* p, const void* W, int N, int K, int ldw, float* ws, int* counters, int max_ctas);
+// Activation map over X row-major [rows, K] (rows = buffer capacity), for a given token-tile size.
+int gemm_make_x_map(CUtensorMap* tm, const void* X, int rows, int K, int ldx, int block_n);
+// out[t, n] (bf16, leading dimension ldo) for t < T.
+int gemm_run(const GemmPlan& p, const CUtensorMap& tm_x, int block_n, void* out, int ldo, int T,
+             cudaStream_t st);
+
+}  // namespace b200

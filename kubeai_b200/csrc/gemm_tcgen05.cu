@@ -1,0 +1,397 @@
+// Dense projection GEMM for the per-step hot path:
+//     out[t, n] = sum_k X[t, k] * W[n, k]        (bf16 x bf16 -> fp32 -> bf16)
+// which is what the reference backend computes for qkv_proj / o_proj /
+// gate_up_proj / down_proj / lm_head (vLLM model_executor/models/llama.py:81-121,
+// :157-233; weights stored [N, K] K-major, outputs rounded to bf16 between ops).
+//
+// B200 design (not a port of any library kernel):
+//   * "swap-AB": the 128-row weight slab is the UMMA M operand, the token tile
+//     (32..256 tokens, runtime N in multiples of 16) is the UMMA N operand, so a
+//     decode step with T=128 tokens streams every weight byte exactly once
+//     through one tcgen05.mma M=128 tile per slab, and T is padded to 16 not 128.
+//   * TMA (cp.async.bulk.tensor, 128B swizzle) feeds a multi-stage smem ring;
+//     one elected thread issues tcgen05.mma into a double-buffered TMEM
+//     accumulator; 4 epilogue warps drain TMEM with tcgen05.ld.
+//   * stream-K persistent schedule: the (tile x k-block) iteration space is cut
+//     into one contiguous range per SM, so every SM streams the same number of
+//     weight bytes whatever N/128 is (32 slabs for o_proj would otherwise light
+//     32 of 148 SMs).  Tiles that straddle CTAs are summed through an fp32 L2
+//     workspace with a reduce-scatter fix-up at the end of the kernel.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "gemm.h"
+#include "ptx.cuh"
+
+namespace b200 {
+
+namespace {
+
+constexpr int kSlab = 128;    // weight rows per tile == UMMA M
+constexpr int kBlockK = 64;   // bf16 per k-block == one 128-byte swizzle span
+constexpr int kUmmaK = 16;
+constexpr int kThreads = 192;  // warp0 TMA, warp1 MMA(+TMEM alloc), warps2-5 epilogue
+constexpr int kEpiThreads = 128;
+constexpr int kABytes = kSlab * kBlockK * 2;  // 16 KiB
+
+template <int BLOCK_N>
+struct Cfg {
+  static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStagesRaw = (200 * 1024) / kStageBytes;
+  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+  static constexpr int kTmemCols = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;  // power of two for 32..256
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+struct Seg {
+  int tile, kb0, kb1;
+};
+
+__device__ __forceinline__ long long it_begin_of(int cta, long long total, int grid) {
+  return (static_cast<long long>(cta) * total) / grid;
+}
+// CTA whose range contains iteration x: largest c with floor(c*total/grid) <= x.
+__device__ __forceinline__ int cta_of_iter(long long x, long long total, int grid) {
+  long long c = ((x + 1) * grid + total - 1) / total - 1;
+  return static_cast<int>(c);
+}
+
+__device__ __forceinline__ int ld_acquire(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_streamk_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_x,
+                    __nv_bfloat16* __restrict__ out, int ldo, float* __restrict__ ws,
+                    int* __restrict__ counters, int N, int T, int K) {
+  using C = Cfg<BLOCK_N>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + C::kStages * C::kStageBytes;
+  // barrier layout: full[kStages], empty[kStages], tmem_full[2], tmem_empty[2], tmem_ptr
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (C::kStages + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * C::kStages + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * C::kStages + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * C::kStages + 4);
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int slabs = (N + kSlab - 1) / kSlab;
+  const int ntt = (T + BLOCK_N - 1) / BLOCK_N;
+  const int KB = (K + kBlockK - 1) / kBlockK;
+  const long long total = static_cast<long long>(slabs) * ntt * KB;
+  const int grid = gridDim.x;
+  const int cta = blockIdx.x;
+  const long long it_begin = it_begin_of(cta, total, grid);
+  const long long it_end = it_begin_of(cta + 1, total, grid);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_w);
+    tma_prefetch_desc(&tm_x);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < C::kStages; ++s) {
+        mbar_init(full_bar(s), 1);
+        mbar_init(empty_bar(s), 1);
+      }
+      for (int a = 0; a < 2; ++a) {
+        mbar_init(tfull_bar(a), 1);
+        mbar_init(tempty_bar(a), 4);  // one arrive per epilogue warp
+      }
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, C::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  auto seg_at = [&](long long it) {
+    Seg s;
+    s.tile = static_cast<int>(it / KB);
+    s.kb0 = static_cast<int>(it - static_cast<long long>(s.tile) * KB);
+    long long rem = it_end - it;
+    s.kb1 = (KB - s.kb0 <= rem) ? KB : s.kb0 + static_cast<int>(rem);
+    return s;
+  };
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (long long it = it_begin; it < it_end;) {
+        Seg sg = seg_at(it);
+        const int slab = sg.tile / ntt, tt = sg.tile - slab * ntt;
+        for (int kb = sg.kb0; kb < sg.kb1; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          mbar_arrive_expect_tx(full_bar(stage), C::kStageBytes);
+          const uint32_t sa = smem_base + stage * C::kStageBytes;
+          // weights are read once per step: evict-first; activations are re-read by every slab.
+          tma_load_2d(sa, &tm_w, full_bar(stage), kb * kBlockK, slab * kSlab,
+                      ntt > 1 ? kEvictNormal : kEvictFirst);
+          tma_load_2d(sa + kABytes, &tm_x, full_bar(stage), kb * kBlockK, tt * BLOCK_N, kEvictLast);
+          if (++stage == C::kStages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        it += sg.kb1 - sg.kb0;
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (long long it = it_begin; it < it_end;) {
+        Seg sg = seg_at(it);
+        const int slab = sg.tile / ntt, tt = sg.tile - slab * ntt;
+        const int rem_t = T - tt * BLOCK_N;
+        const int n_eff = rem_t >= BLOCK_N ? BLOCK_N : ((rem_t + 15) & ~15);
+        const uint32_t idesc = umma_idesc_bf16(kSlab, n_eff);
+        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tc_fence_after();
+        for (int kb = sg.kb0; kb < sg.kb1; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * C::kStageBytes;
+          const uint64_t a_desc = umma_desc_kmajor_sw128(sa);
+          const uint64_t b_desc = umma_desc_kmajor_sw128(sa + kABytes);
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+            // +32 B per UMMA_K step inside the 128 B swizzle span (start address is in 16 B units)
+            umma_bf16(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, (kb > sg.kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(empty_bar(stage));
+          if (kb == sg.kb1 - 1) umma_commit(tfull_bar(acc));
+          if (++stage == C::kStages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+        it += sg.kb1 - sg.kb0;
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue warps
+    const int q = warp & 3;         // TMEM lane quarter this warp may read
+    const int row = q * 32 + lane;  // weight row inside the slab == TMEM lane
+    const int epi_tid = threadIdx.x - 64;
+    constexpr int kSlot = BLOCK_N * kSlab;  // fp32 elements per partial slot
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    int fix_tile[2] = {-1, -1};
+    for (long long it = it_begin; it < it_end;) {
+      Seg sg = seg_at(it);
+      const int slab = sg.tile / ntt, tt = sg.tile - slab * ntt;
+      const int t0 = tt * BLOCK_N;
+      const int rem_t = T - t0;
+      const int n_eff = rem_t >= BLOCK_N ? BLOCK_N : ((rem_t + 15) & ~15);
+      const int n = slab * kSlab + row;
+      const bool complete = (sg.kb0 == 0 && sg.kb1 == KB);
+      const int slot = (it == it_begin) ? 0 : 1;
+      float* wslot = ws + (static_cast<size_t>(cta) * 2 + slot) * kSlot;
+
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N;
+      for (int c0 = 0; c0 < n_eff; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(taddr + c0, v);
+        tmem_ld_wait();
+        if (complete) {
+          if (n < N) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int t = t0 + c0 + j;
+              if (t < T) out[static_cast<size_t>(t) * ldo + n] = __float2bfloat16_rn(__uint_as_float(v[j]));
+            }
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (c0 + j < n_eff) wslot[(c0 + j) * kSlab + row] = __uint_as_float(v[j]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (!complete) {
+        __threadfence();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (epi_tid == 0) atomicAdd(&counters[2 * sg.tile], 1);
+        fix_tile[slot] = sg.tile;
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+      it += sg.kb1 - sg.kb0;
+    }
+    // -------- fix-up: every CTA that holds a partial of tile j reduces a 1/nseg token slice of it.
+#pragma unroll
+    for (int f = 0; f < 2; ++f) {
+      const int j = fix_tile[f];
+      if (j < 0) continue;
+      const int c0 = cta_of_iter(static_cast<long long>(j) * KB, total, grid);
+      const int c1 = cta_of_iter(static_cast<long long>(j + 1) * KB - 1, total, grid);
+      const int nseg = c1 - c0 + 1;
+      const int si = cta - c0;
+      if (epi_tid == 0) {
+        while (ld_acquire(&counters[2 * j]) < nseg) __nanosleep(32);
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      __threadfence();
+      const int slab = j / ntt, tt = j - slab * ntt;
+      const int t0 = tt * BLOCK_N;
+      const int cols = (T - t0) >= BLOCK_N ? BLOCK_N : (T - t0);
+      const int cb = (si * cols) / nseg, ce = ((si + 1) * cols) / nseg;
+      const int n = slab * kSlab + row;
+      for (int col = cb; col < ce; ++col) {
+        float sum = 0.f;
+        for (int p = c0; p <= c1; ++p) {
+          const long long pb = it_begin_of(p, total, grid);
+          const int pslot = (static_cast<int>(pb / KB) == j) ? 0 : 1;
+          sum += __ldcg(ws + (static_cast<size_t>(p) * 2 + pslot) * kSlot + col * kSlab + row);
+        }
+        if (n < N) out[static_cast<size_t>(t0 + col) * ldo + n] = __float2bfloat16_rn(sum);
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (epi_tid == 0) {
+        if (atomicAdd(&counters[2 * j + 1], 1) == nseg - 1) {
+          counters[2 * j] = 0;  // self-reset for the next launch on this stream
+          counters[2 * j + 1] = 0;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::kTmemCols);
+  }
+}
+
+// ---------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !p) return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn>(p);
+  return fn;
+}
+
+// 2-D bf16 row-major [rows, cols] tensor, box = [box_rows, 64 cols], 128B swizzle.
+int make_tmap(CUtensorMap* tm, const void* base, int rows, int cols, int ld, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return -1;
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(kBlockK), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -2;
+}
+
+int g_num_sms = 0;
+int num_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+template <int BLOCK_N>
+int launch(const GemmPlan& p, const CUtensorMap& tm_x, __nv_bfloat16* out, int ldo, int T, cudaStream_t st) {
+  using C = Cfg<BLOCK_N>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_streamk_kernel<BLOCK_N>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
+    if (e != cudaSuccess) return -3;
+    attr_set = true;
+  }
+  const int slabs = (p.N + kSlab - 1) / kSlab;
+  const int ntt = (T + BLOCK_N - 1) / BLOCK_N;
+  const int KB = (p.K + kBlockK - 1) / kBlockK;
+  const long long total = static_cast<long long>(slabs) * ntt * KB;
+  long long g = total / 4;  // at least ~4 k-blocks per CTA
+  if (g < 1) g = 1;
+  int grid = static_cast<int>(g < p.max_ctas ? g : p.max_ctas);
+  gemm_streamk_kernel<BLOCK_N><<<grid, kThreads, C::kSmemBytes, st>>>(p.tm_w, tm_x, out, ldo, p.ws,
+                                                                        p.counters, p.N, T, p.K);
+  return cudaGetLastError() == cudaSuccess ? 0 : -4;
+}
+
+}  // namespace
+
+int gemm_block_n_for(int T) { return T <= 32 ? 32 : T <= 64 ? 64 : T <= 128 ? 128 : 256; }
+
+size_t gemm_workspace_bytes(int max_ctas) {
+  return static_cast<size_t>(max_ctas) * 2 * 256 * kSlab * sizeof(float);
+}
+
+int gemm_plan_init(GemmPlan* p, const void* W, int N, int K, int ldw, float* ws, int* counters, int max_ctas) {
+  memset(p, 0, sizeof(*p));
+  p->N = N;
+  p->K = K;
+  p->ws = ws;
+  p->counters = counters;
+  p->max_ctas = max_ctas > 0 ? max_ctas : num_sms();
+  if (K % 8 != 0 || ldw % 8 != 0) return -5;
+  return make_tmap(&p->tm_w, W, N, K, ldw, kSlab);
+}
+
+int gemm_make_x_map(CUtensorMap* tm, const void* X, int rows, int K, int ldx, int block_n) {
+  if (ldx % 8 != 0) return -5;
+  return make_tmap(tm, X, rows, K, ldx, block_n);
+}
+
+int gemm_run(const GemmPlan& p, const CUtensorMap& tm_x, int block_n, void* out, int ldo, int T,
+             cudaStream_t st) {
+  if (T <= 0) return 0;
+  __nv_bfloat16* o = static_cast<__nv_bfloat16*>(out);
+  switch (block_n) {
+    case 32: return launch<32>(p, tm_x, o, ldo, T, st);
+    case 64: return launch<64>(p, tm_x, o, ldo, T, st);
+    case 128: return launch<128>(p, tm_x, o, ldo, T, st);
+    case 256: return launch<256>(p, tm_x, o, ldo, T, st);
+    default: return -6;
+  }
+}
+
+}  // namespace b200

@@ -1,0 +1,38 @@
+// Host launchers for the non-GEMM kernels (elementwise.cu, attention.cu).  All pointers are device
+// pointers, all tensors bf16 unless stated; return 0 on success, negative on bad shape / launch error.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace b200 {
+
+int embed_gather(const void* table, const int* ids, void* out, int T, int H, int vocab, cudaStream_t st);
+// out[s] = rmsnorm(x[r] (+ residual[r])) * w,  r = row_index ? row_index[s] : s.
+// residual (optional) is updated in place with bf16(x + residual) unless row_index is given.
+int rmsnorm(const void* x, void* residual, const void* w, void* out, const int* row_index, int rows, int H,
+            float eps, cudaStream_t st);
+int rope_kv_write(void* qkv, const int* positions, const int* slots, const void* cos_sin, void* kv_layer,
+                  int T, int Hq, int Hkv, int max_pos, cudaStream_t st);
+int silu_mul(const void* gate_up, void* out, int T, int I, cudaStream_t st);
+int argmax_rows(const void* logits, int* out, int S, int V, int ld, cudaStream_t st);
+int init_uniform(void* p, size_t n, uint32_t seed, float scale, float offset, cudaStream_t st);
+
+// One unit of attention work: q_count query tokens of one sequence starting at row q_tok0 of the
+// step's token batch; the first of them sits at absolute position q_pos0 in the sequence.
+struct AttnWork {
+  int q_tok0;
+  int q_count;  // 1 for decode, <= 16 for a prefill tile
+  int q_pos0;
+  int seq;      // row of block_tables
+};
+
+// Paged causal attention, head_dim 128, GQA group 4 (Hq = 4 * Hkv), page = 16 tokens.
+//   q: rows of the fused qkv buffer (leading dim ldq), out: [T, Hq*128] (leading dim ldo)
+//   kv_layer: [block][2][Hkv][16][128];  block_tables: [num_seqs, max_blocks] int32
+//   decode != 0: every work item has q_count == 1 and the CTA's 4 warps split the KV range.
+int paged_attention(const void* q, int ldq, void* out, int ldo, const void* kv_layer, const int* block_tables,
+                    int max_blocks, const AttnWork* work, int num_work, int Hq, int Hkv, float scale,
+                    int decode, cudaStream_t st);
+
+}  // namespace b200
