@@ -1,0 +1,21 @@
+#!/bin/bash
+# One gpurun call: per-kernel parity first (each group under its own timeout so a hung kernel
+# cannot eat the box), then the engine tests, then optional microbenchmarks.  Logs land in gpurun_out/.
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,memory.total,clocks.max.sm --format=csv > gpurun_out/gpu.txt 2>&1
+run() { # name, timeout, args...
+  local name=$1 to=$2; shift 2
+  timeout $to python -m pytest "$@" -m gpu -q --timeout 150 -p no:cacheprovider > gpurun_out/$name.log 2>&1
+  echo "$name exit $?" | tee -a gpurun_out/summary.txt
+  tail -n 25 gpurun_out/$name.log
+}
+: > gpurun_out/summary.txt
+run gemm 400 tests/test_ops_gpu.py -k gemm
+run ops 300 tests/test_ops_gpu.py -k "not gemm and not attention"
+run attn 400 tests/test_ops_gpu.py -k attention
+run engine 600 tests/test_engine_gpu.py
+cat gpurun_out/summary.txt
+if [ -n "$MICRO" ]; then
+  timeout 900 python scripts/microbench.py $MICRO > gpurun_out/micro.log 2>&1
+  tail -n 120 gpurun_out/micro.log
+fi

@@ -1,0 +1,116 @@
+"""Per-kernel timings on the B200 (CUDA events, L2 flushed between iterations), with cuBLAS /
+FlashInfer on the same box as the bars to beat.  Not a bench.py number."""
+import json
+import math
+import sys
+import time
+
+import torch
+
+sys.path.insert(0, ".")
+from kubeai_b200 import ops  # noqa: E402
+
+PEAK = json.load(open("MEASURED_PEAKS.json"))["hbm_gbs"] if __import__("os").path.exists("MEASURED_PEAKS.json") else 6490.0
+flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
+
+
+def timeit(fn, iters=10, warm=3):
+    for _ in range(warm):
+        fn()
+    ts = []
+    for _ in range(iters):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b) * 1e3)
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+def gemm_bench():
+    print("== GEMM (stream-K tcgen05) vs cuBLAS, us median, L2 flushed")
+    shapes = [("qkv", 6144, 4096), ("o", 4096, 4096), ("gate_up", 28672, 4096), ("down", 4096, 14336),
+              ("lm_head", 128256, 4096)]
+    for T in (16, 128, 256, 512, 2048):
+        for name, N, K in shapes:
+            if name == "lm_head" and T > 256:
+                continue
+            x = torch.randn(T, K, device="cuda").bfloat16()
+            w = (torch.randn(N, K, device="cuda") / math.sqrt(K)).bfloat16()
+            t_mine = timeit(lambda: ops.gemm(x, w))
+            t_cublas = timeit(lambda: torch.nn.functional.linear(x, w))
+            byts = (N * K + T * K + T * N) * 2
+            fl = 2.0 * T * N * K
+            print(f"T={T:5d} {name:8s} mine {t_mine:8.1f} us ({byts / t_mine / 1e3:7.0f} GB/s {byts / t_mine / 1e3 / PEAK:5.2f} of HBM, "
+                  f"{fl / t_mine / 1e6:7.1f} TF/s)   cublas {t_cublas:8.1f} us ({byts / t_cublas / 1e3:7.0f} GB/s)  ratio {t_cublas / t_mine:5.2f}x")
+            del x, w
+
+
+def attn_bench():
+    print("== paged decode attention, B=128, Hq=32/Hkv=8")
+    Hq, Hkv, D = 32, 8, 128
+    for ctx in (256, 1024, 2048):
+        B = 128
+        nblk = B * ((ctx + 15) // 16)
+        kv = (torch.randn(nblk, 2, Hkv, 16, D, device="cuda")).bfloat16()
+        perm = torch.randperm(nblk, device="cuda").to(torch.int32).reshape(B, -1).contiguous()
+        qkv = torch.randn(B, (Hq + 2 * Hkv) * D, device="cuda").bfloat16()
+        work = torch.tensor([[i, 1, ctx - 1, i] for i in range(B)], dtype=torch.int32, device="cuda")
+        out = torch.zeros(B, Hq * D, dtype=torch.bfloat16, device="cuda")
+        t = timeit(lambda: ops.paged_attn(qkv, kv, perm, work, Hq, Hkv, True, out=out))
+        byts = B * ctx * 2 * Hkv * D * 2
+        print(f"ctx={ctx:5d} mine {t:8.1f} us  {byts / t / 1e3:7.0f} GB/s ({byts / t / 1e3 / PEAK:4.2f} of HBM)")
+        try:
+            import flashinfer
+            ws = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+            wr = flashinfer.BatchDecodeWithPagedKVCacheWrapper(ws, "HND", use_tensor_cores=True)
+            indptr = torch.arange(0, B + 1, dtype=torch.int32, device="cuda") * ((ctx + 15) // 16)
+            last = torch.full((B,), (ctx - 1) % 16 + 1, dtype=torch.int32, device="cuda")
+            wr.plan(indptr, perm.reshape(-1), last, Hq, Hkv, D, 16, q_data_type=torch.bfloat16, kv_data_type=torch.bfloat16)
+            q = qkv[:, :Hq * D].reshape(B, Hq, D).contiguous()
+            tf = timeit(lambda: wr.run(q, kv))
+            print(f"          flashinfer {tf:8.1f} us  {byts / tf / 1e3:7.0f} GB/s   ratio {tf / t:5.2f}x")
+            o2 = wr.run(q, kv).reshape(B, Hq * D)
+            print("          max |mine - flashinfer| =", float((out.float() - o2.float()).abs().max()))
+        except Exception as e:  # noqa: BLE001
+            print("          flashinfer unavailable:", repr(e)[:200])
+        del kv
+
+
+def engine_bench():
+    print("== Llama-3-8B engine, 128 seqs")
+    from kubeai_b200.engine import Engine, default_config
+    import numpy as np
+    t0 = time.time()
+    e = Engine(default_config(manual_step=1, record_steps=64, max_batched_tokens=2048, max_num_seqs=128,
+                              max_model_len=2048, kv_fraction=0.5))
+    print("engine create %.1fs, kv blocks %d" % (time.time() - t0, e.stats().kv_blocks_total))
+    rng = np.random.default_rng(0)
+    rids = [e.submit(rng.integers(0, 128000, size=int(rng.integers(300, 500))).tolist(), max_tokens=64) for _ in range(128)]
+    for i in range(60):
+        ran, info = e.step()
+        if i < 30 or i % 10 == 0:
+            print(f"step {i:3d} T={info.tokens:5d} dec={info.decode_seqs:4d} pre={info.prefill_seqs:3d} "
+                  f"kv_read={info.kv_tokens_read:8d} dev={info.device_us / 1e3:7.3f} ms")
+    r = e.replay(8, 3)
+    per = r["ms"] / (8 * 3)
+    byts = 15.009e9 + r["kv_tokens"] / 24 * 131072
+    print(f"replay of last 8 decode steps x3: {per:.3f} ms/step, {r['sampled'] / 24 / per * 1e3:.0f} tok/s, "
+          f"alg bytes/step {byts / 1e9:.2f} GB -> {byts / per / 1e6:.0f} GB/s ({byts / per / 1e6 / PEAK:.2f} of HBM), launches/step {r['launches'] / 24:.0f}")
+    toks = e.poll(rids[0]).tokens
+    print("first request tokens:", toks[:16])
+    e.close()
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["gemm", "attn", "engine"]
+    print("HBM peak (measured):", PEAK)
+    for w in which:
+        try:
+            globals()[w + "_bench"]()
+        except Exception as ex:  # noqa: BLE001
+            import traceback
+            traceback.print_exc()

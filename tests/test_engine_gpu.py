@@ -36,9 +36,10 @@ def test_weights_bit_exact_with_numpy_replica(eng):
         assert np.array_equal(got, w[name].reshape(-1)), name
     cs = eng.tensor("cos_sin").reshape(cfg.max_model_len, 128)
     want = f32_to_bf16_bits(cos_sin_cache(cfg))
-    # host libm cosf/sinf/powf vs numpy: allow a 1-ulp bf16 difference on a handful of entries
+    # host libm cosf/sinf/powf vs numpy differ in the last fp32 bits at large angles: a few entries
+    # land on the other side of a bf16 rounding boundary
     diff = np.abs(cs.astype(np.int32) - want.astype(np.int32))
-    assert diff.max() <= 1 and (diff > 0).mean() < 0.01, (diff.max(), (diff > 0).mean())
+    assert diff.max() <= 2 and (diff > 0).mean() < 0.002, (diff.max(), (diff > 0).mean())
 
 
 def _logit_close(got, want, what):
