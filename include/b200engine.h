@@ -152,6 +152,80 @@ int b200_router_inflight(b200_router* r, const char* name, int64_t* endpoint_inf
 /* cespare/xxhash v1.1.0 Sum64 (seed 0) as used at balance_chwbl.go:140-142 */
 uint64_t b200_xxh64(const void* data, size_t len);
 
+/* ------------------------------------------------------------------ serving shell
+ * internal/openaiserver + internal/modelproxy restated around the in-process engine: route table
+ * (openaiserver/handler.go:20-49), ServeHTTP/proxyHTTP incl. error bodies and <=max_retries re-picks
+ * (modelproxy/handler.go:57-159, request.go:45-63), ParseRequest (apiutils/request.go:64-225),
+ * Prefix (api/openai/v1/chat_completions.go:525-543), the requests-active gauge
+ * (metrics/metrics.go:16-27); plus tokenizer/chat template and vLLM-framed SSE.
+ * A Go http.Handler calls b200_server_handle with a writer that forwards to http.ResponseWriter. */
+typedef struct b200_server b200_server;
+typedef struct {
+  void* ud;
+  int (*begin)(void* ud, int status, const char* content_type); /* WriteHeader; non-zero return = client gone */
+  int (*write)(void* ud, const char* data, size_t len);         /* Write + Flush;  non-zero return = client gone */
+} b200_response_writer;
+typedef struct {
+  const char* model;           /* Model.metadata.name served by every replica */
+  const char* adapters;        /* comma-separated adapter names, or NULL */
+  int32_t strategy;            /* B200_LB_* (api/k8s/v1/model_types.go:173-209) */
+  int32_t mean_load_pct;       /* default 125 */
+  int32_t replication;         /* default 256 */
+  int32_t prefix_char_length;  /* default 100 */
+  int32_t max_retries;         /* default 3 (internal/manager/run.go:267) */
+  int32_t default_max_tokens;  /* when the request has no max_tokens */
+  int32_t vocab;               /* tokenizer range == engine vocab */
+  int32_t max_model_len;
+} b200_server_config;
+int b200_server_create(const b200_server_config* cfg, b200_engine* const* replicas, int32_t n, b200_server** out);
+void b200_server_destroy(b200_server* s);
+/* One request through the handler chain; path includes the "/openai" prefix.  Returns the HTTP status. */
+int b200_server_handle(b200_server* s, const char* method, const char* path, const char* content_type,
+                       const char* body, size_t body_len, const b200_response_writer* writer);
+/* Plain HTTP/1.1 listener in front of b200_server_handle (thread per connection, chunked SSE). port 0 = ephemeral. */
+int b200_server_listen(b200_server* s, const char* host, int32_t port, int32_t* bound_port);
+/* Prometheus text (kubeai_inference_requests_active + engine gauges); returns the full length. */
+int b200_server_metrics(b200_server* s, char* buf, size_t cap);
+/* Fault injection for the retry path: the next `count` submits on `replica` fail. */
+int b200_server_inject_fault(b200_server* s, int32_t replica, int32_t count);
+/* Synthetic tokenizer (ids 0..255 = bytes; " wxyz" spellings round-trip every id). Return the full count/length. */
+int b200_tokenize(int32_t vocab, const char* text, size_t len, int32_t* out, int32_t cap);
+int b200_detokenize(int32_t vocab, const int32_t* ids, int32_t n, char* out, size_t cap);
+
+/* ------------------------------------------------------------------ load generator
+ * benchmarks/multi-turn-chat-go restated (main.go:26-136, benchmark/runner.go:153-352), plus
+ * p50/p99 TTFT and a synthetic thread generator of the published workload's shape. */
+typedef struct {
+  const char* request_model;        /* Config.RequestModel */
+  int32_t max_concurrent_threads;   /* Config.MaxConcurrentThreads */
+  int32_t max_completion_tokens;    /* Config.MaxCompletionTokens */
+  float temperature;                /* Config.Temperature (sent explicitly; 0 = greedy) */
+  int32_t thread_count;             /* main.go:110-116 trim after the seeded shuffle; 0 = all */
+  int64_t seed;
+  double request_timeout_s;
+  int32_t synth_threads;            /* used when threads_json == NULL */
+  double synth_mean_msgs;           /* user messages per thread, clipped geometric on [5,30]; published mean 7.38 */
+  int32_t synth_mean_words;         /* tokens per user message (log-normal mean) */
+  int32_t vocab;
+} b200_harness_config;
+typedef struct {
+  int32_t input_thread_count;
+  double input_messages_per_thread_mean;
+  double duration_s;
+  int32_t request_count, failed_threads;
+  double request_duration_mean_s, chunks_per_request_mean;
+  double run_output_throughput, run_total_throughput;   /* tokens/s over the whole run incl. ramp */
+  double ttft_mean_s, itl_mean_s;                        /* runner.go:228-229 arithmetic */
+  double ttft_p50_s, ttft_p90_s, ttft_p99_s, itl_p50_s, itl_p99_s;   /* added for BASELINE.json's metric */
+  int64_t prompt_tokens, cached_prompt_tokens, completion_tokens, total_tokens;
+  char first_error[256];
+} b200_harness_result;
+void b200_harness_config_default(b200_harness_config* cfg);
+/* server != NULL: in-process transport (b200_server_handle); else HTTP/1.1 to host:port.
+ * threads_json: the reference's input format [{"id":..,"messages":[{"role","content"},..]},..] or NULL = synthetic. */
+int b200_harness_run(b200_server* server, const char* host, int32_t port, const b200_harness_config* cfg,
+                     const char* threads_json, size_t threads_len, b200_harness_result* out);
+
 /* ------------------------------------------------------------------ op-level entry points
  * Raw device pointers (bf16 unless noted) + a cudaStream_t passed as void* (NULL = default stream).
  * These are what the per-kernel parity tests and the ncu captures call. */

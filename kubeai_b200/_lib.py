@@ -51,6 +51,45 @@ class StepInfo(C.Structure):
                 ("sampled", C.c_int32), ("kv_tokens_read", C.c_int64), ("device_us", C.c_double)]
 
 
+BEGIN_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_char_p)
+WRITE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_char), C.c_size_t)
+
+
+class ResponseWriter(C.Structure):
+    _fields_ = [("ud", C.c_void_p), ("begin", BEGIN_FN), ("write", WRITE_FN)]
+
+
+class ServerConfig(C.Structure):
+    _fields_ = [("model", C.c_char_p), ("adapters", C.c_char_p), ("strategy", C.c_int32),
+                ("mean_load_pct", C.c_int32), ("replication", C.c_int32), ("prefix_char_length", C.c_int32),
+                ("max_retries", C.c_int32), ("default_max_tokens", C.c_int32), ("vocab", C.c_int32),
+                ("max_model_len", C.c_int32)]
+
+
+class HarnessConfig(C.Structure):
+    _fields_ = [("request_model", C.c_char_p), ("max_concurrent_threads", C.c_int32),
+                ("max_completion_tokens", C.c_int32), ("temperature", C.c_float), ("thread_count", C.c_int32),
+                ("seed", C.c_int64), ("request_timeout_s", C.c_double), ("synth_threads", C.c_int32),
+                ("synth_mean_msgs", C.c_double), ("synth_mean_words", C.c_int32), ("vocab", C.c_int32)]
+
+
+class HarnessResult(C.Structure):
+    _fields_ = [("input_thread_count", C.c_int32), ("input_messages_per_thread_mean", C.c_double),
+                ("duration_s", C.c_double), ("request_count", C.c_int32), ("failed_threads", C.c_int32),
+                ("request_duration_mean_s", C.c_double), ("chunks_per_request_mean", C.c_double),
+                ("run_output_throughput", C.c_double), ("run_total_throughput", C.c_double),
+                ("ttft_mean_s", C.c_double), ("itl_mean_s", C.c_double),
+                ("ttft_p50_s", C.c_double), ("ttft_p90_s", C.c_double), ("ttft_p99_s", C.c_double),
+                ("itl_p50_s", C.c_double), ("itl_p99_s", C.c_double),
+                ("prompt_tokens", C.c_int64), ("cached_prompt_tokens", C.c_int64),
+                ("completion_tokens", C.c_int64), ("total_tokens", C.c_int64), ("first_error", C.c_char * 256)]
+
+    def as_dict(self):
+        d = {k: getattr(self, k) for k, _ in self._fields_}
+        d["first_error"] = d["first_error"].decode("utf-8", "replace")
+        return d
+
+
 # every symbol include/b200engine.h declares: name -> (restype, argtypes)
 _vp, _i32, _i64, _u64, _f = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64, C.c_float
 _pi32 = C.POINTER(C.c_int32)
@@ -84,6 +123,18 @@ SYMBOLS = {
     "b200_router_add_inflight": (C.c_int, [_vp, C.c_char_p, _i64]),
     "b200_router_inflight": (C.c_int, [_vp, C.c_char_p, C.POINTER(_i64), C.POINTER(_i64)]),
     "b200_xxh64": (_u64, [_vp, C.c_size_t]),
+    "b200_server_create": (C.c_int, [C.POINTER(ServerConfig), C.POINTER(_vp), _i32, C.POINTER(_vp)]),
+    "b200_server_destroy": (None, [_vp]),
+    "b200_server_handle": (C.c_int, [_vp, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_size_t,
+                                      C.POINTER(ResponseWriter)]),
+    "b200_server_listen": (C.c_int, [_vp, C.c_char_p, _i32, _pi32]),
+    "b200_server_metrics": (C.c_int, [_vp, C.c_char_p, C.c_size_t]),
+    "b200_server_inject_fault": (C.c_int, [_vp, _i32, _i32]),
+    "b200_tokenize": (C.c_int, [_i32, C.c_char_p, C.c_size_t, _pi32, _i32]),
+    "b200_detokenize": (C.c_int, [_i32, _pi32, _i32, C.c_char_p, C.c_size_t]),
+    "b200_harness_config_default": (None, [C.POINTER(HarnessConfig)]),
+    "b200_harness_run": (C.c_int, [_vp, C.c_char_p, _i32, C.POINTER(HarnessConfig), C.c_char_p, C.c_size_t,
+                                    C.POINTER(HarnessResult)]),
     "b200_op_gemm": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp]),
     "b200_op_embed": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp]),
     "b200_op_rmsnorm": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _f, _vp]),

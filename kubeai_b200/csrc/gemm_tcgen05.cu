@@ -81,7 +81,8 @@ gemm_streamk_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
   auto empty_bar = [&](int s) { return bar_base + 8u * (C::kStages + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * C::kStages + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * C::kStages + 2 + a); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * C::kStages + 4);
+  const uint32_t fix_bar = bar_base + 8u * (2 * C::kStages + 4);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * C::kStages + 5);
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
@@ -111,6 +112,7 @@ gemm_streamk_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
         mbar_init(tfull_bar(a), 1);
         mbar_init(tempty_bar(a), 4);  // one arrive per epilogue warp
       }
+      mbar_init(fix_bar, 1);
       fence_mbar_init();
     }
     __syncwarp();
@@ -248,6 +250,11 @@ gemm_streamk_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
       it += sg.kb1 - sg.kb0;
     }
     // -------- fix-up: every CTA that holds a partial of tile j reduces a 1/nseg token slice of it.
+    // All of this CTA's MMAs have completed (the last segment's tmem_full was waited on), so the
+    // smem ring is idle: the peers' fp32 slices are pulled into it with one cp.async.bulk each
+    // (one L2 round trip for the whole slice instead of one per element) and summed from smem.
+    uint32_t fix_phase = 0;
+    const float* fix_smem = reinterpret_cast<const float*>(smem_raw + (smem_base - smem_u32(smem_raw)));
 #pragma unroll
     for (int f = 0; f < 2; ++f) {
       const int j = fix_tile[f];
@@ -256,24 +263,37 @@ gemm_streamk_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
       const int c1 = cta_of_iter(static_cast<long long>(j + 1) * KB - 1, total, grid);
       const int nseg = c1 - c0 + 1;
       const int si = cta - c0;
-      if (epi_tid == 0) {
-        while (ld_acquire(&counters[2 * j]) < nseg) __nanosleep(32);
-      }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      __threadfence();
       const int slab = j / ntt, tt = j - slab * ntt;
       const int t0 = tt * BLOCK_N;
       const int cols = (T - t0) >= BLOCK_N ? BLOCK_N : (T - t0);
       const int cb = (si * cols) / nseg, ce = ((si + 1) * cols) / nseg;
+      const int ncol = ce - cb;
       const int n = slab * kSlab + row;
-      for (int col = cb; col < ce; ++col) {
-        float sum = 0.f;
-        for (int p = c0; p <= c1; ++p) {
-          const long long pb = it_begin_of(p, total, grid);
-          const int pslot = (static_cast<int>(pb / KB) == j) ? 0 : 1;
-          sum += __ldcg(ws + (static_cast<size_t>(p) * 2 + pslot) * kSlot + col * kSlab + row);
+      if (epi_tid == 0) {
+        while (ld_acquire(&counters[2 * j]) < nseg) __nanosleep(32);
+        if (ncol > 0) {
+          // peers wrote with generic stores; the bulk copy reads through the async proxy
+          asm volatile("fence.proxy.async;" ::: "memory");
+          const uint32_t bytes = static_cast<uint32_t>(ncol) * kSlab * 4;
+          mbar_arrive_expect_tx(fix_bar, bytes * nseg);
+          for (int p = c0; p <= c1; ++p) {
+            const long long pb = it_begin_of(p, total, grid);
+            const int pslot = (static_cast<int>(pb / KB) == j) ? 0 : 1;
+            bulk_load_1d(smem_base + static_cast<uint32_t>(p - c0) * bytes,
+                         ws + (static_cast<size_t>(p) * 2 + pslot) * kSlot + static_cast<size_t>(cb) * kSlab, bytes,
+                         fix_bar);
+          }
         }
-        if (n < N) out[static_cast<size_t>(t0 + col) * ldo + n] = __float2bfloat16_rn(sum);
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (ncol > 0) {
+        mbar_wait(fix_bar, fix_phase);
+        fix_phase ^= 1u;
+        for (int col = 0; col < ncol; ++col) {
+          float sum = 0.f;
+          for (int p = 0; p < nseg; ++p) sum += fix_smem[(p * ncol + col) * kSlab + row];
+          if (n < N) out[static_cast<size_t>(t0 + cb + col) * ldo + n] = __float2bfloat16_rn(sum);
+        }
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
       if (epi_tid == 0) {

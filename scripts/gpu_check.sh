@@ -10,6 +10,8 @@ run() { # name, timeout, args...
   tail -n 25 gpurun_out/$name.log
 }
 : > gpurun_out/summary.txt
+# make sure the .so matches the sources that travelled (digest-checked; rebuilds only if stale)
+python -c "import __graft_entry__ as g; g.build()" > gpurun_out/build.log 2>&1 || { echo BUILD FAILED; tail -30 gpurun_out/build.log; exit 1; }
 run gemm 400 tests/test_ops_gpu.py -k gemm
 run ops 300 tests/test_ops_gpu.py -k "not gemm and not attention"
 run attn 400 tests/test_ops_gpu.py -k attention
