@@ -85,12 +85,13 @@ typedef struct {
   double total_device_us;     /* sum over steps */
   int64_t last_step_tokens;   /* tokens in the last forward (T) */
   int64_t kernel_launches;    /* kernels launched by this engine so far */
+  int64_t h2d_bytes, d2h_bytes; /* step inputs copied to the device / sampled ids copied back, totals */
 } b200_stats;
 
 typedef struct {
   int32_t tokens;             /* T of the step */
   int32_t decode_seqs, prefill_seqs, sampled;
-  int64_t kv_tokens_read;     /* sum of context lengths attended by this step */
+  int64_t kv_tokens_read;     /* unique K/V tokens streamed by this step: sum over sequences of their context length */
   double device_us;
 } b200_step_info;
 
@@ -115,6 +116,14 @@ int b200_engine_step(b200_engine* e, b200_step_info* info);
  * `repeat` times back to back; returns CUDA-event milliseconds and what those steps carried. */
 int b200_engine_replay(b200_engine* e, int32_t n, int32_t repeat, double* ms_total, int64_t* tokens,
                        int64_t* sampled, int64_t* kv_tokens_read, int64_t* launches);
+/* Recording on (default) = each step's device inputs go to the replay ring; off = ring is frozen. */
+int b200_engine_set_recording(b200_engine* e, int32_t on);
+/* Kernel classes of the forward pass, for per-class device timing. */
+enum { B200_K_EMBED = 0, B200_K_NORM, B200_K_GEMM_QKV, B200_K_ROPE, B200_K_ATTN_DECODE, B200_K_ATTN_PREFILL,
+       B200_K_GEMM_O, B200_K_GEMM_GU, B200_K_SILU, B200_K_GEMM_DOWN, B200_K_GEMM_LM, B200_K_ARGMAX, B200_K_NUM };
+/* Re-run the last `n` recorded steps with a CUDA-event pair around every launch (on the engine's
+ * stream) and return total microseconds and launch counts per kernel class (arrays of B200_K_NUM). */
+int b200_engine_profile(b200_engine* e, int32_t n, double* class_us, int64_t* class_launches, int32_t num_classes);
 /* Drop every cached prefix block (after a replay, which clobbers KV contents). */
 int b200_engine_reset_prefix_cache(b200_engine* e);
 
@@ -221,6 +230,8 @@ typedef struct {
   char first_error[256];
 } b200_harness_result;
 void b200_harness_config_default(b200_harness_config* cfg);
+/* JSON of the synthetic threads (same format as threads_json); returns the length needed (excl. NUL). */
+int64_t b200_harness_synth_threads(const b200_harness_config* cfg, char* buf, size_t cap);
 /* server != NULL: in-process transport (b200_server_handle); else HTTP/1.1 to host:port.
  * threads_json: the reference's input format [{"id":..,"messages":[{"role","content"},..]},..] or NULL = synthetic. */
 int b200_harness_run(b200_server* server, const char* host, int32_t port, const b200_harness_config* cfg,

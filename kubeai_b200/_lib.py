@@ -43,7 +43,8 @@ class Stats(C.Structure):
                 ("kv_blocks_total", C.c_int64), ("kv_blocks_free", C.c_int64),
                 ("prompt_tokens", C.c_int64), ("cached_prompt_tokens", C.c_int64), ("generated_tokens", C.c_int64),
                 ("preemptions", C.c_int64), ("last_step_device_us", C.c_double), ("total_device_us", C.c_double),
-                ("last_step_tokens", C.c_int64), ("kernel_launches", C.c_int64)]
+                ("last_step_tokens", C.c_int64), ("kernel_launches", C.c_int64),
+                ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64)]
 
 
 class StepInfo(C.Structure):
@@ -109,6 +110,8 @@ SYMBOLS = {
     "b200_engine_replay": (C.c_int, [_vp, _i32, _i32, C.POINTER(C.c_double), C.POINTER(_i64), C.POINTER(_i64),
                                       C.POINTER(_i64), C.POINTER(_i64)]),
     "b200_engine_reset_prefix_cache": (C.c_int, [_vp]),
+    "b200_engine_set_recording": (C.c_int, [_vp, _i32]),
+    "b200_engine_profile": (C.c_int, [_vp, _i32, C.POINTER(C.c_double), C.POINTER(_i64), _i32]),
     "b200_engine_tensor_info": (C.c_int, [_vp, C.c_char_p, C.POINTER(_u64), C.POINTER(_vp)]),
     "b200_engine_tensor_read": (C.c_int, [_vp, C.c_char_p, _vp, _u64]),
     "b200_engine_tensor_write": (C.c_int, [_vp, C.c_char_p, _vp, _u64]),
@@ -133,6 +136,7 @@ SYMBOLS = {
     "b200_tokenize": (C.c_int, [_i32, C.c_char_p, C.c_size_t, _pi32, _i32]),
     "b200_detokenize": (C.c_int, [_i32, _pi32, _i32, C.c_char_p, C.c_size_t]),
     "b200_harness_config_default": (None, [C.POINTER(HarnessConfig)]),
+    "b200_harness_synth_threads": (C.c_int64, [C.POINTER(HarnessConfig), C.c_char_p, C.c_size_t]),
     "b200_harness_run": (C.c_int, [_vp, C.c_char_p, _i32, C.POINTER(HarnessConfig), C.c_char_p, C.c_size_t,
                                     C.POINTER(HarnessResult)]),
     "b200_op_gemm": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp]),

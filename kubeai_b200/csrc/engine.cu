@@ -248,6 +248,11 @@ struct Engine {
   std::thread worker;
   b200_stats stats;
   bool fatal = false;
+  bool recording = true;        // when false, steps use the scratch ring slot and the recorded ones are kept
+  // per-kernel-class device timing (b200_engine_profile): events around every launch of a replayed step
+  bool profiling = false;
+  std::vector<std::pair<int, cudaEvent_t>> prof_events;  // (class, event) in launch order: start, stop pairs
+  size_t prof_used = 0;
 
   ~Engine();
   int init(const b200_config& c);
@@ -411,7 +416,7 @@ int Engine::alloc_all() {
   // ---- step input ring
   max_blocks_per_seq = (cfg.max_model_len + kPage - 1) / kPage;
   step_words_cap = 3 * Tcap + Scap + 4 * Scap + 4 * (Tcap / 16 + Scap + 1) + Scap * max_blocks_per_seq + 64;
-  ring_n = std::max(2, cfg.record_steps);
+  ring_n = std::max(1, cfg.record_steps) + 1;  // last slot = scratch for unrecorded steps
   CK(cudaMallocHost(&stage_host, static_cast<size_t>(step_words_cap) * 4));
   stage_dev.assign(ring_n, nullptr);
   ring_meta.assign(ring_n, StepMeta());
@@ -457,22 +462,38 @@ int Engine::forward(const StepMeta& m, int32_t* dbuf, bool all_logits, bf16* log
   const float scale = 1.0f / sqrtf(static_cast<float>(kD));
   int rc = 0;
   auto launched = [&](int n) { stats.kernel_launches += n; };
-  rc |= embed_gather(embed, ids, res, T, H, V, stream); launched(1);
+  // profiling: P(cls) before a launch group, Q() after it
+  auto P = [&](int cls) {
+    if (!profiling) return;
+    if (prof_used + 2 > prof_events.size()) {
+      for (int i = 0; i < 2; ++i) { cudaEvent_t e; cudaEventCreate(&e); prof_events.push_back({cls, e}); }
+    }
+    prof_events[prof_used].first = cls;
+    cudaEventRecord(prof_events[prof_used].second, stream);
+  };
+  auto Q = [&]() {
+    if (!profiling) return;
+    cudaEventRecord(prof_events[prof_used + 1].second, stream);
+    prof_used += 2;
+  };
+  P(B200_K_EMBED); rc |= embed_gather(embed, ids, res, T, H, V, stream); Q(); launched(1);
   for (int l = 0; l < L && !rc; ++l) {
     Layer& ly = layers[l];
     bf16* kv_l = kv + static_cast<size_t>(l) * kv_layer_elems;
+    P(B200_K_NORM);
     if (l == 0) rc |= rmsnorm(res, nullptr, ly.norm1, normed, nullptr, T, H, cfg.rms_eps, stream);
     else rc |= rmsnorm(x, res, ly.norm1, normed, nullptr, T, H, cfg.rms_eps, stream);
-    rc |= gemm(ly.p_qkv, xm_normed, qkv, QKV, T);
-    rc |= rope_kv_write(qkv, pos, slots, cos_sin, kv_l, T, Hq, Hkv, cfg.max_model_len, stream);
+    Q();
+    P(B200_K_GEMM_QKV); rc |= gemm(ly.p_qkv, xm_normed, qkv, QKV, T); Q();
+    P(B200_K_ROPE); rc |= rope_kv_write(qkv, pos, slots, cos_sin, kv_l, T, Hq, Hkv, cfg.max_model_len, stream); Q();
     launched(2);
-    if (m.nd) { rc |= paged_attention(qkv, QKV, attn, Hq * kD, kv_l, btab, max_blocks_per_seq, dwork, m.nd, Hq, Hkv, scale, 1, stream); launched(1); }
-    if (m.np) { rc |= paged_attention(qkv, QKV, attn, Hq * kD, kv_l, btab, max_blocks_per_seq, pwork, m.np, Hq, Hkv, scale, 0, stream); launched(1); }
-    rc |= gemm(ly.p_o, xm_attn, x, H, T);
-    rc |= rmsnorm(x, res, ly.norm2, normed, nullptr, T, H, cfg.rms_eps, stream);
-    rc |= gemm(ly.p_gu, xm_normed, gu, 2 * I, T);
-    rc |= silu_mul(gu, act, T, I, stream);
-    rc |= gemm(ly.p_down, xm_act, x, H, T);
+    if (m.nd) { P(B200_K_ATTN_DECODE); rc |= paged_attention(qkv, QKV, attn, Hq * kD, kv_l, btab, max_blocks_per_seq, dwork, m.nd, Hq, Hkv, scale, 1, stream); Q(); launched(1); }
+    if (m.np) { P(B200_K_ATTN_PREFILL); rc |= paged_attention(qkv, QKV, attn, Hq * kD, kv_l, btab, max_blocks_per_seq, pwork, m.np, Hq, Hkv, scale, 0, stream); Q(); launched(1); }
+    P(B200_K_GEMM_O); rc |= gemm(ly.p_o, xm_attn, x, H, T); Q();
+    P(B200_K_NORM); rc |= rmsnorm(x, res, ly.norm2, normed, nullptr, T, H, cfg.rms_eps, stream); Q();
+    P(B200_K_GEMM_GU); rc |= gemm(ly.p_gu, xm_normed, gu, 2 * I, T); Q();
+    P(B200_K_SILU); rc |= silu_mul(gu, act, T, I, stream); Q();
+    P(B200_K_GEMM_DOWN); rc |= gemm(ly.p_down, xm_act, x, H, T); Q();
     launched(2);
   }
   if (rc) return cuda_fail("forward", -2);
@@ -481,9 +502,9 @@ int Engine::forward(const StepMeta& m, int32_t* dbuf, bool all_logits, bf16* log
     rc |= gemm(p_lm, xm_normed, logits_out, V, T);
     launched(1);
   } else if (m.S > 0) {
-    rc |= rmsnorm(x, res, final_norm, last_hidden, rows, m.S, H, cfg.rms_eps, stream);
-    rc |= gemm(p_lm, xm_last, logits, V, m.S);
-    rc |= argmax_rows(logits, sampled, m.S, V, V, stream);
+    P(B200_K_NORM); rc |= rmsnorm(x, res, final_norm, last_hidden, rows, m.S, H, cfg.rms_eps, stream); Q();
+    P(B200_K_GEMM_LM); rc |= gemm(p_lm, xm_last, logits, V, m.S); Q();
+    P(B200_K_ARGMAX); rc |= argmax_rows(logits, sampled, m.S, V, V, stream); Q();
     launched(2);
   }
   if (rc) return cuda_fail("forward(head)", -2);
@@ -642,7 +663,7 @@ int Engine::step(b200_step_info* info) {
       ++ndec_seq;
     } else {
       for (int j = 0; j < n; j += 16) pwork.push_back({tok + j, std::min(16, n - j), p0 + j, si});
-      m.kv_tokens += static_cast<int64_t>(n) * p0 + static_cast<int64_t>(n) * (n + 1) / 2;
+      m.kv_tokens += p0 + n;  // unique K/V tokens this sequence streams from HBM (query tiles re-read them from L2)
       ++npre_seq;
     }
     if (p0 + n == static_cast<int>(s.toks.size())) rows.push_back(tok + n - 1);
@@ -669,10 +690,13 @@ int Engine::step(b200_step_info* info) {
     return B200_ERR_INVALID;
   }
 
-  const int slot = ring_pos;
-  ring_pos = (ring_pos + 1) % ring_n;
+  int slot = ring_n - 1;  // scratch
+  if (recording && ring_n > 1) {
+    slot = ring_pos;
+    ring_pos = (ring_pos + 1) % (ring_n - 1);
+    ++recorded;
+  }
   ring_meta[slot] = m;
-  ++recorded;
   int32_t* dbuf = stage_dev[slot];
   CK(cudaMemcpyAsync(dbuf, h, static_cast<size_t>(w) * 4, cudaMemcpyHostToDevice, stream));
   CK(cudaEventRecord(ev0, stream));
@@ -726,6 +750,8 @@ int Engine::step(b200_step_info* info) {
     stats.last_step_device_us = ms * 1000.0;
     stats.total_device_us += ms * 1000.0;
     stats.last_step_tokens = m.T;
+    stats.h2d_bytes += static_cast<int64_t>(w) * 4;
+    stats.d2h_bytes += static_cast<int64_t>(m.S) * 4;
     stats.running = static_cast<int>(running.size());
     stats.waiting = static_cast<int>(waiting.size());
     stats.kv_blocks_free = pool.free_count();
@@ -919,14 +945,15 @@ int b200_engine_replay(b200_engine* e, int32_t n, int32_t repeat, double* ms_tot
   if (!e || n <= 0 || repeat <= 0) { set_error("b200_engine_replay: bad arguments"); return B200_ERR_INVALID; }
   Engine& g = e->impl;
   if (!g.cfg.manual_step) { set_error("replay needs manual_step"); return B200_ERR_INVALID; }
-  if (n > g.ring_n || n > g.recorded) { set_error("only %lld steps recorded (ring %d)", static_cast<long long>(g.recorded), g.ring_n); return B200_ERR_INVALID; }
+  if (n > g.ring_n - 1 || n > g.recorded) { set_error("only %lld steps recorded (ring %d)", static_cast<long long>(g.recorded), g.ring_n); return B200_ERR_INVALID; }
   cudaSetDevice(g.cfg.device);
   int64_t tk = 0, sm = 0, kvt = 0;
   const int64_t l0 = g.stats.kernel_launches;
   CK(cudaEventRecord(g.ev0, g.stream));
   for (int r = 0; r < repeat; ++r) {
     for (int i = n; i >= 1; --i) {
-      const int slot = ((g.ring_pos - i) % g.ring_n + g.ring_n) % g.ring_n;
+      const int rn = g.ring_n - 1;
+      const int slot = ((g.ring_pos - i) % rn + rn) % rn;
       const StepMeta& m = g.ring_meta[slot];
       if (int rc = g.forward(m, g.stage_dev[slot], false, nullptr)) return rc;
       tk += m.T; sm += m.S; kvt += m.kv_tokens;
@@ -941,6 +968,38 @@ int b200_engine_replay(b200_engine* e, int32_t n, int32_t repeat, double* ms_tot
   if (sampled) *sampled = sm;
   if (kv_tokens_read) *kv_tokens_read = kvt;
   if (launches) *launches = g.stats.kernel_launches - l0;
+  return 0;
+}
+
+int b200_engine_set_recording(b200_engine* e, int32_t on) {
+  if (!e) { set_error("null engine"); return B200_ERR_INVALID; }
+  e->impl.recording = on != 0;
+  return 0;
+}
+
+int b200_engine_profile(b200_engine* e, int32_t n, double* class_us, int64_t* class_launches, int32_t num_classes) {
+  if (!e || n <= 0 || !class_us || !class_launches || num_classes < B200_K_NUM) { set_error("b200_engine_profile: bad arguments"); return B200_ERR_INVALID; }
+  Engine& g = e->impl;
+  if (!g.cfg.manual_step) { set_error("profile needs manual_step"); return B200_ERR_INVALID; }
+  if (n > g.ring_n - 1 || n > g.recorded) { set_error("only %lld steps recorded", static_cast<long long>(g.recorded)); return B200_ERR_INVALID; }
+  cudaSetDevice(g.cfg.device);
+  for (int i = 0; i < num_classes; ++i) { class_us[i] = 0; class_launches[i] = 0; }
+  const int rn = g.ring_n - 1;
+  for (int i = n; i >= 1; --i) {
+    const int slot = ((g.ring_pos - i) % rn + rn) % rn;
+    g.profiling = true;
+    g.prof_used = 0;
+    int rc = g.forward(g.ring_meta[slot], g.stage_dev[slot], false, nullptr);
+    g.profiling = false;
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(g.stream));
+    for (size_t k = 0; k + 1 < g.prof_used; k += 2) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, g.prof_events[k].second, g.prof_events[k + 1].second);
+      class_us[g.prof_events[k].first] += ms * 1000.0;
+      class_launches[g.prof_events[k].first] += 1;
+    }
+  }
   return 0;
 }
 

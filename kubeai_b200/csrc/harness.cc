@@ -342,6 +342,26 @@ void b200_harness_config_default(b200_harness_config* c) {
   c->vocab = 128256;
 }
 
+/* The synthetic thread list as JSON in the reference's input format (for sharding across ranks). */
+int64_t b200_harness_synth_threads(const b200_harness_config* cfg, char* buf, size_t cap) {
+  if (!cfg) { set_error("null config"); return B200_ERR_INVALID; }
+  std::vector<HThread> threads;
+  synth_threads(*cfg, &threads);
+  std::string o = "[";
+  for (size_t i = 0; i < threads.size(); ++i) {
+    if (i) o += ',';
+    o += "{\"id\":\"t" + std::to_string(i) + "\",\"messages\":[";
+    for (size_t k = 0; k < threads[i].input.size(); ++k) {
+      if (k) o += ',';
+      o += "{\"role\":" + json_str(threads[i].input[k].role) + ",\"content\":" + json_str(threads[i].input[k].content) + "}";
+    }
+    o += "]}";
+  }
+  o += "]";
+  if (buf && cap > o.size()) memcpy(buf, o.c_str(), o.size() + 1);
+  return static_cast<int64_t>(o.size());
+}
+
 int b200_harness_run(b200_server* server, const char* host, int32_t port, const b200_harness_config* cfg,
                      const char* threads_json, size_t threads_len, b200_harness_result* out) {
   if (!cfg || !out || (!server && (!host || port <= 0))) { set_error("b200_harness_run: bad arguments"); return B200_ERR_INVALID; }

@@ -109,6 +109,19 @@ class Engine:
                                          C.byref(ln)))
         return dict(ms=ms.value, tokens=tok.value, sampled=smp.value, kv_tokens=kvt.value, launches=ln.value)
 
+    KERNEL_CLASSES = ["embed", "rmsnorm", "gemm_qkv", "rope_kvwrite", "attn_decode", "attn_prefill", "gemm_o",
+                      "gemm_gate_up", "silu_mul", "gemm_down", "gemm_lm_head", "argmax"]
+
+    def set_recording(self, on: bool):
+        check(self._l.b200_engine_set_recording(self._h, 1 if on else 0))
+
+    def profile(self, n: int) -> dict:
+        """Per-kernel-class device time (us) and launch counts over the last n recorded steps."""
+        k = len(self.KERNEL_CLASSES)
+        us, ln = (C.c_double * k)(), (C.c_int64 * k)()
+        check(self._l.b200_engine_profile(self._h, n, us, ln, k))
+        return {name: dict(us=us[i], launches=ln[i]) for i, name in enumerate(self.KERNEL_CLASSES)}
+
     def reset_prefix_cache(self):
         check(self._l.b200_engine_reset_prefix_cache(self._h))
 

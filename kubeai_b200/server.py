@@ -110,6 +110,13 @@ def harness_config(**kw) -> HarnessConfig:
     return cfg
 
 
+def synth_threads(cfg: HarnessConfig) -> list:
+    n = lib().b200_harness_synth_threads(C.byref(cfg), None, 0)
+    buf = C.create_string_buffer(n + 1)
+    lib().b200_harness_synth_threads(C.byref(cfg), buf, n + 1)
+    return json.loads(buf.value)
+
+
 def harness_run(cfg: HarnessConfig, server: Server | None = None, host: str | None = None, port: int = 0,
                 threads=None) -> dict:
     res = HarnessResult()

@@ -16,8 +16,13 @@ run gemm 400 tests/test_ops_gpu.py -k gemm
 run ops 300 tests/test_ops_gpu.py -k "not gemm and not attention"
 run attn 400 tests/test_ops_gpu.py -k attention
 run engine 600 tests/test_engine_gpu.py
+run server 400 tests/test_server_gpu.py
 cat gpurun_out/summary.txt
 if [ -n "$MICRO" ]; then
   timeout 900 python scripts/microbench.py $MICRO > gpurun_out/micro.log 2>&1
   tail -n 120 gpurun_out/micro.log
+fi
+if [ -n "$BENCH" ]; then
+  timeout 1200 python bench.py $BENCH > gpurun_out/bench.log 2> gpurun_out/bench.err
+  echo "bench exit $?"; tail -c 6000 gpurun_out/bench.log; tail -n 15 gpurun_out/bench.err
 fi
