@@ -240,6 +240,9 @@ int b200_harness_run(b200_server* server, const char* host, int32_t port, const 
 /* ------------------------------------------------------------------ op-level entry points
  * Raw device pointers (bf16 unless noted) + a cudaStream_t passed as void* (NULL = default stream).
  * These are what the per-kernel parity tests and the ncu captures call. */
+/* GEMM kernel variant for plans/engines created afterwards: 2 = CTA-pair tcgen05 cta_group::2 (default),
+ * 1 = single-CTA kernel (kept for A/B measurements).  Returns the active variant. */
+int b200_set_gemm_variant(int32_t v);
 int b200_op_gemm(const void* w, const void* x, void* out, int32_t N, int32_t T, int32_t K, void* stream);
 int b200_op_embed(const void* table, const int32_t* ids, void* out, int32_t T, int32_t H, int32_t vocab, void* stream);
 int b200_op_rmsnorm(const void* x, void* residual, const void* w, void* out, const int32_t* row_index, int32_t rows,

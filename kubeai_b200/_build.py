@@ -19,6 +19,7 @@ OBJ = ROOT / "lib" / "obj"
 
 SOURCES = [
     "gemm_tcgen05.cu",
+    "gemm2_tcgen05.cu",
     "attention.cu",
     "elementwise.cu",
     "abi_ops.cu",

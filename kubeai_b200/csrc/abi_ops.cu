@@ -95,6 +95,11 @@ int b200_op_gemm(const void* w, const void* x, void* out, int32_t N, int32_t T, 
   return 0;
 }
 
+int b200_set_gemm_variant(int32_t v) {
+  gemm_set_variant(v);
+  return gemm_variant();
+}
+
 int b200_op_embed(const void* table, const int32_t* ids, void* out, int32_t T, int32_t H, int32_t vocab,
                   void* stream) {
   if (int rc = require_device()) return rc;

@@ -19,6 +19,7 @@
 #include <stdint.h>
 
 #include "kernels.h"
+#include "launch.h"
 #include "ptx.cuh"
 
 namespace b200 {
@@ -40,6 +41,8 @@ paged_attn_kernel(const __nv_bfloat16* __restrict__ q, int ldq, __nv_bfloat16* _
   constexpr int NT = WT / 8;
   extern __shared__ __align__(128) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
+  griddep_wait();
+  griddep_launch();
 
   const AttnWork wk = work[blockIdx.x];
   const int kvh = blockIdx.y;
@@ -271,11 +274,11 @@ int paged_attention(const void* q, int ldq, void* out, int ldo, const void* kv_l
   __nv_bfloat16* oo = static_cast<__nv_bfloat16*>(out);
   const __nv_bfloat16* kk = static_cast<const __nv_bfloat16*>(kv_layer);
   if (decode)
-    paged_attn_kernel<true><<<grid, 128, kAttnSmem, st>>>(qq, ldq, oo, ldo, kk, block_tables, max_blocks, work,
-                                                          Hkv, scale_log2);
+    launch_pdl(paged_attn_kernel<true>, grid, dim3(128), kAttnSmem, st, qq, ldq, oo, ldo, kk, block_tables,
+               max_blocks, work, Hkv, scale_log2);
   else
-    paged_attn_kernel<false><<<grid, 128, kAttnSmem, st>>>(qq, ldq, oo, ldo, kk, block_tables, max_blocks, work,
-                                                           Hkv, scale_log2);
+    launch_pdl(paged_attn_kernel<false>, grid, dim3(128), kAttnSmem, st, qq, ldq, oo, ldo, kk, block_tables,
+               max_blocks, work, Hkv, scale_log2);
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 

@@ -10,6 +10,8 @@
 #include <stdint.h>
 
 #include "kernels.h"
+#include "launch.h"
+#include "ptx.cuh"
 
 namespace b200 {
 
@@ -29,6 +31,8 @@ __device__ __forceinline__ float warp_sum(float v) {
 // ------------------------------------------------------------------ embedding gather
 __global__ void embed_kernel(const __nv_bfloat16* __restrict__ table, const int* __restrict__ ids,
                              __nv_bfloat16* __restrict__ out, int H, int vocab) {
+  griddep_wait();
+  griddep_launch();
   const int t = blockIdx.x;
   int id = ids[t];
   if (id < 0 || id >= vocab) id = 0;
@@ -44,6 +48,8 @@ template <int VPT>  // uint4 vectors per thread (H = VPT * 8 * blockDim)
 __global__ void rmsnorm_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ residual,
                                const __nv_bfloat16* __restrict__ w, __nv_bfloat16* __restrict__ out,
                                const int* __restrict__ row_index, int H, float eps) {
+  griddep_wait();
+  griddep_launch();
   const int s = blockIdx.x;
   const int r = row_index ? row_index[s] : s;
   const uint4* xin = reinterpret_cast<const uint4*>(x + static_cast<size_t>(r) * H);
@@ -107,6 +113,8 @@ __global__ void rmsnorm_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat1
 __global__ void rope_kv_kernel(__nv_bfloat16* __restrict__ qkv, const int* __restrict__ positions,
                                const int* __restrict__ slots, const __nv_bfloat16* __restrict__ cos_sin,
                                __nv_bfloat16* __restrict__ kv, int Hq, int Hkv, int max_pos) {
+  griddep_wait();
+  griddep_launch();
   constexpr int D = 128, HALF = 64;
   const int t = blockIdx.x;
   int pos = positions[t];
@@ -164,6 +172,8 @@ __global__ void rope_kv_kernel(__nv_bfloat16* __restrict__ qkv, const int* __res
 // ------------------------------------------------------------------ SiLU(gate) * up
 __global__ void silu_mul_kernel(const __nv_bfloat16* __restrict__ gu, __nv_bfloat16* __restrict__ out, int I,
                                 int ldi) {
+  griddep_wait();
+  griddep_launch();
   const int t = blockIdx.y;
   const uint4* g = reinterpret_cast<const uint4*>(gu + static_cast<size_t>(t) * ldi);
   const uint4* u = reinterpret_cast<const uint4*>(gu + static_cast<size_t>(t) * ldi + I);
@@ -184,6 +194,8 @@ __global__ void silu_mul_kernel(const __nv_bfloat16* __restrict__ gu, __nv_bfloa
 
 // ------------------------------------------------------------------ greedy argmax over bf16 logits
 __global__ void argmax_kernel(const __nv_bfloat16* __restrict__ logits, int* __restrict__ out, int V, int ld) {
+  griddep_wait();
+  griddep_launch();
   const int s = blockIdx.x;
   const __nv_bfloat16* row = logits + static_cast<size_t>(s) * ld;
   float best = -INFINITY;
@@ -270,8 +282,8 @@ __global__ void init_uniform_kernel(__nv_bfloat16* __restrict__ p, size_t n, uin
 int embed_gather(const void* table, const int* ids, void* out, int T, int H, int vocab, cudaStream_t st) {
   if (T <= 0) return 0;
   if (H % 8) return -1;
-  embed_kernel<<<T, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(table), ids,
-                                  static_cast<__nv_bfloat16*>(out), H, vocab);
+  launch_pdl(embed_kernel, dim3(T), dim3(256), 0, st, static_cast<const __nv_bfloat16*>(table), ids,
+             static_cast<__nv_bfloat16*>(out), H, vocab);
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 
@@ -287,13 +299,13 @@ int rmsnorm(const void* x, void* residual, const void* w, void* out, const int* 
   // pick threads so that every thread owns exactly VPT vectors
   if (vecs % 256 == 0 && vecs / 256 <= 4) {
     switch (vecs / 256) {
-      case 1: rmsnorm_kernel<1><<<rows, 256, 0, st>>>(xx, rr, ww, oo, row_index, H, eps); break;
-      case 2: rmsnorm_kernel<2><<<rows, 256, 0, st>>>(xx, rr, ww, oo, row_index, H, eps); break;
-      case 3: rmsnorm_kernel<3><<<rows, 256, 0, st>>>(xx, rr, ww, oo, row_index, H, eps); break;
-      default: rmsnorm_kernel<4><<<rows, 256, 0, st>>>(xx, rr, ww, oo, row_index, H, eps); break;
+      case 1: launch_pdl(rmsnorm_kernel<1>, dim3(rows), dim3(256), 0, st, xx, rr, ww, oo, row_index, H, eps); break;
+      case 2: launch_pdl(rmsnorm_kernel<2>, dim3(rows), dim3(256), 0, st, xx, rr, ww, oo, row_index, H, eps); break;
+      case 3: launch_pdl(rmsnorm_kernel<3>, dim3(rows), dim3(256), 0, st, xx, rr, ww, oo, row_index, H, eps); break;
+      default: launch_pdl(rmsnorm_kernel<4>, dim3(rows), dim3(256), 0, st, xx, rr, ww, oo, row_index, H, eps); break;
     }
   } else if (vecs % 32 == 0 && vecs <= 1024) {
-    rmsnorm_kernel<1><<<rows, vecs, 0, st>>>(xx, rr, ww, oo, row_index, H, eps);
+    launch_pdl(rmsnorm_kernel<1>, dim3(rows), dim3(vecs), 0, st, xx, rr, ww, oo, row_index, H, eps);
   } else {
     return -1;
   }
@@ -303,9 +315,8 @@ int rmsnorm(const void* x, void* residual, const void* w, void* out, const int* 
 int rope_kv_write(void* qkv, const int* positions, const int* slots, const void* cos_sin, void* kv_layer,
                   int T, int Hq, int Hkv, int max_pos, cudaStream_t st) {
   if (T <= 0) return 0;
-  rope_kv_kernel<<<T, 128, 0, st>>>(static_cast<__nv_bfloat16*>(qkv), positions, slots,
-                                    static_cast<const __nv_bfloat16*>(cos_sin),
-                                    static_cast<__nv_bfloat16*>(kv_layer), Hq, Hkv, max_pos);
+  launch_pdl(rope_kv_kernel, dim3(T), dim3(128), 0, st, static_cast<__nv_bfloat16*>(qkv), positions, slots,
+             static_cast<const __nv_bfloat16*>(cos_sin), static_cast<__nv_bfloat16*>(kv_layer), Hq, Hkv, max_pos);
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 
@@ -313,15 +324,15 @@ int silu_mul(const void* gate_up, void* out, int T, int I, cudaStream_t st) {
   if (T <= 0) return 0;
   if (I % 8) return -1;
   dim3 grid((I / 8 + 255) / 256, T);
-  silu_mul_kernel<<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(gate_up),
-                                        static_cast<__nv_bfloat16*>(out), I, 2 * I);
+  launch_pdl(silu_mul_kernel, grid, dim3(256), 0, st, static_cast<const __nv_bfloat16*>(gate_up),
+             static_cast<__nv_bfloat16*>(out), I, 2 * I);
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 
 int argmax_rows(const void* logits, int* out, int S, int V, int ld, cudaStream_t st) {
   if (S <= 0) return 0;
   if (ld % 8) return -1;
-  argmax_kernel<<<S, 1024, 0, st>>>(static_cast<const __nv_bfloat16*>(logits), out, V, ld);
+  launch_pdl(argmax_kernel, dim3(S), dim3(1024), 0, st, static_cast<const __nv_bfloat16*>(logits), out, V, ld);
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 

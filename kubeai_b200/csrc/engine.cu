@@ -186,7 +186,7 @@ struct StepMeta {
 };
 
 struct XMaps {
-  CUtensorMap m[4];  // block_n 32, 64, 128, 256
+  CUtensorMap m[kGemmNumBlockN];  // token tiles 32, 64, 128, 256, 512
 };
 
 }  // namespace
@@ -265,7 +265,7 @@ struct Engine {
   void preempt(std::shared_ptr<Seq> s);
   void finish(std::shared_ptr<Seq> s, int code);
   void admit_prefix(Seq& s);
-  const CUtensorMap& xmap(const XMaps& xm, int bn) const { return xm.m[bn == 32 ? 0 : bn == 64 ? 1 : bn == 128 ? 2 : 3]; }
+  const CUtensorMap& xmap(const XMaps& xm, int bn) const { return xm.m[gemm_block_n_index(bn)]; }
   int gemm(const GemmPlan& p, const XMaps& xm, void* out, int ldo, int T) {
     const int bn = gemm_block_n_for(T);
     ++stats.kernel_launches;
@@ -386,8 +386,8 @@ int Engine::alloc_all() {
       return cuda_fail("gemm_plan_init", -2);
   }
   if (plan(&p_lm, lm_head, V, H)) return cuda_fail("gemm_plan_init(lm_head)", -2);
-  const int bns[4] = {32, 64, 128, 256};
-  for (int i = 0; i < 4; ++i) {
+  const int bns[kGemmNumBlockN] = {32, 64, 128, 256, 512};
+  for (int i = 0; i < kGemmNumBlockN; ++i) {
     if (gemm_make_x_map(&xm_normed.m[i], normed, Tcap, H, H, bns[i]) ||
         gemm_make_x_map(&xm_attn.m[i], attn, Tcap, Hq * kD, Hq * kD, bns[i]) ||
         gemm_make_x_map(&xm_act.m[i], act, Tcap, I, I, bns[i]) ||

@@ -14,12 +14,22 @@ struct GemmPlan {
   int max_ctas;   // persistent grid size cap (SM count)
 };
 
-int gemm_block_n_for(int T);
+// variant 2 (default): CTA-pair kernel (gemm2_tcgen05.cu); variant 1: single-CTA kernel (gemm_tcgen05.cu)
+void gemm_set_variant(int v);
+int gemm_variant();
+constexpr int kGemmNumBlockN = 5;         // token-tile sizes 32, 64, 128, 256, 512 (512: variant 2 only)
+int gemm_block_n_for(int T);              // token-tile size the active variant uses for T tokens
+int gemm_block_n_index(int block_n);      // 0..4
+int gemm_x_box_rows(int block_n);         // rows of the activation TMA box for that tile size
 size_t gemm_workspace_bytes(int max_ctas);
 // W row-major [N, K] with leading dimension ldw (elements).
 int gemm_plan_init(GemmPlan* p, const void* W, int N, int K, int ldw, float* ws, int* counters, int max_ctas);
 // Activation map over X row-major [rows, K] (rows = buffer capacity), for a given token-tile size.
 int gemm_make_x_map(CUtensorMap* tm, const void* X, int rows, int K, int ldx, int block_n);
+// variant-2 internals (gemm2_tcgen05.cu)
+int gemm2_block_n_for(int T);
+int gemm2_x_box_rows(int block_n);
+int gemm2_run(const GemmPlan& p, const CUtensorMap& tm_x, int block_n, void* out, int ldo, int T, cudaStream_t st);
 // out[t, n] (bf16, leading dimension ldo) for t < T.
 int gemm_run(const GemmPlan& p, const CUtensorMap& tm_x, int block_n, void* out, int ldo, int T,
              cudaStream_t st);

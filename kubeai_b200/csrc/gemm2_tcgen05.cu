@@ -1,0 +1,488 @@
+// Projection GEMM, CTA-pair version (tcgen05 cta_group::2) — the default for every step.
+//     out[t, n] = sum_k X[t, k] * W[n, k]        (bf16 x bf16 -> fp32 -> bf16)
+// Same contract and stream-K schedule as gemm_tcgen05.cu (see there for the reference citations);
+// what changes is the unit of work, because the single-CTA kernel measured L2-bound, not HBM-bound:
+// every 128-row weight slab re-read the whole activation tile from L2 (1 byte of X per byte of W at
+// T=128, 2:1 and W twice at T=384) and the L2 output port (~11 TB/s measured) saturated first.
+//   * Two SMs (a cluster of 2) issue ONE tcgen05.mma.cta_group::2 with M=256: each CTA stages its own
+//     128 weight rows and only HALF of the token tile; the tensor core reads both halves across the
+//     pair.  Activation traffic per weight byte is halved and per-CTA smem per stage shrinks.
+//   * The token tile is up to 512 wide (two N<=256 instructions per k-step into two TMEM regions), so
+//     a mixed decode+prefill step of <=512 tokens still streams every weight byte exactly once.
+//   * stream-K over CTA pairs (74 ranges); the split-tile fix-up, the fp32 L2 workspace, the
+//     cp.async.bulk pull, PDL with early weight prefetch are as in the single-CTA kernel, per CTA.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string.h>
+
+#include "gemm.h"
+#include "launch.h"
+#include "ptx.cuh"
+
+namespace b200 {
+
+namespace {
+
+constexpr int kSlab = 128;   // weight rows per CTA (UMMA M = 256 per pair)
+constexpr int kBlockK = 64;
+constexpr int kUmmaK = 16;
+constexpr int kThreads = 192;
+constexpr int kABytes = kSlab * kBlockK * 2;
+constexpr uint32_t kPeerMask = 0xFEFFFFFFu;  // clears the CTA-rank bit of a shared::cluster address -> rank 0's copy
+
+template <int BLOCK_N>
+struct Cfg2 {
+  static constexpr int kChunk = BLOCK_N > 256 ? 256 : BLOCK_N;  // tokens per MMA instruction
+  static constexpr int kNch = BLOCK_N / kChunk;                 // instructions per k-step (1 or 2)
+  static constexpr int kHalf = kChunk / 2;                      // token rows of one chunk staged by one CTA
+  static constexpr int kBBytes = kNch * kHalf * kBlockK * 2;    // B bytes per CTA per stage
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStagesRaw = (200 * 1024) / kStageBytes;
+  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+  static constexpr int kAccStages = (2 * BLOCK_N <= 512) ? 2 : 1;
+  static constexpr int kTmemCols = kAccStages * BLOCK_N < 32 ? 32 : kAccStages * BLOCK_N;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+};
+
+struct Seg {
+  int tile, kb0, kb1;
+};
+
+__device__ __forceinline__ long long range_begin(int unit, long long total, int units) {
+  return (static_cast<long long>(unit) * total) / units;
+}
+__device__ __forceinline__ int unit_of_iter(long long x, long long total, int units) {
+  return static_cast<int>(((x + 1) * units + total - 1) / total - 1);
+}
+__device__ __forceinline__ int ld_acquire(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// 2-D TMA load into OWN smem, completion bytes credited to the LEADER CTA's mbarrier.
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst_smem, const void* tmap, uint32_t bar, int32_t c0,
+                                                 int32_t c1, uint64_t hint) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar & kPeerMask), "r"(c0), "r"(c1), "l"(hint)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish2() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem, 256 x N over the pair] (+)= A[256 x 16] * B[N x 16]; issued by the leader CTA only.
+__device__ __forceinline__ void umma2_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0u)
+      : "memory");
+}
+// Completion of all prior MMAs of this thread arrives on the same-offset mbarrier of BOTH CTAs.
+__device__ __forceinline__ void umma2_commit_both(uint32_t bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(bar), "h"(static_cast<uint16_t>(3))
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t cta) {
+  asm volatile(
+      "{\n"
+      ".reg .b32 ra;\n"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n"
+      "}\n" ::"r"(bar),
+      "r"(cta)
+      : "memory");
+}
+
+template <int BLOCK_N>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+gemm2_streamk_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_x,
+                     __nv_bfloat16* __restrict__ out, int ldo, float* __restrict__ ws, int* __restrict__ counters,
+                     int N, int T, int K) {
+  using C = Cfg2<BLOCK_N>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + C::kStages * C::kStageBytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };                       // leader's copy is the live one
+  auto empty_bar = [&](int s) { return bar_base + 8u * (C::kStages + s); };       // both CTAs (multicast commit)
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * C::kStages + a); };   // both CTAs (multicast commit)
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * C::kStages + 2 + a); };  // leader's copy, 8 arrivals
+  const uint32_t fix_bar = bar_base + 8u * (2 * C::kStages + 4);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * C::kStages + 5);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+
+  const int pairs_n = (N + 2 * kSlab - 1) / (2 * kSlab);  // 256-row tiles
+  const int ntt = (T + BLOCK_N - 1) / BLOCK_N;
+  const int KB = (K + kBlockK - 1) / kBlockK;
+  const long long total = static_cast<long long>(pairs_n) * ntt * KB;
+  const int units = gridDim.x >> 1;
+  const int unit = blockIdx.x >> 1;
+  const int cta = blockIdx.x;
+  const long long it_begin = range_begin(unit, total, units);
+  const long long it_end = range_begin(unit + 1, total, units);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_w);
+    tma_prefetch_desc(&tm_x);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < C::kStages; ++s) {
+        mbar_init(full_bar(s), 1);
+        mbar_init(empty_bar(s), 1);
+      }
+      for (int a = 0; a < 2; ++a) {
+        mbar_init(tfull_bar(a), 1);
+        mbar_init(tempty_bar(a), 8);  // 4 epilogue warps of each CTA
+      }
+      mbar_init(fix_bar, 1);
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc2(tmem_slot, C::kTmemCols);
+    tmem_relinquish2();
+  }
+  tc_fence_before();
+  cluster_sync();  // barrier inits + TMEM allocation visible to the peer CTA
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+  griddep_launch();
+
+  auto seg_at = [&](long long it) {
+    Seg s;
+    s.tile = static_cast<int>(it / KB);
+    s.kb0 = static_cast<int>(it - static_cast<long long>(s.tile) * KB);
+    long long rem = it_end - it;
+    s.kb1 = (KB - s.kb0 <= rem) ? KB : s.kb0 + static_cast<int>(rem);
+    return s;
+  };
+  // token layout of a tile: chunk c covers tokens [t0 + c*256, ...), nc_c = its (16-padded) width
+  auto chunk_n = [&](int tt, int c) {
+    const int rem = T - tt * BLOCK_N - c * C::kChunk;
+    return rem <= 0 ? 0 : (rem >= C::kChunk ? C::kChunk : ((rem + 15) & ~15));
+  };
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer (both CTAs)
+    if (lane == 0) {
+      const uint64_t w_hint = ntt > 1 ? kEvictNormal : kEvictFirst;
+      int pre = 0;
+      for (long long it = it_begin; it < it_end && pre < C::kStages; ++it, ++pre) {
+        const int tile = static_cast<int>(it / KB), kb = static_cast<int>(it - static_cast<long long>(tile) * KB);
+        if (leader) mbar_arrive_expect_tx(full_bar(pre), 2u * C::kStageBytes);
+        tma_load_2d_pair(smem_base + pre * C::kStageBytes, &tm_w, full_bar(pre), kb * kBlockK,
+                         (tile / ntt) * 2 * kSlab + static_cast<int>(rank) * kSlab, w_hint);
+      }
+      griddep_wait();
+      int stage = 0, idx = 0;
+      uint32_t phase = 0;
+      for (long long it = it_begin; it < it_end; ++it, ++idx) {
+        const int tile = static_cast<int>(it / KB), kb = static_cast<int>(it - static_cast<long long>(tile) * KB);
+        const int slab2 = tile / ntt, tt = tile - slab2 * ntt;
+        const uint32_t sa = smem_base + stage * C::kStageBytes;
+        if (idx >= pre) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          if (leader) mbar_arrive_expect_tx(full_bar(stage), 2u * C::kStageBytes);
+          tma_load_2d_pair(sa, &tm_w, full_bar(stage), kb * kBlockK, slab2 * 2 * kSlab + static_cast<int>(rank) * kSlab, w_hint);
+        }
+#pragma unroll
+        for (int c = 0; c < C::kNch; ++c) {
+          // this CTA stages the rank-th half of chunk c (the box is always kHalf rows; rows past nc/2 are ignored)
+          const int nc = chunk_n(tt, c);
+          const int row0 = tt * BLOCK_N + c * C::kChunk + static_cast<int>(rank) * (nc >> 1);
+          tma_load_2d_pair(sa + kABytes + c * (C::kHalf * kBlockK * 2), &tm_x, full_bar(stage), kb * kBlockK,
+                           nc > 0 ? row0 : T /* fully out of range -> zero fill */, kEvictLast);
+        }
+        if (++stage == C::kStages) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer (leader CTA only)
+    if (lane == 0 && leader) {
+      griddep_wait();
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (long long it = it_begin; it < it_end;) {
+        Seg sg = seg_at(it);
+        const int slab2 = sg.tile / ntt, tt = sg.tile - slab2 * ntt;
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tc_fence_after();
+        for (int kb = sg.kb0; kb < sg.kb1; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * C::kStageBytes;
+          const uint64_t a_desc = umma_desc_kmajor_sw128(sa);
+#pragma unroll
+          for (int c = 0; c < C::kNch; ++c) {
+            const int nc = chunk_n(tt, c);
+            if (nc == 0) continue;
+            const uint32_t idesc = umma_idesc_bf16(2 * kSlab, nc);
+            const uint32_t d_tmem = tmem_base + acc * BLOCK_N + c * C::kChunk;
+            const uint64_t b_desc = umma_desc_kmajor_sw128(sa + kABytes + c * (C::kHalf * kBlockK * 2));
+#pragma unroll
+            for (int k = 0; k < kBlockK / kUmmaK; ++k)
+              umma2_bf16(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, (kb > sg.kb0 || k > 0) ? 1u : 0u);
+          }
+          umma2_commit_both(empty_bar(stage));
+          if (kb == sg.kb1 - 1) umma2_commit_both(tfull_bar(acc));
+          if (++stage == C::kStages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        if (++acc == C::kAccStages) {
+          acc = 0;
+          acc_phase ^= 1u;
+        }
+        it += sg.kb1 - sg.kb0;
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue warps (both CTAs, own 128 rows)
+    griddep_wait();
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int epi_tid = threadIdx.x - 64;
+    constexpr int kSlot = BLOCK_N * kSlab;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    int fix_tile[2] = {-1, -1};
+    for (long long it = it_begin; it < it_end;) {
+      Seg sg = seg_at(it);
+      const int slab2 = sg.tile / ntt, tt = sg.tile - slab2 * ntt;
+      const int t0 = tt * BLOCK_N;
+      int n_eff = 0;
+#pragma unroll
+      for (int c = 0; c < C::kNch; ++c) n_eff += chunk_n(tt, c);
+      const int n = (slab2 * 2 + static_cast<int>(rank)) * kSlab + row;
+      const bool complete = (sg.kb0 == 0 && sg.kb1 == KB);
+      const int slot = (it == it_begin) ? 0 : 1;
+      float* wslot = ws + (static_cast<size_t>(cta) * 2 + slot) * kSlot;
+
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N;
+      for (int c0 = 0; c0 < n_eff; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(taddr + c0, v);
+        tmem_ld_wait();
+        if (complete) {
+          if (n < N) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int t = t0 + c0 + j;
+              if (t < T) out[static_cast<size_t>(t) * ldo + n] = __float2bfloat16_rn(__uint_as_float(v[j]));
+            }
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (c0 + j < n_eff) wslot[(c0 + j) * kSlab + row] = __uint_as_float(v[j]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (leader) mbar_arrive(tempty_bar(acc));
+        else mbar_arrive_remote(tempty_bar(acc), 0);
+      }
+      if (!complete) {
+        __threadfence();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (epi_tid == 0) atomicAdd(&counters[2 * (sg.tile * 2 + static_cast<int>(rank))], 1);
+        fix_tile[slot] = sg.tile;
+      }
+      if (++acc == C::kAccStages) {
+        acc = 0;
+        acc_phase ^= 1u;
+      }
+      it += sg.kb1 - sg.kb0;
+    }
+
+    // -------- fix-up (per CTA, same-rank CTAs of the other pairs are the peers)
+    struct Fix {
+      int j, u0, nseg, cb, ncol, t0, n, cid;
+    };
+    Fix fx[2];
+    int nfix = 0;
+    uint32_t total_bytes = 0;
+#pragma unroll
+    for (int f = 0; f < 2; ++f) {
+      const int j = fix_tile[f];
+      if (j < 0) continue;
+      Fix& x = fx[nfix];
+      x.j = j;
+      x.cid = j * 2 + static_cast<int>(rank);
+      x.u0 = unit_of_iter(static_cast<long long>(j) * KB, total, units);
+      const int u1 = unit_of_iter(static_cast<long long>(j + 1) * KB - 1, total, units);
+      x.nseg = u1 - x.u0 + 1;
+      const int si = unit - x.u0;
+      const int slab2 = j / ntt, tt = j - slab2 * ntt;
+      x.t0 = tt * BLOCK_N;
+      const int cols = (T - x.t0) >= BLOCK_N ? BLOCK_N : (T - x.t0);
+      x.cb = (si * cols) / x.nseg;
+      x.ncol = ((si + 1) * cols) / x.nseg - x.cb;
+      x.n = (slab2 * 2 + static_cast<int>(rank)) * kSlab + row;
+      total_bytes += static_cast<uint32_t>(x.nseg) * x.ncol * kSlab * 4;
+      ++nfix;
+    }
+    constexpr uint32_t kRing = C::kStages * C::kStageBytes;
+    const float* fix_smem = reinterpret_cast<const float*>(smem_raw + (smem_base - smem_u32(smem_raw)));
+    uint32_t fix_phase = 0;
+    auto src_of = [&](const Fix& x, int p, int col) {
+      const long long pbeg = range_begin(x.u0 + p, total, units);
+      const int pslot = (static_cast<int>(pbeg / KB) == x.j) ? 0 : 1;
+      const int pcta = (x.u0 + p) * 2 + static_cast<int>(rank);
+      return ws + (static_cast<size_t>(pcta) * 2 + pslot) * kSlot + static_cast<size_t>(col) * kSlab;
+    };
+    auto finish = [&](const Fix& x) {
+      if (atomicAdd(&counters[2 * x.cid + 1], 1) == x.nseg - 1) {
+        counters[2 * x.cid] = 0;
+        counters[2 * x.cid + 1] = 0;
+      }
+    };
+    if (nfix > 0 && total_bytes <= kRing) {
+      // fast path (decode shapes): both split tiles in ONE L2 round trip
+      uint32_t off[2] = {0, 0};
+      if (nfix == 2) off[1] = static_cast<uint32_t>(fx[0].nseg) * fx[0].ncol * kSlab * 4;
+      if (epi_tid == 0) {
+        for (int f = 0; f < nfix; ++f)
+          while (ld_acquire(&counters[2 * fx[f].cid]) < fx[f].nseg) __nanosleep(20);
+        if (total_bytes) {
+          asm volatile("fence.proxy.async;" ::: "memory");
+          mbar_arrive_expect_tx(fix_bar, total_bytes);
+          for (int f = 0; f < nfix; ++f) {
+            const uint32_t pb = static_cast<uint32_t>(fx[f].ncol) * kSlab * 4;
+            if (pb == 0) continue;
+            for (int p = 0; p < fx[f].nseg; ++p)
+              bulk_load_1d(smem_base + off[f] + static_cast<uint32_t>(p) * pb, src_of(fx[f], p, fx[f].cb), pb, fix_bar);
+          }
+        }
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (total_bytes) mbar_wait(fix_bar, fix_phase);
+      for (int f = 0; f < nfix; ++f) {
+        const Fix& x = fx[f];
+        const float* base = fix_smem + off[f] / 4;
+        for (int col = 0; col < x.ncol; ++col) {
+          float sum = 0.f;
+          for (int p = 0; p < x.nseg; ++p) sum += base[(p * x.ncol + col) * kSlab + row];
+          if (x.n < N) out[static_cast<size_t>(x.t0 + x.cb + col) * ldo + x.n] = __float2bfloat16_rn(sum);
+        }
+      }
+      if (epi_tid == 0)
+        for (int f = 0; f < nfix; ++f) finish(fx[f]);
+    } else {
+      // general path: one tile at a time, the column slice in pieces that fit the ring
+      for (int f = 0; f < nfix; ++f) {
+        const Fix& x = fx[f];
+        if (epi_tid == 0)
+          while (ld_acquire(&counters[2 * x.cid]) < x.nseg) __nanosleep(20);
+        const int cstep = static_cast<int>(kRing / (static_cast<uint32_t>(x.nseg) * kSlab * 4));
+        for (int c0 = 0; c0 < x.ncol; c0 += cstep) {
+          const int nc = (x.ncol - c0) < cstep ? (x.ncol - c0) : cstep;
+          const uint32_t pb = static_cast<uint32_t>(nc) * kSlab * 4;
+          if (epi_tid == 0) {
+            asm volatile("fence.proxy.async;" ::: "memory");
+            mbar_arrive_expect_tx(fix_bar, pb * x.nseg);
+            for (int p = 0; p < x.nseg; ++p)
+              bulk_load_1d(smem_base + static_cast<uint32_t>(p) * pb, src_of(x, p, x.cb + c0), pb, fix_bar);
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          mbar_wait(fix_bar, fix_phase);
+          fix_phase ^= 1u;
+          for (int col = 0; col < nc; ++col) {
+            float sum = 0.f;
+            for (int p = 0; p < x.nseg; ++p) sum += fix_smem[(p * nc + col) * kSlab + row];
+            if (x.n < N) out[static_cast<size_t>(x.t0 + x.cb + c0 + col) * ldo + x.n] = __float2bfloat16_rn(sum);
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
+        if (x.ncol == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (epi_tid == 0) finish(x);
+      }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync();  // neither CTA may exit (or free TMEM) while the peer can still signal its barriers / read its smem
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc2(tmem_base, C::kTmemCols);
+  }
+}
+
+template <int BLOCK_N>
+int launch2(const GemmPlan& p, const CUtensorMap& tm_x, __nv_bfloat16* out, int ldo, int T, cudaStream_t st) {
+  using C = Cfg2<BLOCK_N>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(gemm2_streamk_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes) !=
+        cudaSuccess)
+      return -3;
+    attr_set = true;
+  }
+  const int pairs_n = (p.N + 2 * kSlab - 1) / (2 * kSlab);
+  const int ntt = (T + BLOCK_N - 1) / BLOCK_N;
+  const int KB = (p.K + kBlockK - 1) / kBlockK;
+  const long long total = static_cast<long long>(pairs_n) * ntt * KB;
+  long long u = total / 4;
+  if (u < 1) u = 1;
+  const int max_units = p.max_ctas / 2;
+  const int units = static_cast<int>(u < max_units ? u : max_units);
+  cudaError_t e = launch_pdl(gemm2_streamk_kernel<BLOCK_N>, dim3(2 * units), dim3(kThreads), C::kSmemBytes, st, p.tm_w, tm_x,
+                             out, ldo, p.ws, p.counters, p.N, T, p.K);
+  return e == cudaSuccess ? 0 : -4;
+}
+
+}  // namespace
+
+int gemm2_block_n_for(int T) { return T <= 32 ? 32 : T <= 64 ? 64 : T <= 128 ? 128 : T <= 256 ? 256 : 512; }
+int gemm2_x_box_rows(int block_n) { return (block_n > 256 ? 256 : block_n) / 2; }
+
+int gemm2_run(const GemmPlan& p, const CUtensorMap& tm_x, int block_n, void* out, int ldo, int T, cudaStream_t st) {
+  if (T <= 0) return 0;
+  __nv_bfloat16* o = static_cast<__nv_bfloat16*>(out);
+  switch (block_n) {
+    case 32: return launch2<32>(p, tm_x, o, ldo, T, st);
+    case 64: return launch2<64>(p, tm_x, o, ldo, T, st);
+    case 128: return launch2<128>(p, tm_x, o, ldo, T, st);
+    case 256: return launch2<256>(p, tm_x, o, ldo, T, st);
+    case 512: return launch2<512>(p, tm_x, o, ldo, T, st);
+    default: return -6;
+  }
+}
+
+}  // namespace b200

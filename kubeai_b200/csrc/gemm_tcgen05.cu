@@ -25,6 +25,7 @@
 #include <string.h>
 
 #include "gemm.h"
+#include "launch.h"
 #include "ptx.cuh"
 
 namespace b200 {
@@ -123,6 +124,7 @@ gemm_streamk_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  griddep_launch();  // the next kernel may start its own prologue; it waits for our completion before reading `out`
 
   auto seg_at = [&](long long it) {
     Seg s;
@@ -136,30 +138,40 @@ gemm_streamk_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      int stage = 0;
+      const uint64_t w_hint = ntt > 1 ? kEvictNormal : kEvictFirst;  // weights are read once per step
+      // Weights do not depend on the previous kernel: fill the ring's weight halves BEFORE the
+      // programmatic-dependency wait, so launch latency, prologue and the DRAM ramp of this GEMM
+      // overlap the tail of the previous kernel.  The activation halves follow after the wait.
+      int pre = 0;
+      for (long long it = it_begin; it < it_end && pre < C::kStages; ++it, ++pre) {
+        const int tile = static_cast<int>(it / KB), kb = static_cast<int>(it - static_cast<long long>(tile) * KB);
+        mbar_arrive_expect_tx(full_bar(pre), C::kStageBytes);
+        tma_load_2d(smem_base + pre * C::kStageBytes, &tm_w, full_bar(pre), kb * kBlockK, (tile / ntt) * kSlab, w_hint);
+      }
+      griddep_wait();
+      int stage = 0, idx = 0;
       uint32_t phase = 0;
-      for (long long it = it_begin; it < it_end;) {
-        Seg sg = seg_at(it);
-        const int slab = sg.tile / ntt, tt = sg.tile - slab * ntt;
-        for (int kb = sg.kb0; kb < sg.kb1; ++kb) {
+      for (long long it = it_begin; it < it_end; ++it, ++idx) {
+        const int tile = static_cast<int>(it / KB), kb = static_cast<int>(it - static_cast<long long>(tile) * KB);
+        const int slab = tile / ntt, tt = tile - slab * ntt;
+        const uint32_t sa = smem_base + stage * C::kStageBytes;
+        if (idx >= pre) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           mbar_arrive_expect_tx(full_bar(stage), C::kStageBytes);
-          const uint32_t sa = smem_base + stage * C::kStageBytes;
-          // weights are read once per step: evict-first; activations are re-read by every slab.
-          tma_load_2d(sa, &tm_w, full_bar(stage), kb * kBlockK, slab * kSlab,
-                      ntt > 1 ? kEvictNormal : kEvictFirst);
-          tma_load_2d(sa + kABytes, &tm_x, full_bar(stage), kb * kBlockK, tt * BLOCK_N, kEvictLast);
-          if (++stage == C::kStages) {
-            stage = 0;
-            phase ^= 1u;
-          }
+          tma_load_2d(sa, &tm_w, full_bar(stage), kb * kBlockK, slab * kSlab, w_hint);
         }
-        it += sg.kb1 - sg.kb0;
+        // activations are re-read by every slab: keep them in L2
+        tma_load_2d(sa + kABytes, &tm_x, full_bar(stage), kb * kBlockK, tt * BLOCK_N, kEvictLast);
+        if (++stage == C::kStages) {
+          stage = 0;
+          phase ^= 1u;
+        }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
     if (lane == 0) {
+      griddep_wait();
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
       for (long long it = it_begin; it < it_end;) {
@@ -196,6 +208,7 @@ gemm_streamk_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
     }
   } else {
     // ------------------------------------------------------------ epilogue warps
+    griddep_wait();                 // before the first write to out / workspace / counters
     const int q = warp & 3;         // TMEM lane quarter this warp may read
     const int row = q * 32 + lane;  // weight row inside the slab == TMEM lane
     const int epi_tid = threadIdx.x - 64;
@@ -253,53 +266,95 @@ gemm_streamk_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
     // All of this CTA's MMAs have completed (the last segment's tmem_full was waited on), so the
     // smem ring is idle: the peers' fp32 slices are pulled into it with one cp.async.bulk each
     // (one L2 round trip for the whole slice instead of one per element) and summed from smem.
-    uint32_t fix_phase = 0;
-    const float* fix_smem = reinterpret_cast<const float*>(smem_raw + (smem_base - smem_u32(smem_raw)));
+    // Both of a CTA's split tiles (head of its range, tail of its range) share ONE round trip
+    // when their slices fit the ring together.
+    struct Fix {
+      int j, c0, nseg, cb, ncol, t0, n;
+      uint32_t bytes, off;
+    };
+    Fix fx[2];
+    int nfix = 0;
+    uint32_t total_bytes = 0;
 #pragma unroll
     for (int f = 0; f < 2; ++f) {
       const int j = fix_tile[f];
       if (j < 0) continue;
-      const int c0 = cta_of_iter(static_cast<long long>(j) * KB, total, grid);
+      Fix& x = fx[nfix];
+      x.j = j;
+      x.c0 = cta_of_iter(static_cast<long long>(j) * KB, total, grid);
       const int c1 = cta_of_iter(static_cast<long long>(j + 1) * KB - 1, total, grid);
-      const int nseg = c1 - c0 + 1;
-      const int si = cta - c0;
+      x.nseg = c1 - x.c0 + 1;
+      const int si = cta - x.c0;
       const int slab = j / ntt, tt = j - slab * ntt;
-      const int t0 = tt * BLOCK_N;
-      const int cols = (T - t0) >= BLOCK_N ? BLOCK_N : (T - t0);
-      const int cb = (si * cols) / nseg, ce = ((si + 1) * cols) / nseg;
-      const int ncol = ce - cb;
-      const int n = slab * kSlab + row;
-      if (epi_tid == 0) {
-        while (ld_acquire(&counters[2 * j]) < nseg) __nanosleep(32);
-        if (ncol > 0) {
-          // peers wrote with generic stores; the bulk copy reads through the async proxy
-          asm volatile("fence.proxy.async;" ::: "memory");
-          const uint32_t bytes = static_cast<uint32_t>(ncol) * kSlab * 4;
-          mbar_arrive_expect_tx(fix_bar, bytes * nseg);
-          for (int p = c0; p <= c1; ++p) {
-            const long long pb = it_begin_of(p, total, grid);
-            const int pslot = (static_cast<int>(pb / KB) == j) ? 0 : 1;
-            bulk_load_1d(smem_base + static_cast<uint32_t>(p - c0) * bytes,
-                         ws + (static_cast<size_t>(p) * 2 + pslot) * kSlot + static_cast<size_t>(cb) * kSlab, bytes,
-                         fix_bar);
+      x.t0 = tt * BLOCK_N;
+      const int cols = (T - x.t0) >= BLOCK_N ? BLOCK_N : (T - x.t0);
+      x.cb = (si * cols) / x.nseg;
+      x.ncol = ((si + 1) * cols) / x.nseg - x.cb;
+      x.n = slab * kSlab + row;
+      x.bytes = static_cast<uint32_t>(x.nseg) * x.ncol * kSlab * 4;
+      x.off = total_bytes;
+      total_bytes += x.bytes;
+      ++nfix;
+    }
+    const bool merged = total_bytes <= static_cast<uint32_t>(C::kStages * C::kStageBytes);
+    uint32_t fix_phase = 0;
+    const float* fix_smem = reinterpret_cast<const float*>(smem_raw + (smem_base - smem_u32(smem_raw)));
+    auto pull = [&](int f0, int f1) {  // one thread: wait for the peers' partials, start the bulk copies
+      uint32_t tot = 0;
+      for (int f = f0; f < f1; ++f) {
+        while (ld_acquire(&counters[2 * fx[f].j]) < fx[f].nseg) __nanosleep(20);
+        tot += fx[f].bytes;
+      }
+      if (tot == 0) return;
+      asm volatile("fence.proxy.async;" ::: "memory");  // peers wrote with generic stores; bulk copy reads via the async proxy
+      mbar_arrive_expect_tx(fix_bar, tot);
+      for (int f = f0; f < f1; ++f) {
+        const Fix& x = fx[f];
+        if (x.ncol == 0) continue;
+        const uint32_t pb_bytes = static_cast<uint32_t>(x.ncol) * kSlab * 4;
+        for (int p = 0; p < x.nseg; ++p) {
+          const long long pbeg = it_begin_of(x.c0 + p, total, grid);
+          const int pslot = (static_cast<int>(pbeg / KB) == x.j) ? 0 : 1;
+          bulk_load_1d(smem_base + (merged ? x.off : 0u) + static_cast<uint32_t>(p) * pb_bytes,
+                       ws + (static_cast<size_t>(x.c0 + p) * 2 + pslot) * kSlot + static_cast<size_t>(x.cb) * kSlab,
+                       pb_bytes, fix_bar);
+        }
+      }
+    };
+    auto reduce = [&](int f) {
+      const Fix& x = fx[f];
+      const float* base = fix_smem + (merged ? x.off : 0u) / 4;
+      for (int col = 0; col < x.ncol; ++col) {
+        float sum = 0.f;
+        for (int p = 0; p < x.nseg; ++p) sum += base[(p * x.ncol + col) * kSlab + row];
+        if (x.n < N) out[static_cast<size_t>(x.t0 + x.cb + col) * ldo + x.n] = __float2bfloat16_rn(sum);
+      }
+    };
+    auto finish = [&](int f) {  // one thread: last reducer of a tile resets its counters for the next launch
+      if (atomicAdd(&counters[2 * fx[f].j + 1], 1) == fx[f].nseg - 1) {
+        counters[2 * fx[f].j] = 0;
+        counters[2 * fx[f].j + 1] = 0;
+      }
+    };
+    if (nfix > 0) {
+      if (merged) {
+        if (epi_tid == 0) pull(0, nfix);
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (total_bytes > 0) mbar_wait(fix_bar, fix_phase);
+        for (int f = 0; f < nfix; ++f) reduce(f);
+        if (epi_tid == 0)
+          for (int f = 0; f < nfix; ++f) finish(f);
+      } else {
+        for (int f = 0; f < nfix; ++f) {
+          if (epi_tid == 0) pull(f, f + 1);
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (fx[f].bytes > 0) {
+            mbar_wait(fix_bar, fix_phase);
+            fix_phase ^= 1u;
           }
-        }
-      }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (ncol > 0) {
-        mbar_wait(fix_bar, fix_phase);
-        fix_phase ^= 1u;
-        for (int col = 0; col < ncol; ++col) {
-          float sum = 0.f;
-          for (int p = 0; p < nseg; ++p) sum += fix_smem[(p * ncol + col) * kSlab + row];
-          if (n < N) out[static_cast<size_t>(t0 + cb + col) * ldo + n] = __float2bfloat16_rn(sum);
-        }
-      }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (epi_tid == 0) {
-        if (atomicAdd(&counters[2 * j + 1], 1) == nseg - 1) {
-          counters[2 * j] = 0;  // self-reset for the next launch on this stream
-          counters[2 * j + 1] = 0;
+          reduce(f);
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (epi_tid == 0) finish(f);
         }
       }
     }
@@ -372,17 +427,26 @@ int launch(const GemmPlan& p, const CUtensorMap& tm_x, __nv_bfloat16* out, int l
   long long g = total / 4;  // at least ~4 k-blocks per CTA
   if (g < 1) g = 1;
   int grid = static_cast<int>(g < p.max_ctas ? g : p.max_ctas);
-  gemm_streamk_kernel<BLOCK_N><<<grid, kThreads, C::kSmemBytes, st>>>(p.tm_w, tm_x, out, ldo, p.ws,
-                                                                        p.counters, p.N, T, p.K);
-  return cudaGetLastError() == cudaSuccess ? 0 : -4;
+  cudaError_t e = launch_pdl(gemm_streamk_kernel<BLOCK_N>, dim3(grid), dim3(kThreads), C::kSmemBytes, st, p.tm_w, tm_x,
+                             out, ldo, p.ws, p.counters, p.N, T, p.K);
+  return e == cudaSuccess ? 0 : -4;
 }
 
 }  // namespace
 
-int gemm_block_n_for(int T) { return T <= 32 ? 32 : T <= 64 ? 64 : T <= 128 ? 128 : 256; }
+static int g_variant = 2;
+void gemm_set_variant(int v) { g_variant = (v == 1) ? 1 : 2; }
+int gemm_variant() { return g_variant; }
+
+int gemm_block_n_for(int T) {
+  if (g_variant == 2) return gemm2_block_n_for(T);
+  return T <= 32 ? 32 : T <= 64 ? 64 : T <= 128 ? 128 : 256;
+}
+int gemm_block_n_index(int bn) { return bn == 32 ? 0 : bn == 64 ? 1 : bn == 128 ? 2 : bn == 256 ? 3 : 4; }
+int gemm_x_box_rows(int bn) { return g_variant == 2 ? gemm2_x_box_rows(bn) : (bn > 256 ? 256 : bn); }
 
 size_t gemm_workspace_bytes(int max_ctas) {
-  return static_cast<size_t>(max_ctas) * 2 * 256 * kSlab * sizeof(float);
+  return static_cast<size_t>(max_ctas) * 2 * 512 * kSlab * sizeof(float);
 }
 
 int gemm_plan_init(GemmPlan* p, const void* W, int N, int K, int ldw, float* ws, int* counters, int max_ctas) {
@@ -398,12 +462,13 @@ int gemm_plan_init(GemmPlan* p, const void* W, int N, int K, int ldw, float* ws,
 
 int gemm_make_x_map(CUtensorMap* tm, const void* X, int rows, int K, int ldx, int block_n) {
   if (ldx % 8 != 0) return -5;
-  return make_tmap(tm, X, rows, K, ldx, block_n);
+  return make_tmap(tm, X, rows, K, ldx, gemm_x_box_rows(block_n));
 }
 
 int gemm_run(const GemmPlan& p, const CUtensorMap& tm_x, int block_n, void* out, int ldo, int T,
              cudaStream_t st) {
   if (T <= 0) return 0;
+  if (g_variant == 2) return gemm2_run(p, tm_x, block_n, out, ldo, T, st);
   __nv_bfloat16* o = static_cast<__nv_bfloat16*>(out);
   switch (block_n) {
     case 32: return launch<32>(p, tm_x, o, ldo, T, st);

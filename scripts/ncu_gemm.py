@@ -1,0 +1,12 @@
+"""One GEMM shape, a few launches — the target of `ncu --set full` (run under gpurun)."""
+import math, sys, torch
+sys.path.insert(0, ".")
+from kubeai_b200 import ops
+T, N, K = (int(a) for a in sys.argv[1:4])
+x = torch.randn(T, K, device="cuda").bfloat16()
+w = (torch.randn(N, K, device="cuda") / math.sqrt(K)).bfloat16()
+flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+for _ in range(4):
+    flush.zero_()
+    ops.gemm(x, w)
+torch.cuda.synchronize()

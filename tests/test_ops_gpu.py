@@ -32,6 +32,15 @@ def rnd(*shape, scale=1.0, seed=0):
     return O.r(torch.randn(*shape, generator=g) * scale)
 
 
+@pytest.fixture(params=[2, 1], ids=["pair", "single"])
+def gemm_variant(request):
+    """2 = CTA-pair kernel (default product path), 1 = single-CTA kernel kept for A/B measurements."""
+    from kubeai_b200 import lib
+    lib().b200_set_gemm_variant(request.param)
+    yield request.param
+    lib().b200_set_gemm_variant(2)
+
+
 @pytest.mark.parametrize("T,N,K", [
     (128, 256, 256),      # single k-range, multiple slabs
     (16, 128, 64),        # one tile, one k-block
@@ -44,8 +53,12 @@ def rnd(*shape, scale=1.0, seed=0):
     (700, 640, 384),      # three token tiles
     (64, 4096, 14336),    # down_proj shape (deep K)
     (33, 130, 72),
+    (384, 1024, 512),     # 512-token tile: 256 + 128 (two MMA chunks per k-step in the pair kernel)
+    (400, 28672, 4096),   # gate_up at a mixed decode+prefill step
+    (512, 768, 1024),
+    (1100, 512, 256),     # three 512-token tiles (512 + 512 + 76)
 ])
-def test_gemm_matches_oracle(T, N, K):
+def test_gemm_matches_oracle(T, N, K, gemm_variant):
     from kubeai_b200 import ops
     x, w = rnd(T, K, seed=1), rnd(N, K, scale=1 / math.sqrt(K), seed=2)
     got = ops.gemm(dev(x), dev(w))
@@ -55,7 +68,7 @@ def test_gemm_matches_oracle(T, N, K):
     close(got, want, atol=2e-3, rtol=RTOL, what=f"gemm {T}x{N}x{K}")
 
 
-def test_gemm_repeatable_and_counters_reset():
+def test_gemm_repeatable_and_counters_reset(gemm_variant):
     from kubeai_b200 import ops
     x, w = dev(rnd(128, 4096, seed=3)), dev(rnd(4096, 4096, scale=1 / 64, seed=4))
     a = ops.gemm(x, w)
