@@ -243,6 +243,13 @@ int b200_harness_run(b200_server* server, const char* host, int32_t port, const 
 /* GEMM kernel variant for plans/engines created afterwards: 2 = CTA-pair tcgen05 cta_group::2 (default),
  * 1 = single-CTA kernel (kept for A/B measurements).  Returns the active variant. */
 int b200_set_gemm_variant(int32_t v);
+/* Debug: subsequent pair-GEMM launches write 8 clock64() phase stamps per CTA into trace_dev (int64[grid][8]);
+ * NULL turns it off.  Stamps: 0 entry, 1 after prologue, 2 first tile accumulated, 3 main loop + partial stores
+ * done, 4 peers' partials visible, 5 bulk pull landed, 6 before final cluster sync, 7 exit. */
+int b200_op_gemm_trace(void* trace_dev);
+/* Same contraction, but the GEMM only dumps fp32 stream-K partials and a second kernel reduces them to bf16 —
+ * the engine's T <= 512 path (there the reduction is fused into the consumer kernels). */
+int b200_op_gemm_deferred(const void* w, const void* x, void* out, int32_t N, int32_t T, int32_t K, void* stream);
 int b200_op_gemm(const void* w, const void* x, void* out, int32_t N, int32_t T, int32_t K, void* stream);
 int b200_op_embed(const void* table, const int32_t* ids, void* out, int32_t T, int32_t H, int32_t vocab, void* stream);
 int b200_op_rmsnorm(const void* x, void* residual, const void* w, void* out, const int32_t* row_index, int32_t rows,

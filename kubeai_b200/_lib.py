@@ -140,6 +140,8 @@ SYMBOLS = {
     "b200_harness_run": (C.c_int, [_vp, C.c_char_p, _i32, C.POINTER(HarnessConfig), C.c_char_p, C.c_size_t,
                                     C.POINTER(HarnessResult)]),
     "b200_set_gemm_variant": (C.c_int, [_i32]),
+    "b200_op_gemm_trace": (C.c_int, [_vp]),
+    "b200_op_gemm_deferred": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp]),
     "b200_op_gemm": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp]),
     "b200_op_embed": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp]),
     "b200_op_rmsnorm": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _f, _vp]),

@@ -4,6 +4,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <algorithm>
 #include <mutex>
 
 #include "../../include/b200engine.h"
@@ -43,6 +44,7 @@ namespace {
 // scratch for b200_op_gemm (the engine owns its own)
 std::mutex g_mu;
 float* g_ws = nullptr;
+size_t g_ws_bytes = 0;
 int* g_counters = nullptr;
 constexpr int kCounterInts = 1 << 20;
 
@@ -52,7 +54,8 @@ int ensure_scratch() {
   int sms = 0, dev = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  if (cudaMalloc(&g_ws, gemm_workspace_bytes(sms)) != cudaSuccess) return -1;
+  g_ws_bytes = std::max<size_t>(gemm_workspace_bytes(sms), 256ull << 20);
+  if (cudaMalloc(&g_ws, g_ws_bytes) != cudaSuccess) return -1;
   if (cudaMalloc(&g_counters, kCounterInts * sizeof(int)) != cudaSuccess) return -1;
   cudaMemset(g_counters, 0, kCounterInts * sizeof(int));
   return 0;
@@ -95,9 +98,38 @@ int b200_op_gemm(const void* w, const void* x, void* out, int32_t N, int32_t T, 
   return 0;
 }
 
+int b200_op_gemm_deferred(const void* w, const void* x, void* out, int32_t N, int32_t T, int32_t K, void* stream) {
+  if (int rc = require_device()) return rc;
+  if (!w || !x || !out || N <= 0 || T <= 0 || K <= 0 || K % 8 || T > kGemmDeferredMaxT || gemm_variant() != 2) {
+    set_error("b200_op_gemm_deferred: bad arguments N=%d T=%d K=%d (needs T <= %d and the pair kernel)", N, T, K, kGemmDeferredMaxT);
+    return B200_ERR_INVALID;
+  }
+  if (ensure_scratch()) { set_error("workspace allocation failed"); return B200_ERR_OOM; }
+  GemmPlan plan;
+  int rc = gemm_plan_init(&plan, w, N, K, K, g_ws, g_counters, 0);
+  if (rc) return cuda_fail("gemm_plan_init", rc);
+  plan.ws_bytes = g_ws_bytes;
+  if ((rc = gemm_plan_build_table(&plan))) return cuda_fail("gemm_plan_build_table", rc);
+  const int bn = gemm_block_n_for(T);
+  CUtensorMap tmx;
+  rc = gemm_make_x_map(&tmx, x, T, K, K, bn);
+  PartialView pv = no_partials();
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!rc) rc = gemm_run_deferred(plan, tmx, bn, T, st, &pv);
+  if (!rc) rc = reduce_partials(pv, out, N, T, N, st);
+  cudaStreamSynchronize(st);  // the segment table is freed below
+  gemm_plan_destroy(&plan);
+  return rc ? cuda_fail("gemm_deferred", rc) : 0;
+}
+
 int b200_set_gemm_variant(int32_t v) {
   gemm_set_variant(v);
   return gemm_variant();
+}
+
+int b200_op_gemm_trace(void* trace_dev) {
+  gemm2_set_trace(static_cast<long long*>(trace_dev));
+  return 0;
 }
 
 int b200_op_embed(const void* table, const int32_t* ids, void* out, int32_t T, int32_t H, int32_t vocab,

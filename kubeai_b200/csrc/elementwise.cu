@@ -11,6 +11,7 @@
 
 #include "kernels.h"
 #include "launch.h"
+#include "partials.cuh"
 #include "ptx.cuh"
 
 namespace b200 {
@@ -47,7 +48,7 @@ __global__ void embed_kernel(const __nv_bfloat16* __restrict__ table, const int*
 template <int VPT>  // uint4 vectors per thread (H = VPT * 8 * blockDim)
 __global__ void rmsnorm_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ residual,
                                const __nv_bfloat16* __restrict__ w, __nv_bfloat16* __restrict__ out,
-                               const int* __restrict__ row_index, int H, float eps) {
+                               const int* __restrict__ row_index, int H, float eps, PartialView pv) {
   griddep_wait();
   griddep_launch();
   const int s = blockIdx.x;
@@ -59,22 +60,29 @@ __global__ void rmsnorm_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat1
 #pragma unroll
   for (int i = 0; i < VPT; ++i) {
     const int idx = threadIdx.x + i * blockDim.x;
-    Vec8 a;
-    a.u = xin[idx];
+    float xa[8];
+    if (pv.ws) {
+      load8_partials(pv, r, idx * 8, xa);  // x = bf16(sum of the GEMM's stream-K segments)
+    } else {
+      Vec8 a;
+      a.u = xin[idx];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) xa[j] = __bfloat162float(a.h[j]);
+    }
     if (res) {
       Vec8 b;
       b.u = res[idx];
       Vec8 o;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        float f = __bfloat162float(a.h[j]) + __bfloat162float(b.h[j]);
+        float f = xa[j] + __bfloat162float(b.h[j]);
         o.h[j] = __float2bfloat16_rn(f);  // residual stored in input dtype ...
         v[i][j] = f;                      // ... variance from the fp32 sum (layernorm.py:51-56)
       }
       if (!row_index) res[idx] = o.u;
     } else {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[i][j] = __bfloat162float(a.h[j]);
+      for (int j = 0; j < 8; ++j) v[i][j] = xa[j];
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) ss += v[i][j] * v[i][j];
@@ -112,7 +120,7 @@ __global__ void rmsnorm_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat1
 // kv layout per layer: [block][2][Hkv][16][128]  (head-major inside a page: one (page,head) = 4 KiB contiguous)
 __global__ void rope_kv_kernel(__nv_bfloat16* __restrict__ qkv, const int* __restrict__ positions,
                                const int* __restrict__ slots, const __nv_bfloat16* __restrict__ cos_sin,
-                               __nv_bfloat16* __restrict__ kv, int Hq, int Hkv, int max_pos) {
+                               __nv_bfloat16* __restrict__ kv, int Hq, int Hkv, int max_pos, PartialView pv) {
   griddep_wait();
   griddep_launch();
   constexpr int D = 128, HALF = 64;
@@ -132,14 +140,26 @@ __global__ void rope_kv_kernel(__nv_bfloat16* __restrict__ qkv, const int* __res
   for (int task = threadIdx.x; task < rot_tasks; task += blockDim.x) {
     const int head = task >> 3, c = task & 7;
     __nv_bfloat16* hp = row + head * D;
-    Vec8 x1, x2, co, si, o1, o2;
-    x1.u = *reinterpret_cast<const uint4*>(hp + c * 8);
-    x2.u = *reinterpret_cast<const uint4*>(hp + HALF + c * 8);
+    Vec8 co, si, o1, o2;
+    float xa[8], xb[8];
+    if (pv.ws) {
+      load8_partials(pv, t, head * D + c * 8, xa);
+      load8_partials(pv, t, head * D + HALF + c * 8, xb);
+    } else {
+      Vec8 x1, x2;
+      x1.u = *reinterpret_cast<const uint4*>(hp + c * 8);
+      x2.u = *reinterpret_cast<const uint4*>(hp + HALF + c * 8);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        xa[j] = __bfloat162float(x1.h[j]);
+        xb[j] = __bfloat162float(x2.h[j]);
+      }
+    }
     co.u = __ldg(reinterpret_cast<const uint4*>(cs + c * 8));
     si.u = __ldg(reinterpret_cast<const uint4*>(cs + HALF + c * 8));
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float a = __bfloat162float(x1.h[j]), b = __bfloat162float(x2.h[j]);
+      const float a = xa[j], b = xb[j];
       const float cc = __bfloat162float(co.h[j]), sn = __bfloat162float(si.h[j]);
       // every bf16 op rounds, exactly like the reference kernel's scalar_t arithmetic
       // (x * cos - y * sin with c10::BFloat16 operators == rotary_embedding/common.py:173-174)
@@ -163,7 +183,17 @@ __global__ void rope_kv_kernel(__nv_bfloat16* __restrict__ qkv, const int* __res
     const __nv_bfloat16* vrow = row + (Hq + Hkv) * D;
     for (int task = threadIdx.x; task < v_tasks; task += blockDim.x) {
       const int head = task >> 4, c = task & 15;
-      uint4 val = *reinterpret_cast<const uint4*>(vrow + head * D + c * 8);
+      uint4 val;
+      if (pv.ws) {
+        float f[8];
+        load8_partials(pv, t, (Hq + Hkv + head) * D + c * 8, f);
+        val.x = pack_bf16x2(f[0], f[1]);
+        val.y = pack_bf16x2(f[2], f[3]);
+        val.z = pack_bf16x2(f[4], f[5]);
+        val.w = pack_bf16x2(f[6], f[7]);
+      } else {
+        val = *reinterpret_cast<const uint4*>(vrow + head * D + c * 8);
+      }
       *reinterpret_cast<uint4*>(vbase + (static_cast<size_t>(head) * 16 + off) * D + c * 8) = val;
     }
   }
@@ -171,7 +201,7 @@ __global__ void rope_kv_kernel(__nv_bfloat16* __restrict__ qkv, const int* __res
 
 // ------------------------------------------------------------------ SiLU(gate) * up
 __global__ void silu_mul_kernel(const __nv_bfloat16* __restrict__ gu, __nv_bfloat16* __restrict__ out, int I,
-                                int ldi) {
+                                int ldi, PartialView pv) {
   griddep_wait();
   griddep_launch();
   const int t = blockIdx.y;
@@ -179,21 +209,34 @@ __global__ void silu_mul_kernel(const __nv_bfloat16* __restrict__ gu, __nv_bfloa
   const uint4* u = reinterpret_cast<const uint4*>(gu + static_cast<size_t>(t) * ldi + I);
   uint4* o = reinterpret_cast<uint4*>(out + static_cast<size_t>(t) * I);
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < I / 8; i += gridDim.x * blockDim.x) {
-    Vec8 a, b, r;
-    a.u = g[i];
-    b.u = u[i];
+    Vec8 r;
+    float ga[8], ua[8];
+    if (pv.ws) {
+      load8_partials(pv, t, i * 8, ga);
+      load8_partials(pv, t, I + i * 8, ua);
+    } else {
+      Vec8 a, b;
+      a.u = g[i];
+      b.u = u[i];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        ga[j] = __bfloat162float(a.h[j]);
+        ua[j] = __bfloat162float(b.h[j]);
+      }
+    }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float x = __bfloat162float(a.h[j]);
+      const float x = ga[j];
       const __nv_bfloat16 s = __float2bfloat16_rn(x / (1.0f + expf(-x)));
-      r.h[j] = __float2bfloat16_rn(__bfloat162float(s) * __bfloat162float(b.h[j]));
+      r.h[j] = __float2bfloat16_rn(__bfloat162float(s) * ua[j]);
     }
     o[i] = r.u;
   }
 }
 
 // ------------------------------------------------------------------ greedy argmax over bf16 logits
-__global__ void argmax_kernel(const __nv_bfloat16* __restrict__ logits, int* __restrict__ out, int V, int ld) {
+__global__ void argmax_kernel(const __nv_bfloat16* __restrict__ logits, int* __restrict__ out, int V, int ld,
+                              PartialView pv) {
   griddep_wait();
   griddep_launch();
   const int s = blockIdx.x;
@@ -203,11 +246,18 @@ __global__ void argmax_kernel(const __nv_bfloat16* __restrict__ logits, int* __r
   const int nvec = V / 8;
   const uint4* r4 = reinterpret_cast<const uint4*>(row);
   for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
-    Vec8 a;
-    a.u = r4[i];
+    float fa[8];
+    if (pv.ws) {
+      load8_partials(pv, s, i * 8, fa);
+    } else {
+      Vec8 a;
+      a.u = r4[i];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) fa[j] = __bfloat162float(a.h[j]);
+    }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float f = __bfloat162float(a.h[j]);
+      const float f = fa[j];
       const int idx = i * 8 + j;
       if (f > best || (f == best && idx < bi)) {
         best = f;
@@ -215,7 +265,7 @@ __global__ void argmax_kernel(const __nv_bfloat16* __restrict__ logits, int* __r
       }
     }
   }
-  for (int idx = nvec * 8 + threadIdx.x; idx < V; idx += blockDim.x) {
+  for (int idx = nvec * 8 + threadIdx.x; idx < V && !pv.ws; idx += blockDim.x) {
     const float f = __bfloat162float(row[idx]);
     if (f > best || (f == best && idx < bi)) {
       best = f;
@@ -288,7 +338,7 @@ int embed_gather(const void* table, const int* ids, void* out, int T, int H, int
 }
 
 int rmsnorm(const void* x, void* residual, const void* w, void* out, const int* row_index, int rows, int H,
-            float eps, cudaStream_t st) {
+            float eps, cudaStream_t st, PartialView pv) {
   if (rows <= 0) return 0;
   const __nv_bfloat16* xx = static_cast<const __nv_bfloat16*>(x);
   __nv_bfloat16* rr = static_cast<__nv_bfloat16*>(residual);
@@ -299,13 +349,13 @@ int rmsnorm(const void* x, void* residual, const void* w, void* out, const int* 
   // pick threads so that every thread owns exactly VPT vectors
   if (vecs % 256 == 0 && vecs / 256 <= 4) {
     switch (vecs / 256) {
-      case 1: launch_pdl(rmsnorm_kernel<1>, dim3(rows), dim3(256), 0, st, xx, rr, ww, oo, row_index, H, eps); break;
-      case 2: launch_pdl(rmsnorm_kernel<2>, dim3(rows), dim3(256), 0, st, xx, rr, ww, oo, row_index, H, eps); break;
-      case 3: launch_pdl(rmsnorm_kernel<3>, dim3(rows), dim3(256), 0, st, xx, rr, ww, oo, row_index, H, eps); break;
-      default: launch_pdl(rmsnorm_kernel<4>, dim3(rows), dim3(256), 0, st, xx, rr, ww, oo, row_index, H, eps); break;
+      case 1: launch_pdl(rmsnorm_kernel<1>, dim3(rows), dim3(256), 0, st, xx, rr, ww, oo, row_index, H, eps, pv); break;
+      case 2: launch_pdl(rmsnorm_kernel<2>, dim3(rows), dim3(256), 0, st, xx, rr, ww, oo, row_index, H, eps, pv); break;
+      case 3: launch_pdl(rmsnorm_kernel<3>, dim3(rows), dim3(256), 0, st, xx, rr, ww, oo, row_index, H, eps, pv); break;
+      default: launch_pdl(rmsnorm_kernel<4>, dim3(rows), dim3(256), 0, st, xx, rr, ww, oo, row_index, H, eps, pv); break;
     }
   } else if (vecs % 32 == 0 && vecs <= 1024) {
-    launch_pdl(rmsnorm_kernel<1>, dim3(rows), dim3(vecs), 0, st, xx, rr, ww, oo, row_index, H, eps);
+    launch_pdl(rmsnorm_kernel<1>, dim3(rows), dim3(vecs), 0, st, xx, rr, ww, oo, row_index, H, eps, pv);
   } else {
     return -1;
   }
@@ -313,26 +363,26 @@ int rmsnorm(const void* x, void* residual, const void* w, void* out, const int* 
 }
 
 int rope_kv_write(void* qkv, const int* positions, const int* slots, const void* cos_sin, void* kv_layer,
-                  int T, int Hq, int Hkv, int max_pos, cudaStream_t st) {
+                  int T, int Hq, int Hkv, int max_pos, cudaStream_t st, PartialView pv) {
   if (T <= 0) return 0;
   launch_pdl(rope_kv_kernel, dim3(T), dim3(128), 0, st, static_cast<__nv_bfloat16*>(qkv), positions, slots,
-             static_cast<const __nv_bfloat16*>(cos_sin), static_cast<__nv_bfloat16*>(kv_layer), Hq, Hkv, max_pos);
+             static_cast<const __nv_bfloat16*>(cos_sin), static_cast<__nv_bfloat16*>(kv_layer), Hq, Hkv, max_pos, pv);
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 
-int silu_mul(const void* gate_up, void* out, int T, int I, cudaStream_t st) {
+int silu_mul(const void* gate_up, void* out, int T, int I, cudaStream_t st, PartialView pv) {
   if (T <= 0) return 0;
   if (I % 8) return -1;
   dim3 grid((I / 8 + 255) / 256, T);
   launch_pdl(silu_mul_kernel, grid, dim3(256), 0, st, static_cast<const __nv_bfloat16*>(gate_up),
-             static_cast<__nv_bfloat16*>(out), I, 2 * I);
+             static_cast<__nv_bfloat16*>(out), I, 2 * I, pv);
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 
-int argmax_rows(const void* logits, int* out, int S, int V, int ld, cudaStream_t st) {
+int argmax_rows(const void* logits, int* out, int S, int V, int ld, cudaStream_t st, PartialView pv) {
   if (S <= 0) return 0;
-  if (ld % 8) return -1;
-  launch_pdl(argmax_kernel, dim3(S), dim3(1024), 0, st, static_cast<const __nv_bfloat16*>(logits), out, V, ld);
+  if (ld % 8 || (pv.ws && V % 8)) return -1;
+  launch_pdl(argmax_kernel, dim3(S), dim3(1024), 0, st, static_cast<const __nv_bfloat16*>(logits), out, V, ld, pv);
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 

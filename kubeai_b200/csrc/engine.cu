@@ -219,7 +219,9 @@ struct Engine {
   int32_t* sampled_host = nullptr;  // pinned
   XMaps xm_normed, xm_attn, xm_act, xm_last;
   float* gemm_ws = nullptr;
+  size_t gemm_ws_bytes = 0;
   int* gemm_counters = nullptr;
+  bool deferred_ok = false;  // pair kernel + segment tables available
 
   // KV
   bf16* kv = nullptr;
@@ -270,6 +272,12 @@ struct Engine {
     const int bn = gemm_block_n_for(T);
     ++stats.kernel_launches;
     return gemm_run(p, xmap(xm, bn), bn, out, ldo, T, stream);
+  }
+  // GEMM that leaves its stream-K segments as fp32 partials for the next kernel to sum (partials.cuh)
+  int gemm_def(const GemmPlan& p, const XMaps& xm, int T, PartialView* pv) {
+    const int bn = gemm_block_n_for(T);
+    ++stats.kernel_launches;
+    return gemm_run_deferred(p, xmap(xm, bn), bn, T, stream, pv);
   }
 };
 
@@ -370,7 +378,17 @@ int Engine::alloc_all() {
   CK(cudaMemset(act, 0, static_cast<size_t>(Tcap) * I * 2));
   CK(cudaMemset(last_hidden, 0, static_cast<size_t>(Scap) * H * 2));
   CK(cudaMallocHost(&sampled_host, static_cast<size_t>(Scap) * 4));
-  CK(cudaMalloc(&gemm_ws, gemm_workspace_bytes(sms)));
+  // split-K workspace: in-kernel fix-up slots, or (T <= 512) one fp32 slot per stream-K segment for deferred reduction
+  size_t ws_bytes = gemm_workspace_bytes(sms);
+  {
+    const int bn_t = gemm_block_n_for(std::min(Tcap, kGemmDeferredMaxT)), bn_s = gemm_block_n_for(std::min(Scap, kGemmDeferredMaxT));
+    ws_bytes = std::max(ws_bytes, gemm_deferred_ws_bytes(QKV, H, sms, bn_t));
+    ws_bytes = std::max(ws_bytes, gemm_deferred_ws_bytes(2 * I, H, sms, bn_t));
+    ws_bytes = std::max(ws_bytes, gemm_deferred_ws_bytes(H, I, sms, bn_t));
+    ws_bytes = std::max(ws_bytes, gemm_deferred_ws_bytes(V, H, sms, bn_s));
+  }
+  gemm_ws_bytes = ws_bytes;
+  CK(cudaMalloc(&gemm_ws, ws_bytes));
   const int maxN = std::max(std::max(QKV, 2 * I), V);
   const size_t n_counters = 2ull * (maxN / 128 + 2) * (Tcap / 32 + 2);
   CK(cudaMalloc(&gemm_counters, n_counters * 4));
@@ -378,7 +396,10 @@ int Engine::alloc_all() {
 
   // ---- GEMM plans + activation tensor maps (encoded once; kernels mask rows >= T)
   auto plan = [&](GemmPlan* p, const void* W, int N, int K) {
-    return gemm_plan_init(p, W, N, K, K, gemm_ws, gemm_counters, sms);
+    int rc = gemm_plan_init(p, W, N, K, K, gemm_ws, gemm_counters, sms);
+    if (rc) return rc;
+    p->ws_bytes = gemm_ws_bytes;
+    return gemm_variant() == 2 ? gemm_plan_build_table(p) : 0;
   };
   for (int l = 0; l < L; ++l) {
     if (plan(&layers[l].p_qkv, layers[l].wqkv, QKV, H) || plan(&layers[l].p_o, layers[l].wo, H, Hq * kD) ||
@@ -386,6 +407,7 @@ int Engine::alloc_all() {
       return cuda_fail("gemm_plan_init", -2);
   }
   if (plan(&p_lm, lm_head, V, H)) return cuda_fail("gemm_plan_init(lm_head)", -2);
+  deferred_ok = gemm_variant() == 2;
   const int bns[kGemmNumBlockN] = {32, 64, 128, 256, 512};
   for (int i = 0; i < kGemmNumBlockN; ++i) {
     if (gemm_make_x_map(&xm_normed.m[i], normed, Tcap, H, H, bns[i]) ||
@@ -477,23 +499,37 @@ int Engine::forward(const StepMeta& m, int32_t* dbuf, bool all_logits, bf16* log
     prof_used += 2;
   };
   P(B200_K_EMBED); rc |= embed_gather(embed, ids, res, T, H, V, stream); Q(); launched(1);
+  // T <= 512: every GEMM dumps fp32 stream-K partials and its consumer (norm / rope / silu / argmax) sums them while
+  // loading — no in-GEMM reduction handshake.  Larger steps use the in-kernel fix-up and bf16 intermediates.
+  const bool dfr = deferred_ok && !all_logits && T <= kGemmDeferredMaxT && m.S <= kGemmDeferredMaxT;
+  PartialView pv_x = no_partials();  // partials of the GEMM whose output is `x` (o_proj / down_proj)
   for (int l = 0; l < L && !rc; ++l) {
     Layer& ly = layers[l];
     bf16* kv_l = kv + static_cast<size_t>(l) * kv_layer_elems;
     P(B200_K_NORM);
     if (l == 0) rc |= rmsnorm(res, nullptr, ly.norm1, normed, nullptr, T, H, cfg.rms_eps, stream);
-    else rc |= rmsnorm(x, res, ly.norm1, normed, nullptr, T, H, cfg.rms_eps, stream);
+    else rc |= rmsnorm(x, res, ly.norm1, normed, nullptr, T, H, cfg.rms_eps, stream, pv_x);
     Q();
-    P(B200_K_GEMM_QKV); rc |= gemm(ly.p_qkv, xm_normed, qkv, QKV, T); Q();
-    P(B200_K_ROPE); rc |= rope_kv_write(qkv, pos, slots, cos_sin, kv_l, T, Hq, Hkv, cfg.max_model_len, stream); Q();
+    PartialView pv = no_partials();
+    P(B200_K_GEMM_QKV);
+    if (dfr) rc |= gemm_def(ly.p_qkv, xm_normed, T, &pv); else rc |= gemm(ly.p_qkv, xm_normed, qkv, QKV, T);
+    Q();
+    P(B200_K_ROPE); rc |= rope_kv_write(qkv, pos, slots, cos_sin, kv_l, T, Hq, Hkv, cfg.max_model_len, stream, pv); Q();
     launched(2);
     if (m.nd) { P(B200_K_ATTN_DECODE); rc |= paged_attention(qkv, QKV, attn, Hq * kD, kv_l, btab, max_blocks_per_seq, dwork, m.nd, Hq, Hkv, scale, 1, stream); Q(); launched(1); }
     if (m.np) { P(B200_K_ATTN_PREFILL); rc |= paged_attention(qkv, QKV, attn, Hq * kD, kv_l, btab, max_blocks_per_seq, pwork, m.np, Hq, Hkv, scale, 0, stream); Q(); launched(1); }
-    P(B200_K_GEMM_O); rc |= gemm(ly.p_o, xm_attn, x, H, T); Q();
-    P(B200_K_NORM); rc |= rmsnorm(x, res, ly.norm2, normed, nullptr, T, H, cfg.rms_eps, stream); Q();
-    P(B200_K_GEMM_GU); rc |= gemm(ly.p_gu, xm_normed, gu, 2 * I, T); Q();
-    P(B200_K_SILU); rc |= silu_mul(gu, act, T, I, stream); Q();
-    P(B200_K_GEMM_DOWN); rc |= gemm(ly.p_down, xm_act, x, H, T); Q();
+    P(B200_K_GEMM_O);
+    if (dfr) rc |= gemm_def(ly.p_o, xm_attn, T, &pv_x); else rc |= gemm(ly.p_o, xm_attn, x, H, T);
+    Q();
+    P(B200_K_NORM); rc |= rmsnorm(x, res, ly.norm2, normed, nullptr, T, H, cfg.rms_eps, stream, pv_x); Q();
+    pv = no_partials();
+    P(B200_K_GEMM_GU);
+    if (dfr) rc |= gemm_def(ly.p_gu, xm_normed, T, &pv); else rc |= gemm(ly.p_gu, xm_normed, gu, 2 * I, T);
+    Q();
+    P(B200_K_SILU); rc |= silu_mul(gu, act, T, I, stream, pv); Q();
+    P(B200_K_GEMM_DOWN);
+    if (dfr) rc |= gemm_def(ly.p_down, xm_act, T, &pv_x); else rc |= gemm(ly.p_down, xm_act, x, H, T);
+    Q();
     launched(2);
   }
   if (rc) return cuda_fail("forward", -2);
@@ -502,9 +538,12 @@ int Engine::forward(const StepMeta& m, int32_t* dbuf, bool all_logits, bf16* log
     rc |= gemm(p_lm, xm_normed, logits_out, V, T);
     launched(1);
   } else if (m.S > 0) {
-    P(B200_K_NORM); rc |= rmsnorm(x, res, final_norm, last_hidden, rows, m.S, H, cfg.rms_eps, stream); Q();
-    P(B200_K_GEMM_LM); rc |= gemm(p_lm, xm_last, logits, V, m.S); Q();
-    P(B200_K_ARGMAX); rc |= argmax_rows(logits, sampled, m.S, V, V, stream); Q();
+    P(B200_K_NORM); rc |= rmsnorm(x, res, final_norm, last_hidden, rows, m.S, H, cfg.rms_eps, stream, pv_x); Q();
+    PartialView pv = no_partials();
+    P(B200_K_GEMM_LM);
+    if (dfr) rc |= gemm_def(p_lm, xm_last, m.S, &pv); else rc |= gemm(p_lm, xm_last, logits, V, m.S);
+    Q();
+    P(B200_K_ARGMAX); rc |= argmax_rows(logits, sampled, m.S, V, V, stream, pv); Q();
     launched(2);
   }
   if (rc) return cuda_fail("forward(head)", -2);

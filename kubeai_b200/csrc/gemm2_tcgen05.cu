@@ -17,6 +17,8 @@
 #include <stdint.h>
 #include <string.h>
 
+#include <vector>
+
 #include "gemm.h"
 #include "launch.h"
 #include "ptx.cuh"
@@ -122,8 +124,14 @@ template <int BLOCK_N>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 gemm2_streamk_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_x,
                      __nv_bfloat16* __restrict__ out, int ldo, float* __restrict__ ws, int* __restrict__ counters,
-                     int N, int T, int K) {
+                     int N, int T, int K, const int2* __restrict__ seg_table, int deferred,
+                     long long* __restrict__ trace) {
   using C = Cfg2<BLOCK_N>;
+  // optional phase trace (debug): 16 clock64() stamps per CTA
+  auto mark = [&](int i) {
+    if (trace) trace[static_cast<size_t>(blockIdx.x) * 16 + i] = clock64();
+  };
+  if (threadIdx.x == 64) mark(0);
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_base = smem_base + C::kStages * C::kStageBytes;
@@ -176,6 +184,7 @@ gemm2_streamk_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_cons
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
   griddep_launch();
+  if (threadIdx.x == 64) mark(1);
 
   auto seg_at = [&](long long it) {
     Seg s;
@@ -203,6 +212,7 @@ gemm2_streamk_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_cons
                          (tile / ntt) * 2 * kSlab + static_cast<int>(rank) * kSlab, w_hint);
       }
       griddep_wait();
+      mark(12);
       int stage = 0, idx = 0;
       uint32_t phase = 0;
       for (long long it = it_begin; it < it_end; ++it, ++idx) {
@@ -227,6 +237,7 @@ gemm2_streamk_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_cons
           phase ^= 1u;
         }
       }
+      mark(13);
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer (leader CTA only)
@@ -242,6 +253,7 @@ gemm2_streamk_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_cons
         for (int kb = sg.kb0; kb < sg.kb1; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
+          if (it == it_begin && kb == sg.kb0) mark(10);
           const uint32_t sa = smem_base + stage * C::kStageBytes;
           const uint64_t a_desc = umma_desc_kmajor_sw128(sa);
 #pragma unroll
@@ -268,6 +280,7 @@ gemm2_streamk_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_cons
         }
         it += sg.kb1 - sg.kb0;
       }
+      mark(11);
     }
   } else {
     // ------------------------------------------------------------ epilogue warps (both CTAs, own 128 rows)
@@ -287,12 +300,21 @@ gemm2_streamk_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_cons
 #pragma unroll
       for (int c = 0; c < C::kNch; ++c) n_eff += chunk_n(tt, c);
       const int n = (slab2 * 2 + static_cast<int>(rank)) * kSlab + row;
-      const bool complete = (sg.kb0 == 0 && sg.kb1 == KB);
+      const bool complete = !deferred && (sg.kb0 == 0 && sg.kb1 == KB);
       const int slot = (it == it_begin) ? 0 : 1;
-      float* wslot = ws + (static_cast<size_t>(cta) * 2 + slot) * kSlot;
+      float* wslot;
+      if (deferred) {
+        // segment index = table[tile].first + (this unit's position among the units covering the tile); ntt == 1
+        const int u0 = unit_of_iter(static_cast<long long>(sg.tile) * KB, total, units);
+        const int seg = __ldg(&seg_table[sg.tile]).x + (unit - u0);
+        wslot = ws + (static_cast<size_t>(seg) * 2 + rank) * kSlot;
+      } else {
+        wslot = ws + (static_cast<size_t>(cta) * 2 + slot) * kSlot;
+      }
 
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
+      if (epi_tid == 0 && it == it_begin) mark(2);
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N;
       for (int c0 = 0; c0 < n_eff; c0 += 32) {
         uint32_t v[32];
@@ -318,7 +340,7 @@ gemm2_streamk_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_cons
         if (leader) mbar_arrive(tempty_bar(acc));
         else mbar_arrive_remote(tempty_bar(acc), 0);
       }
-      if (!complete) {
+      if (!complete && !deferred) {
         __threadfence();
         asm volatile("bar.sync 1, 128;" ::: "memory");
         if (epi_tid == 0) atomicAdd(&counters[2 * (sg.tile * 2 + static_cast<int>(rank))], 1);
@@ -331,6 +353,7 @@ gemm2_streamk_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_cons
       it += sg.kb1 - sg.kb0;
     }
 
+    if (epi_tid == 0) mark(3);
     // -------- fix-up (per CTA, same-rank CTAs of the other pairs are the peers)
     struct Fix {
       int j, u0, nseg, cb, ncol, t0, n, cid;
@@ -380,6 +403,7 @@ gemm2_streamk_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_cons
       if (epi_tid == 0) {
         for (int f = 0; f < nfix; ++f)
           while (ld_acquire(&counters[2 * fx[f].cid]) < fx[f].nseg) __nanosleep(20);
+        mark(4);
         if (total_bytes) {
           asm volatile("fence.proxy.async;" ::: "memory");
           mbar_arrive_expect_tx(fix_bar, total_bytes);
@@ -393,6 +417,7 @@ gemm2_streamk_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_cons
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
       if (total_bytes) mbar_wait(fix_bar, fix_phase);
+      if (epi_tid == 0) mark(5);
       for (int f = 0; f < nfix; ++f) {
         const Fix& x = fx[f];
         const float* base = fix_smem + off[f] / 4;
@@ -402,8 +427,10 @@ gemm2_streamk_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_cons
           if (x.n < N) out[static_cast<size_t>(x.t0 + x.cb + col) * ldo + x.n] = __float2bfloat16_rn(sum);
         }
       }
+      if (epi_tid == 0) mark(8);
       if (epi_tid == 0)
         for (int f = 0; f < nfix; ++f) finish(fx[f]);
+      if (epi_tid == 0) mark(9);
     } else {
       // general path: one tile at a time, the column slice in pieces that fit the ring
       for (int f = 0; f < nfix; ++f) {
@@ -436,16 +463,31 @@ gemm2_streamk_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_cons
     }
   }
 
+  if (threadIdx.x == 64) mark(6);
   tc_fence_before();
   cluster_sync();  // neither CTA may exit (or free TMEM) while the peer can still signal its barriers / read its smem
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc2(tmem_base, C::kTmemCols);
   }
+  if (threadIdx.x == 64) mark(7);
+}
+
+long long* g_trace = nullptr;  // debug: device buffer of 8 stamps per CTA (b200_op_gemm_trace)
+
+int units_for(const GemmPlan& p, int ntt) {
+  const int pairs_n = (p.N + 2 * kSlab - 1) / (2 * kSlab);
+  const int KB = (p.K + kBlockK - 1) / kBlockK;
+  const long long total = static_cast<long long>(pairs_n) * ntt * KB;
+  long long u = total / 4;
+  if (u < 1) u = 1;
+  const int max_units = p.max_ctas / 2;
+  return static_cast<int>(u < max_units ? u : max_units);
 }
 
 template <int BLOCK_N>
-int launch2(const GemmPlan& p, const CUtensorMap& tm_x, __nv_bfloat16* out, int ldo, int T, cudaStream_t st) {
+int launch2(const GemmPlan& p, const CUtensorMap& tm_x, __nv_bfloat16* out, int ldo, int T, cudaStream_t st,
+            int deferred = 0) {
   using C = Cfg2<BLOCK_N>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -454,20 +496,95 @@ int launch2(const GemmPlan& p, const CUtensorMap& tm_x, __nv_bfloat16* out, int 
       return -3;
     attr_set = true;
   }
-  const int pairs_n = (p.N + 2 * kSlab - 1) / (2 * kSlab);
   const int ntt = (T + BLOCK_N - 1) / BLOCK_N;
-  const int KB = (p.K + kBlockK - 1) / kBlockK;
-  const long long total = static_cast<long long>(pairs_n) * ntt * KB;
-  long long u = total / 4;
-  if (u < 1) u = 1;
-  const int max_units = p.max_ctas / 2;
-  const int units = static_cast<int>(u < max_units ? u : max_units);
+  const int units = units_for(p, ntt);
   cudaError_t e = launch_pdl(gemm2_streamk_kernel<BLOCK_N>, dim3(2 * units), dim3(kThreads), C::kSmemBytes, st, p.tm_w, tm_x,
-                             out, ldo, p.ws, p.counters, p.N, T, p.K);
+                             out, ldo, p.ws, p.counters, p.N, T, p.K, static_cast<const int2*>(p.seg_table), deferred,
+                             g_trace);
   return e == cudaSuccess ? 0 : -4;
 }
 
+// out[t, n] = bf16(sum of the tile's segments): the generic consumer of deferred partials.
+__global__ void reduce_partials_kernel(PartialView v, __nv_bfloat16* __restrict__ out, int ldo, int T, int N) {
+  griddep_wait();
+  griddep_launch();
+  const int t = blockIdx.y;
+  const int n0 = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  if (n0 >= N) return;
+  float f[8];
+  load8_partials(v, t, n0, f);
+  if (n0 + 8 <= N) {
+    uint4 u;
+    u.x = pack_bf16x2(f[0], f[1]);
+    u.y = pack_bf16x2(f[2], f[3]);
+    u.z = pack_bf16x2(f[4], f[5]);
+    u.w = pack_bf16x2(f[6], f[7]);
+    *reinterpret_cast<uint4*>(out + static_cast<size_t>(t) * ldo + n0) = u;
+  } else {
+    for (int j = 0; j < 8 && n0 + j < N; ++j) out[static_cast<size_t>(t) * ldo + n0 + j] = __float2bfloat16_rn(f[j]);
+  }
+}
+
 }  // namespace
+
+int gemm2_units_for(const GemmPlan& p, int ntt) { return units_for(p, ntt); }
+
+int gemm_plan_build_table(GemmPlan* p) {
+  if (p->seg_table) return 0;
+  const int pairs_n = (p->N + 2 * kSlab - 1) / (2 * kSlab);
+  const int KB = (p->K + kBlockK - 1) / kBlockK;
+  const long long total = static_cast<long long>(pairs_n) * KB;
+  const int units = units_for(*p, 1);
+  auto unit_of = [&](long long x) { return static_cast<int>(((x + 1) * units + total - 1) / total - 1); };
+  std::vector<int2> tab(pairs_n);
+  int seg = 0;
+  for (int j = 0; j < pairs_n; ++j) {
+    const int u0 = unit_of(static_cast<long long>(j) * KB), u1 = unit_of(static_cast<long long>(j + 1) * KB - 1);
+    tab[j] = make_int2(seg, u1 - u0 + 1);
+    seg += u1 - u0 + 1;
+  }
+  p->num_segs = seg;
+  if (cudaMalloc(&p->seg_table, tab.size() * sizeof(int2)) != cudaSuccess) return -7;
+  if (cudaMemcpy(p->seg_table, tab.data(), tab.size() * sizeof(int2), cudaMemcpyHostToDevice) != cudaSuccess) return -7;
+  return 0;
+}
+
+void gemm_plan_destroy(GemmPlan* p) {
+  if (p->seg_table) cudaFree(p->seg_table);
+  p->seg_table = nullptr;
+}
+
+size_t gemm_deferred_ws_bytes(int N, int K, int max_ctas, int max_block_n) {
+  const int pairs_n = (N + 2 * kSlab - 1) / (2 * kSlab);
+  const size_t segs = static_cast<size_t>(pairs_n) + max_ctas / 2;  // every unit boundary adds at most one segment
+  return segs * 2 * static_cast<size_t>(max_block_n) * kSlab * sizeof(float);
+}
+
+int gemm_run_deferred(const GemmPlan& p, const CUtensorMap& tm_x, int block_n, int T, cudaStream_t st, PartialView* view) {
+  if (T <= 0 || T > kGemmDeferredMaxT || !p.seg_table) return -8;
+  const size_t need = static_cast<size_t>(p.num_segs) * 2 * block_n * kSlab * sizeof(float);
+  if (need > p.ws_bytes) return -9;
+  view->ws = p.ws;
+  view->table = p.seg_table;
+  view->slot = block_n * kSlab;
+  switch (block_n) {
+    case 32: return launch2<32>(p, tm_x, nullptr, 0, T, st, 1);
+    case 64: return launch2<64>(p, tm_x, nullptr, 0, T, st, 1);
+    case 128: return launch2<128>(p, tm_x, nullptr, 0, T, st, 1);
+    case 256: return launch2<256>(p, tm_x, nullptr, 0, T, st, 1);
+    case 512: return launch2<512>(p, tm_x, nullptr, 0, T, st, 1);
+    default: return -6;
+  }
+}
+
+int reduce_partials(const PartialView& v, void* out, int ldo, int T, int N, cudaStream_t st) {
+  if (T <= 0) return 0;
+  dim3 grid((N / 8 + 127) / 128 + 1, T);
+  cudaError_t e = launch_pdl(reduce_partials_kernel, grid, dim3(128), 0, st, v, static_cast<__nv_bfloat16*>(out), ldo, T, N);
+  return e == cudaSuccess ? 0 : -4;
+}
+
+void gemm2_set_trace(long long* dev_ptr) { g_trace = dev_ptr; }
 
 int gemm2_block_n_for(int T) { return T <= 32 ? 32 : T <= 64 ? 64 : T <= 128 ? 128 : T <= 256 ? 256 : 512; }
 int gemm2_x_box_rows(int block_n) { return (block_n > 256 ? 256 : block_n) / 2; }

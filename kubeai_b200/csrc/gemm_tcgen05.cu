@@ -456,6 +456,9 @@ int gemm_plan_init(GemmPlan* p, const void* W, int N, int K, int ldw, float* ws,
   p->ws = ws;
   p->counters = counters;
   p->max_ctas = max_ctas > 0 ? max_ctas : num_sms();
+  p->seg_table = nullptr;
+  p->num_segs = 0;
+  p->ws_bytes = gemm_workspace_bytes(p->max_ctas);
   if (K % 8 != 0 || ldw % 8 != 0) return -5;
   return make_tmap(&p->tm_w, W, N, K, ldw, kSlab);
 }

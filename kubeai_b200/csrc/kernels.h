@@ -5,17 +5,21 @@
 #include <stddef.h>
 #include <stdint.h>
 
+#include "partials.cuh"
+
 namespace b200 {
 
 int embed_gather(const void* table, const int* ids, void* out, int T, int H, int vocab, cudaStream_t st);
 // out[s] = rmsnorm(x[r] (+ residual[r])) * w,  r = row_index ? row_index[s] : s.
 // residual (optional) is updated in place with bf16(x + residual) unless row_index is given.
+// Every consumer of a GEMM output takes an optional PartialView: when pv.ws != nullptr the input is the fp32
+// stream-K partials of the preceding deferred GEMM (summed + rounded to bf16 on load) instead of the bf16 tensor.
 int rmsnorm(const void* x, void* residual, const void* w, void* out, const int* row_index, int rows, int H,
-            float eps, cudaStream_t st);
+            float eps, cudaStream_t st, PartialView pv = no_partials());
 int rope_kv_write(void* qkv, const int* positions, const int* slots, const void* cos_sin, void* kv_layer,
-                  int T, int Hq, int Hkv, int max_pos, cudaStream_t st);
-int silu_mul(const void* gate_up, void* out, int T, int I, cudaStream_t st);
-int argmax_rows(const void* logits, int* out, int S, int V, int ld, cudaStream_t st);
+                  int T, int Hq, int Hkv, int max_pos, cudaStream_t st, PartialView pv = no_partials());
+int silu_mul(const void* gate_up, void* out, int T, int I, cudaStream_t st, PartialView pv = no_partials());
+int argmax_rows(const void* logits, int* out, int S, int V, int ld, cudaStream_t st, PartialView pv = no_partials());
 int init_uniform(void* p, size_t n, uint32_t seed, float scale, float offset, cudaStream_t st);
 
 // One unit of attention work: q_count query tokens of one sequence starting at row q_tok0 of the

@@ -1,0 +1,61 @@
+// Deferred stream-K reduction: the pair GEMM (gemm2_tcgen05.cu) can leave every tile segment as an
+// fp32 partial in an L2-resident workspace instead of reducing in-kernel; the consumer kernel sums
+// the segments while it loads its input.  The kernel boundary is then the only synchronisation of
+// the split-K reduction (no flags, fences, spin-waits or extra round trips inside the GEMM).
+//   workspace: [segment][rank 0|1][token (slot/128)][128 weight rows] fp32
+//   table:     per 256-row tile {first segment, number of segments}
+// Segments are summed in index order in fp32 and rounded to bf16 once — the same rounding point as
+// a GEMM that writes bf16 (vllm linear output), so downstream numerics are unchanged.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace b200 {
+
+struct PartialView {
+  const float* ws;     // nullptr => the op reads its ordinary bf16 input
+  const int2* table;
+  int slot;            // floats per (segment, rank) slot = block_n * 128
+};
+
+inline PartialView no_partials() { return PartialView{nullptr, nullptr, 0}; }
+
+// Sum of all segments for token t, weight rows [n0, n0+8) (n0 % 8 == 0), rounded to bf16 precision.
+__device__ __forceinline__ void load8_partials(const PartialView& v, int t, int n0, float (&o)[8]) {
+  const int tile = n0 >> 8, rank = (n0 >> 7) & 1, row = n0 & 127;
+  const int2 e = __ldg(v.table + tile);
+  const size_t stride = 2 * static_cast<size_t>(v.slot);
+  const float* p = v.ws + (static_cast<size_t>(e.x) * 2 + rank) * v.slot + static_cast<size_t>(t) * 128 + row;
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+  // four segments' loads are issued before the first add (independent L2 round trips), the adds stay in
+  // segment order so the result does not depend on the unrolling
+  for (int s = 0; s < e.y; s += 4, p += 4 * stride) {
+    float4 x[4], y[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (s + u < e.y) {
+        x[u] = __ldcg(reinterpret_cast<const float4*>(p + u * stride));
+        y[u] = __ldcg(reinterpret_cast<const float4*>(p + u * stride + 4));
+      } else {
+        x[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        y[u] = x[u];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      a.x += x[u].x; a.y += x[u].y; a.z += x[u].z; a.w += x[u].w;
+      b.x += y[u].x; b.y += y[u].y; b.z += y[u].z; b.w += y[u].w;
+    }
+  }
+  o[0] = __bfloat162float(__float2bfloat16_rn(a.x));
+  o[1] = __bfloat162float(__float2bfloat16_rn(a.y));
+  o[2] = __bfloat162float(__float2bfloat16_rn(a.z));
+  o[3] = __bfloat162float(__float2bfloat16_rn(a.w));
+  o[4] = __bfloat162float(__float2bfloat16_rn(b.x));
+  o[5] = __bfloat162float(__float2bfloat16_rn(b.y));
+  o[6] = __bfloat162float(__float2bfloat16_rn(b.z));
+  o[7] = __bfloat162float(__float2bfloat16_rn(b.w));
+}
+
+}  // namespace b200

@@ -32,6 +32,16 @@ def gemm(x: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def gemm_deferred(x: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
+    """Pair GEMM in deferred-reduction mode + the generic partial reducer (T <= 512)."""
+    _chk(x), _chk(w)
+    T, K = x.shape
+    N = w.shape[0]
+    out = torch.empty(T, N, dtype=torch.bfloat16, device=x.device)
+    check(lib().b200_op_gemm_deferred(_p(w), _p(x), _p(out), N, T, K, _stream()))
+    return out
+
+
 def embed(table, ids):
     _chk(table), _chk(ids, torch.int32)
     out = torch.empty(ids.numel(), table.shape[1], dtype=torch.bfloat16, device=table.device)

@@ -22,6 +22,9 @@ if [ -n "$MICRO" ]; then
   timeout 900 python scripts/microbench.py $MICRO > gpurun_out/micro.log 2>&1
   tail -n 120 gpurun_out/micro.log
 fi
+if [ -n "$TRACE" ]; then
+  timeout 300 python scripts/gemm_trace.py > gpurun_out/trace.log 2>&1; cat gpurun_out/trace.log
+fi
 if [ -n "$BENCH" ]; then
   timeout 1200 python bench.py $BENCH > gpurun_out/bench.log 2> gpurun_out/bench.err
   echo "bench exit $?"; tail -c 6000 gpurun_out/bench.log; tail -n 15 gpurun_out/bench.err

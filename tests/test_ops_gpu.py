@@ -68,6 +68,18 @@ def test_gemm_matches_oracle(T, N, K, gemm_variant):
     close(got, want, atol=2e-3, rtol=RTOL, what=f"gemm {T}x{N}x{K}")
 
 
+@pytest.mark.parametrize("T,N,K", [(128, 4096, 4096), (1, 512, 512), (40, 768, 512), (100, 1000, 520), (384, 2048, 1024),
+                                   (512, 28672, 4096), (128, 128256, 4096), (17, 4096, 14336)])
+def test_gemm_deferred_reduction_matches_oracle(T, N, K):
+    """The engine's T <= 512 path: fp32 stream-K partials summed by the consumer (partials.cuh)."""
+    from kubeai_b200 import ops
+    x, w = rnd(T, K, seed=1), rnd(N, K, scale=1 / math.sqrt(K), seed=2)
+    got = ops.gemm_deferred(dev(x), dev(w))
+    torch.cuda.synchronize()
+    close(got, O.gemm(x, w), atol=2e-3, rtol=RTOL, what=f"deferred gemm {T}x{N}x{K}")
+    assert torch.equal(got, ops.gemm_deferred(dev(x), dev(w))), "fixed summation order => bit-reproducible"
+
+
 def test_gemm_repeatable_and_counters_reset(gemm_variant):
     from kubeai_b200 import ops
     x, w = dev(rnd(128, 4096, seed=3)), dev(rnd(4096, 4096, scale=1 / 64, seed=4))
