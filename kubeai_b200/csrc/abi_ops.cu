@@ -100,8 +100,8 @@ int b200_op_gemm(const void* w, const void* x, void* out, int32_t N, int32_t T, 
 
 int b200_op_gemm_deferred(const void* w, const void* x, void* out, int32_t N, int32_t T, int32_t K, void* stream) {
   if (int rc = require_device()) return rc;
-  if (!w || !x || !out || N <= 0 || T <= 0 || K <= 0 || K % 8 || T > kGemmDeferredMaxT || gemm_variant() != 2) {
-    set_error("b200_op_gemm_deferred: bad arguments N=%d T=%d K=%d (needs T <= %d and the pair kernel)", N, T, K, kGemmDeferredMaxT);
+  if (!w || !x || !out || N <= 0 || T <= 0 || K <= 0 || K % 8 || gemm_variant() != 2) {
+    set_error("b200_op_gemm_deferred: bad arguments N=%d T=%d K=%d (needs the pair kernel)", N, T, K);
     return B200_ERR_INVALID;
   }
   if (ensure_scratch()) { set_error("workspace allocation failed"); return B200_ERR_OOM; }
@@ -109,13 +109,14 @@ int b200_op_gemm_deferred(const void* w, const void* x, void* out, int32_t N, in
   int rc = gemm_plan_init(&plan, w, N, K, K, g_ws, g_counters, 0);
   if (rc) return cuda_fail("gemm_plan_init", rc);
   plan.ws_bytes = g_ws_bytes;
-  if ((rc = gemm_plan_build_table(&plan))) return cuda_fail("gemm_plan_build_table", rc);
+  if ((rc = gemm_plan_build_table(&plan, T))) return cuda_fail("gemm_plan_build_table", rc);
   const int bn = gemm_block_n_for(T);
   CUtensorMap tmx;
   rc = gemm_make_x_map(&tmx, x, T, K, K, bn);
   PartialView pv = no_partials();
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (!rc) rc = gemm_run_deferred(plan, tmx, bn, T, st, &pv);
+  // complete tiles land in `out` directly; the reducer then fills in the split tiles (in place)
+  if (!rc) rc = gemm_run_deferred(plan, tmx, bn, out, N, T, st, &pv);
   if (!rc) rc = reduce_partials(pv, out, N, T, N, st);
   cudaStreamSynchronize(st);  // the segment table is freed below
   gemm_plan_destroy(&plan);

@@ -33,7 +33,7 @@ constexpr int kStageBytes = 2 * kTileBytes;     // K + V
 constexpr int kAttnSmem = 2 * kStageBytes;      // double buffered: 64 KiB
 
 template <bool DECODE>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, DECODE ? 3 : 2)  // decode: 3 CTAs/SM (168 regs, ~70 B spill) => 96 KiB of KV in flight per SM
 paged_attn_kernel(const __nv_bfloat16* __restrict__ q, int ldq, __nv_bfloat16* __restrict__ out, int ldo,
                   const __nv_bfloat16* __restrict__ kv, const int* __restrict__ block_tables, int max_blocks,
                   const AttnWork* __restrict__ work, int Hkv, float scale_log2) {

@@ -137,6 +137,8 @@ __global__ void rope_kv_kernel(__nv_bfloat16* __restrict__ qkv, const int* __res
   __nv_bfloat16* vbase = kbase + page_stride;
 
   const int rot_tasks = (Hq + Hkv) * (HALF / 8);  // 8 elements of x1 (and the matching 8 of x2) per task
+  const int v_tasks = Hkv * (D / 8);
+  // rotation tasks and V-copy tasks share one index space so that a 512-thread CTA gives every thread one task
   for (int task = threadIdx.x; task < rot_tasks; task += blockDim.x) {
     const int head = task >> 3, c = task & 7;
     __nv_bfloat16* hp = row + head * D;
@@ -179,9 +181,10 @@ __global__ void rope_kv_kernel(__nv_bfloat16* __restrict__ qkv, const int* __res
     }
   }
   if (slot >= 0) {
-    const int v_tasks = Hkv * (D / 8);
     const __nv_bfloat16* vrow = row + (Hq + Hkv) * D;
-    for (int task = threadIdx.x; task < v_tasks; task += blockDim.x) {
+    // start the V tasks where the rotation tasks ended so idle threads of the first pass take them
+    for (int task = static_cast<int>((threadIdx.x + blockDim.x - rot_tasks % blockDim.x) % blockDim.x); task < v_tasks;
+         task += blockDim.x) {
       const int head = task >> 4, c = task & 15;
       uint4 val;
       if (pv.ws) {
@@ -346,16 +349,16 @@ int rmsnorm(const void* x, void* residual, const void* w, void* out, const int* 
   __nv_bfloat16* oo = static_cast<__nv_bfloat16*>(out);
   if (H % 8) return -1;
   const int vecs = H / 8;
-  // pick threads so that every thread owns exactly VPT vectors
-  if (vecs % 256 == 0 && vecs / 256 <= 4) {
+  // one 8-element vector per thread when the row fits a CTA (most loads in flight per row: the partial
+  // reads are L2 round trips), otherwise 256 threads with up to 4 vectors each
+  if (vecs % 32 == 0 && vecs <= 1024) {
+    launch_pdl(rmsnorm_kernel<1>, dim3(rows), dim3(vecs), 0, st, xx, rr, ww, oo, row_index, H, eps, pv);
+  } else if (vecs % 256 == 0 && vecs / 256 <= 4) {
     switch (vecs / 256) {
-      case 1: launch_pdl(rmsnorm_kernel<1>, dim3(rows), dim3(256), 0, st, xx, rr, ww, oo, row_index, H, eps, pv); break;
       case 2: launch_pdl(rmsnorm_kernel<2>, dim3(rows), dim3(256), 0, st, xx, rr, ww, oo, row_index, H, eps, pv); break;
       case 3: launch_pdl(rmsnorm_kernel<3>, dim3(rows), dim3(256), 0, st, xx, rr, ww, oo, row_index, H, eps, pv); break;
       default: launch_pdl(rmsnorm_kernel<4>, dim3(rows), dim3(256), 0, st, xx, rr, ww, oo, row_index, H, eps, pv); break;
     }
-  } else if (vecs % 32 == 0 && vecs <= 1024) {
-    launch_pdl(rmsnorm_kernel<1>, dim3(rows), dim3(vecs), 0, st, xx, rr, ww, oo, row_index, H, eps, pv);
   } else {
     return -1;
   }
@@ -365,7 +368,9 @@ int rmsnorm(const void* x, void* residual, const void* w, void* out, const int* 
 int rope_kv_write(void* qkv, const int* positions, const int* slots, const void* cos_sin, void* kv_layer,
                   int T, int Hq, int Hkv, int max_pos, cudaStream_t st, PartialView pv) {
   if (T <= 0) return 0;
-  launch_pdl(rope_kv_kernel, dim3(T), dim3(128), 0, st, static_cast<__nv_bfloat16*>(qkv), positions, slots,
+  const int tasks = (Hq + Hkv) * 8 + Hkv * 16;
+  const int threads = tasks >= 512 ? 512 : tasks >= 256 ? 256 : 128;
+  launch_pdl(rope_kv_kernel, dim3(T), dim3(threads), 0, st, static_cast<__nv_bfloat16*>(qkv), positions, slots,
              static_cast<const __nv_bfloat16*>(cos_sin), static_cast<__nv_bfloat16*>(kv_layer), Hq, Hkv, max_pos, pv);
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }

@@ -12,6 +12,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -274,10 +275,10 @@ struct Engine {
     return gemm_run(p, xmap(xm, bn), bn, out, ldo, T, stream);
   }
   // GEMM that leaves its stream-K segments as fp32 partials for the next kernel to sum (partials.cuh)
-  int gemm_def(const GemmPlan& p, const XMaps& xm, int T, PartialView* pv) {
+  int gemm_def(const GemmPlan& p, const XMaps& xm, void* out, int ldo, int T, PartialView* pv) {
     const int bn = gemm_block_n_for(T);
     ++stats.kernel_launches;
-    return gemm_run_deferred(p, xmap(xm, bn), bn, T, stream, pv);
+    return gemm_run_deferred(p, xmap(xm, bn), bn, out, ldo, T, stream, pv);
   }
 };
 
@@ -378,15 +379,8 @@ int Engine::alloc_all() {
   CK(cudaMemset(act, 0, static_cast<size_t>(Tcap) * I * 2));
   CK(cudaMemset(last_hidden, 0, static_cast<size_t>(Scap) * H * 2));
   CK(cudaMallocHost(&sampled_host, static_cast<size_t>(Scap) * 4));
-  // split-K workspace: in-kernel fix-up slots, or (T <= 512) one fp32 slot per stream-K segment for deferred reduction
-  size_t ws_bytes = gemm_workspace_bytes(sms);
-  {
-    const int bn_t = gemm_block_n_for(std::min(Tcap, kGemmDeferredMaxT)), bn_s = gemm_block_n_for(std::min(Scap, kGemmDeferredMaxT));
-    ws_bytes = std::max(ws_bytes, gemm_deferred_ws_bytes(QKV, H, sms, bn_t));
-    ws_bytes = std::max(ws_bytes, gemm_deferred_ws_bytes(2 * I, H, sms, bn_t));
-    ws_bytes = std::max(ws_bytes, gemm_deferred_ws_bytes(H, I, sms, bn_t));
-    ws_bytes = std::max(ws_bytes, gemm_deferred_ws_bytes(V, H, sms, bn_s));
-  }
+  // split-K workspace: 2 fp32 slots of 512 tokens x 128 rows per CTA (in-kernel fix-up slots == deferred segments)
+  size_t ws_bytes = std::max(gemm_workspace_bytes(sms), gemm_deferred_ws_bytes(sms));
   gemm_ws_bytes = ws_bytes;
   CK(cudaMalloc(&gemm_ws, ws_bytes));
   const int maxN = std::max(std::max(QKV, 2 * I), V);
@@ -399,7 +393,7 @@ int Engine::alloc_all() {
     int rc = gemm_plan_init(p, W, N, K, K, gemm_ws, gemm_counters, sms);
     if (rc) return rc;
     p->ws_bytes = gemm_ws_bytes;
-    return gemm_variant() == 2 ? gemm_plan_build_table(p) : 0;
+    return gemm_variant() == 2 ? gemm_plan_build_table(p, std::max(Tcap, Scap)) : 0;
   };
   for (int l = 0; l < L; ++l) {
     if (plan(&layers[l].p_qkv, layers[l].wqkv, QKV, H) || plan(&layers[l].p_o, layers[l].wo, H, Hq * kD) ||
@@ -501,7 +495,11 @@ int Engine::forward(const StepMeta& m, int32_t* dbuf, bool all_logits, bf16* log
   P(B200_K_EMBED); rc |= embed_gather(embed, ids, res, T, H, V, stream); Q(); launched(1);
   // T <= 512: every GEMM dumps fp32 stream-K partials and its consumer (norm / rope / silu / argmax) sums them while
   // loading — no in-GEMM reduction handshake.  Larger steps use the in-kernel fix-up and bf16 intermediates.
-  const bool dfr = deferred_ok && !all_logits && T <= kGemmDeferredMaxT && m.S <= kGemmDeferredMaxT;
+  static const int defer_max_t = [] {
+    const char* e = getenv("B200_DEFER_MAX_T");  // A/B knob: 0 disables deferred reduction
+    return e ? atoi(e) : (1 << 30);
+  }();
+  const bool dfr = deferred_ok && !all_logits && T <= defer_max_t;
   PartialView pv_x = no_partials();  // partials of the GEMM whose output is `x` (o_proj / down_proj)
   for (int l = 0; l < L && !rc; ++l) {
     Layer& ly = layers[l];
@@ -512,23 +510,23 @@ int Engine::forward(const StepMeta& m, int32_t* dbuf, bool all_logits, bf16* log
     Q();
     PartialView pv = no_partials();
     P(B200_K_GEMM_QKV);
-    if (dfr) rc |= gemm_def(ly.p_qkv, xm_normed, T, &pv); else rc |= gemm(ly.p_qkv, xm_normed, qkv, QKV, T);
+    if (dfr) rc |= gemm_def(ly.p_qkv, xm_normed, qkv, QKV, T, &pv); else rc |= gemm(ly.p_qkv, xm_normed, qkv, QKV, T);
     Q();
     P(B200_K_ROPE); rc |= rope_kv_write(qkv, pos, slots, cos_sin, kv_l, T, Hq, Hkv, cfg.max_model_len, stream, pv); Q();
     launched(2);
     if (m.nd) { P(B200_K_ATTN_DECODE); rc |= paged_attention(qkv, QKV, attn, Hq * kD, kv_l, btab, max_blocks_per_seq, dwork, m.nd, Hq, Hkv, scale, 1, stream); Q(); launched(1); }
     if (m.np) { P(B200_K_ATTN_PREFILL); rc |= paged_attention(qkv, QKV, attn, Hq * kD, kv_l, btab, max_blocks_per_seq, pwork, m.np, Hq, Hkv, scale, 0, stream); Q(); launched(1); }
     P(B200_K_GEMM_O);
-    if (dfr) rc |= gemm_def(ly.p_o, xm_attn, T, &pv_x); else rc |= gemm(ly.p_o, xm_attn, x, H, T);
+    if (dfr) rc |= gemm_def(ly.p_o, xm_attn, x, H, T, &pv_x); else rc |= gemm(ly.p_o, xm_attn, x, H, T);
     Q();
     P(B200_K_NORM); rc |= rmsnorm(x, res, ly.norm2, normed, nullptr, T, H, cfg.rms_eps, stream, pv_x); Q();
     pv = no_partials();
     P(B200_K_GEMM_GU);
-    if (dfr) rc |= gemm_def(ly.p_gu, xm_normed, T, &pv); else rc |= gemm(ly.p_gu, xm_normed, gu, 2 * I, T);
+    if (dfr) rc |= gemm_def(ly.p_gu, xm_normed, gu, 2 * I, T, &pv); else rc |= gemm(ly.p_gu, xm_normed, gu, 2 * I, T);
     Q();
     P(B200_K_SILU); rc |= silu_mul(gu, act, T, I, stream, pv); Q();
     P(B200_K_GEMM_DOWN);
-    if (dfr) rc |= gemm_def(ly.p_down, xm_act, T, &pv_x); else rc |= gemm(ly.p_down, xm_act, x, H, T);
+    if (dfr) rc |= gemm_def(ly.p_down, xm_act, x, H, T, &pv_x); else rc |= gemm(ly.p_down, xm_act, x, H, T);
     Q();
     launched(2);
   }
@@ -541,7 +539,7 @@ int Engine::forward(const StepMeta& m, int32_t* dbuf, bool all_logits, bf16* log
     P(B200_K_NORM); rc |= rmsnorm(x, res, final_norm, last_hidden, rows, m.S, H, cfg.rms_eps, stream, pv_x); Q();
     PartialView pv = no_partials();
     P(B200_K_GEMM_LM);
-    if (dfr) rc |= gemm_def(p_lm, xm_last, m.S, &pv); else rc |= gemm(p_lm, xm_last, logits, V, m.S);
+    if (dfr) rc |= gemm_def(p_lm, xm_last, logits, V, m.S, &pv); else rc |= gemm(p_lm, xm_last, logits, V, m.S);
     Q();
     P(B200_K_ARGMAX); rc |= argmax_rows(logits, sampled, m.S, V, V, stream, pv); Q();
     launched(2);

@@ -14,10 +14,12 @@ struct GemmPlan {
   float* ws;      // fp32 partial workspace, gemm_workspace_bytes(max_ctas)
   int* counters;  // 2 ints per output tile, zero-initialised, self-resetting
   int max_ctas;   // persistent grid size cap (SM count)
-  // deferred reduction (T <= 512, pair kernel): segment table for the single-token-tile schedule
-  int2* seg_table;   // device, one entry per 256-row tile: {first segment, #segments}
-  int num_segs;
-  size_t ws_bytes;   // capacity of ws
+  // deferred reduction (pair kernel): per token-tile-count schedule, {first partial segment, #segments} per tile
+  int2* seg_table;     // device; tables for ntt = 1..max_ntt concatenated
+  int table_off[65];   // offset of the ntt-th table inside seg_table (index ntt, 1-based)
+  int table_segs[65];  // partial segments the ntt-th schedule produces
+  int max_ntt;
+  size_t ws_bytes;     // capacity of ws
 };
 
 // variant 2 (default): CTA-pair kernel (gemm2_tcgen05.cu); variant 1: single-CTA kernel (gemm_tcgen05.cu)
@@ -38,13 +40,13 @@ int gemm2_x_box_rows(int block_n);
 void gemm2_set_trace(long long* dev_ptr);  // debug: 8 clock64 stamps per CTA, or nullptr
 int gemm2_run(const GemmPlan& p, const CUtensorMap& tm_x, int block_n, void* out, int ldo, int T, cudaStream_t st);
 int gemm2_units_for(const GemmPlan& p, int ntt);
-// Deferred mode: dump fp32 partials of every tile segment into p.ws (no output tensor); the consumer
-// kernel reduces them through the returned view.  Requires T <= 512 (one token tile) and variant 2.
-constexpr int kGemmDeferredMaxT = 512;
-int gemm_plan_build_table(GemmPlan* p);   // allocates/uploads seg_table (once per plan)
+// Deferred mode (variant 2): complete tiles go to `out` as bf16, split tiles stay as fp32 segments in p.ws; the
+// consumer kernel reads both through the returned view (partials.cuh).  No in-kernel reduction handshake.
+int gemm_plan_build_table(GemmPlan* p, int max_tokens);   // allocates/uploads the segment tables (once per plan)
 void gemm_plan_destroy(GemmPlan* p);
-size_t gemm_deferred_ws_bytes(int N, int K, int max_ctas, int max_block_n);
-int gemm_run_deferred(const GemmPlan& p, const CUtensorMap& tm_x, int block_n, int T, cudaStream_t st, PartialView* view);
+size_t gemm_deferred_ws_bytes(int max_ctas);
+int gemm_run_deferred(const GemmPlan& p, const CUtensorMap& tm_x, int block_n, void* out, int ldo, int T, cudaStream_t st,
+                      PartialView* view);
 // Generic consumer: out[t, n] = bf16(sum of segments) — used by tests and by paths without a fused consumer.
 int reduce_partials(const PartialView& v, void* out, int ldo, int T, int N, cudaStream_t st);
 // out[t, n] (bf16, leading dimension ldo) for t < T.

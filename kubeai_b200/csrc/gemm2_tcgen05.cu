@@ -300,13 +300,13 @@ gemm2_streamk_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_cons
 #pragma unroll
       for (int c = 0; c < C::kNch; ++c) n_eff += chunk_n(tt, c);
       const int n = (slab2 * 2 + static_cast<int>(rank)) * kSlab + row;
-      const bool complete = !deferred && (sg.kb0 == 0 && sg.kb1 == KB);
+      const bool complete = (sg.kb0 == 0 && sg.kb1 == KB);
       const int slot = (it == it_begin) ? 0 : 1;
       float* wslot;
       if (deferred) {
-        // segment index = table[tile].first + (this unit's position among the units covering the tile); ntt == 1
+        // partial segment index = table[tile].first + (this unit's position among the units sharing the tile)
         const int u0 = unit_of_iter(static_cast<long long>(sg.tile) * KB, total, units);
-        const int seg = __ldg(&seg_table[sg.tile]).x + (unit - u0);
+        const int seg = complete ? 0 : __ldg(&seg_table[sg.tile]).x + (unit - u0);
         wslot = ws + (static_cast<size_t>(seg) * 2 + rank) * kSlot;
       } else {
         wslot = ws + (static_cast<size_t>(cta) * 2 + slot) * kSlot;
@@ -529,21 +529,29 @@ __global__ void reduce_partials_kernel(PartialView v, __nv_bfloat16* __restrict_
 
 int gemm2_units_for(const GemmPlan& p, int ntt) { return units_for(p, ntt); }
 
-int gemm_plan_build_table(GemmPlan* p) {
+int gemm_plan_build_table(GemmPlan* p, int max_tokens) {
   if (p->seg_table) return 0;
   const int pairs_n = (p->N + 2 * kSlab - 1) / (2 * kSlab);
   const int KB = (p->K + kBlockK - 1) / kBlockK;
-  const long long total = static_cast<long long>(pairs_n) * KB;
-  const int units = units_for(*p, 1);
-  auto unit_of = [&](long long x) { return static_cast<int>(((x + 1) * units + total - 1) / total - 1); };
-  std::vector<int2> tab(pairs_n);
-  int seg = 0;
-  for (int j = 0; j < pairs_n; ++j) {
-    const int u0 = unit_of(static_cast<long long>(j) * KB), u1 = unit_of(static_cast<long long>(j + 1) * KB - 1);
-    tab[j] = make_int2(seg, u1 - u0 + 1);
-    seg += u1 - u0 + 1;
+  int max_ntt = (max_tokens + 511) / 512;
+  if (max_ntt < 1) max_ntt = 1;
+  if (max_ntt > 64) max_ntt = 64;
+  p->max_ntt = max_ntt;
+  std::vector<int2> tab;
+  for (int ntt = 1; ntt <= max_ntt; ++ntt) {
+    const long long total = static_cast<long long>(pairs_n) * ntt * KB;
+    const int units = units_for(*p, ntt);
+    auto unit_of = [&](long long x) { return static_cast<int>(((x + 1) * units + total - 1) / total - 1); };
+    p->table_off[ntt] = static_cast<int>(tab.size());
+    int seg = 0;
+    for (int j = 0; j < pairs_n * ntt; ++j) {
+      const int u0 = unit_of(static_cast<long long>(j) * KB), u1 = unit_of(static_cast<long long>(j + 1) * KB - 1);
+      const int nseg = u1 - u0 + 1;
+      tab.push_back(make_int2(nseg > 1 ? seg : 0, nseg));
+      if (nseg > 1) seg += nseg;
+    }
+    p->table_segs[ntt] = seg;
   }
-  p->num_segs = seg;
   if (cudaMalloc(&p->seg_table, tab.size() * sizeof(int2)) != cudaSuccess) return -7;
   if (cudaMemcpy(p->seg_table, tab.data(), tab.size() * sizeof(int2), cudaMemcpyHostToDevice) != cudaSuccess) return -7;
   return 0;
@@ -554,25 +562,35 @@ void gemm_plan_destroy(GemmPlan* p) {
   p->seg_table = nullptr;
 }
 
-size_t gemm_deferred_ws_bytes(int N, int K, int max_ctas, int max_block_n) {
-  const int pairs_n = (N + 2 * kSlab - 1) / (2 * kSlab);
-  const size_t segs = static_cast<size_t>(pairs_n) + max_ctas / 2;  // every unit boundary adds at most one segment
-  return segs * 2 * static_cast<size_t>(max_block_n) * kSlab * sizeof(float);
+// every unit has at most two partial segments (the head and the tail of its range)
+size_t gemm_deferred_ws_bytes(int max_ctas) {
+  return static_cast<size_t>(max_ctas / 2) * 2 * 2 * 512 * kSlab * sizeof(float);
 }
 
-int gemm_run_deferred(const GemmPlan& p, const CUtensorMap& tm_x, int block_n, int T, cudaStream_t st, PartialView* view) {
-  if (T <= 0 || T > kGemmDeferredMaxT || !p.seg_table) return -8;
-  const size_t need = static_cast<size_t>(p.num_segs) * 2 * block_n * kSlab * sizeof(float);
+int gemm_run_deferred(const GemmPlan& p, const CUtensorMap& tm_x, int block_n, void* out, int ldo, int T, cudaStream_t st,
+                      PartialView* view) {
+  if (T <= 0 || !p.seg_table) return -8;
+  const int ntt = (T + block_n - 1) / block_n;
+  if (ntt > 1 && block_n != 512) return -8;   // tables are built for 512-token tiles when there are several
+  if (ntt > p.max_ntt) return -8;
+  const size_t need = static_cast<size_t>(p.table_segs[ntt]) * 2 * block_n * kSlab * sizeof(float);
   if (need > p.ws_bytes) return -9;
+  GemmPlan q = p;
+  q.seg_table = p.seg_table + p.table_off[ntt];
   view->ws = p.ws;
-  view->table = p.seg_table;
+  view->table = q.seg_table;
+  view->dense = static_cast<const __nv_bfloat16*>(out);
+  view->ld_dense = ldo;
   view->slot = block_n * kSlab;
+  view->ntt = ntt;
+  view->block_n = block_n;
+  __nv_bfloat16* o = static_cast<__nv_bfloat16*>(out);
   switch (block_n) {
-    case 32: return launch2<32>(p, tm_x, nullptr, 0, T, st, 1);
-    case 64: return launch2<64>(p, tm_x, nullptr, 0, T, st, 1);
-    case 128: return launch2<128>(p, tm_x, nullptr, 0, T, st, 1);
-    case 256: return launch2<256>(p, tm_x, nullptr, 0, T, st, 1);
-    case 512: return launch2<512>(p, tm_x, nullptr, 0, T, st, 1);
+    case 32: return launch2<32>(q, tm_x, o, ldo, T, st, 1);
+    case 64: return launch2<64>(q, tm_x, o, ldo, T, st, 1);
+    case 128: return launch2<128>(q, tm_x, o, ldo, T, st, 1);
+    case 256: return launch2<256>(q, tm_x, o, ldo, T, st, 1);
+    case 512: return launch2<512>(q, tm_x, o, ldo, T, st, 1);
     default: return -6;
   }
 }

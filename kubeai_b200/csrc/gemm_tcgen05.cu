@@ -445,7 +445,7 @@ int gemm_block_n_for(int T) {
 int gemm_block_n_index(int bn) { return bn == 32 ? 0 : bn == 64 ? 1 : bn == 128 ? 2 : bn == 256 ? 3 : 4; }
 int gemm_x_box_rows(int bn) { return g_variant == 2 ? gemm2_x_box_rows(bn) : (bn > 256 ? 256 : bn); }
 
-size_t gemm_workspace_bytes(int max_ctas) {
+size_t gemm_workspace_bytes(int max_ctas) {  // in-kernel fix-up slots (2 per CTA) == deferred segments (2 per unit x 2 ranks)
   return static_cast<size_t>(max_ctas) * 2 * 512 * kSlab * sizeof(float);
 }
 
@@ -457,7 +457,7 @@ int gemm_plan_init(GemmPlan* p, const void* W, int N, int K, int ldw, float* ws,
   p->counters = counters;
   p->max_ctas = max_ctas > 0 ? max_ctas : num_sms();
   p->seg_table = nullptr;
-  p->num_segs = 0;
+  p->max_ntt = 0;
   p->ws_bytes = gemm_workspace_bytes(p->max_ctas);
   if (K % 8 != 0 || ldw % 8 != 0) return -5;
   return make_tmap(&p->tm_w, W, N, K, ldw, kSlab);

@@ -1,9 +1,12 @@
-// Deferred stream-K reduction: the pair GEMM (gemm2_tcgen05.cu) can leave every tile segment as an
-// fp32 partial in an L2-resident workspace instead of reducing in-kernel; the consumer kernel sums
-// the segments while it loads its input.  The kernel boundary is then the only synchronisation of
-// the split-K reduction (no flags, fences, spin-waits or extra round trips inside the GEMM).
-//   workspace: [segment][rank 0|1][token (slot/128)][128 weight rows] fp32
-//   table:     per 256-row tile {first segment, number of segments}
+// Deferred stream-K reduction: the pair GEMM (gemm2_tcgen05.cu) never reduces split tiles in-kernel.
+// A tile computed entirely by one CTA pair is written as bf16 to the output tensor; a tile whose
+// k-range is shared by several pairs is left as one fp32 segment per pair in an L2-resident
+// workspace.  The consumer kernel (RMSNorm, RoPE, SiLU*mul, argmax, or the generic reducer) sums the
+// segments while it loads its input, so the kernel boundary is the only synchronisation of the
+// split-K reduction: no flags, fences, spin-waits or extra round trips inside the GEMM.
+//   table:     per output tile (256 weight rows x block_n tokens) {first segment, #segments};
+//              #segments == 1 means "complete: read the bf16 tensor"
+//   workspace: [segment][rank 0|1][token in tile][128 weight rows] fp32
 // Segments are summed in index order in fp32 and rounded to bf16 once — the same rounding point as
 // a GEMM that writes bf16 (vllm linear output), so downstream numerics are unchanged.
 #pragma once
@@ -14,19 +17,35 @@
 namespace b200 {
 
 struct PartialView {
-  const float* ws;     // nullptr => the op reads its ordinary bf16 input
-  const int2* table;
-  int slot;            // floats per (segment, rank) slot = block_n * 128
+  const float* ws;               // nullptr => the op reads its ordinary bf16 input tensor
+  const int2* table;             // [slab2 * ntt + tt]
+  const __nv_bfloat16* dense;    // output tensor holding the complete tiles
+  int ld_dense;
+  int slot;                      // floats per (segment, rank) slot = block_n * 128
+  int ntt;                       // token tiles
+  int block_n;                   // tokens per tile
 };
 
-inline PartialView no_partials() { return PartialView{nullptr, nullptr, 0}; }
+inline PartialView no_partials() { return PartialView{nullptr, nullptr, nullptr, 0, 0, 1, 512}; }
 
-// Sum of all segments for token t, weight rows [n0, n0+8) (n0 % 8 == 0), rounded to bf16 precision.
+// Value of the GEMM output for token t, weight rows [n0, n0+8) (n0 % 8 == 0), as bf16-representable floats.
 __device__ __forceinline__ void load8_partials(const PartialView& v, int t, int n0, float (&o)[8]) {
-  const int tile = n0 >> 8, rank = (n0 >> 7) & 1, row = n0 & 127;
-  const int2 e = __ldg(v.table + tile);
+  const int slab2 = n0 >> 8, rank = (n0 >> 7) & 1, row = n0 & 127;
+  const int tt = t / v.block_n, tl = t - tt * v.block_n;
+  const int2 e = __ldg(v.table + slab2 * v.ntt + tt);
+  if (e.y == 1) {  // complete tile: already bf16 in the output tensor
+    const uint4 u = __ldcg(reinterpret_cast<const uint4*>(v.dense + static_cast<size_t>(t) * v.ld_dense + n0));
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __bfloat1622float2(h[j]);
+      o[2 * j] = f.x;
+      o[2 * j + 1] = f.y;
+    }
+    return;
+  }
   const size_t stride = 2 * static_cast<size_t>(v.slot);
-  const float* p = v.ws + (static_cast<size_t>(e.x) * 2 + rank) * v.slot + static_cast<size_t>(t) * 128 + row;
+  const float* p = v.ws + (static_cast<size_t>(e.x) * 2 + rank) * v.slot + static_cast<size_t>(tl) * 128 + row;
   float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
   // four segments' loads are issued before the first add (independent L2 round trips), the adds stay in
   // segment order so the result does not depend on the unrolling

@@ -25,6 +25,11 @@ fi
 if [ -n "$TRACE" ]; then
   timeout 300 python scripts/gemm_trace.py > gpurun_out/trace.log 2>&1; cat gpurun_out/trace.log
 fi
+if [ -n "$BENCH2" ]; then
+  # A/B: same bench with an environment override (e.g. B200_DEFER_MAX_T=128)
+  env $BENCH2_ENV timeout 1200 python bench.py $BENCH2 > gpurun_out/bench2.log 2> gpurun_out/bench2.err
+  echo "bench2 ($BENCH2_ENV) exit $?"; tail -c 3000 gpurun_out/bench2.log
+fi
 if [ -n "$BENCH" ]; then
   timeout 1200 python bench.py $BENCH > gpurun_out/bench.log 2> gpurun_out/bench.err
   echo "bench exit $?"; tail -c 6000 gpurun_out/bench.log; tail -n 15 gpurun_out/bench.err

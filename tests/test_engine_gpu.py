@@ -101,6 +101,24 @@ def test_continuous_batching_prefix_cache_and_chunked_prefill(oracle):
             assert st.kv_blocks_free == st.kv_blocks_total, "all KV pages must return to the pool"
 
 
+def test_large_prefill_steps_use_multi_tile_gemm(oracle):
+    """A 600-token prompt in one step (two 512-token GEMM tiles, prefill attention over 38 query tiles)."""
+    from kubeai_b200.engine import Engine, mini_config
+    rng = np.random.default_rng(11)
+    prompts = [rng.integers(0, 512, size=600).tolist(), rng.integers(0, 512, size=333).tolist()]
+    with Engine(mini_config(max_model_len=1024, max_batched_tokens=1024, num_kv_blocks=256)) as e:
+        outs = e.generate(prompts, max_tokens=6)
+    ocfg = ModelCfg(max_model_len=1024)
+    big = LlamaOracle(ocfg, make_weights(ocfg))
+    for p, o in zip(prompts, outs):
+        w, rows = big.generate(p, 6)
+        for j, (a, b) in enumerate(zip(o, w)):
+            m = torch.sort(rows[j])[0]
+            if float(m[-1] - m[-2]) < 0.25:
+                break
+            assert a == b, f"token {j}: {a} != {b}"
+
+
 def test_preemption_under_kv_pressure_keeps_outputs(oracle):
     from kubeai_b200.engine import Engine, mini_config
     rng = np.random.default_rng(5)

@@ -69,9 +69,10 @@ def test_gemm_matches_oracle(T, N, K, gemm_variant):
 
 
 @pytest.mark.parametrize("T,N,K", [(128, 4096, 4096), (1, 512, 512), (40, 768, 512), (100, 1000, 520), (384, 2048, 1024),
-                                   (512, 28672, 4096), (128, 128256, 4096), (17, 4096, 14336)])
+                                   (512, 28672, 4096), (128, 128256, 4096), (17, 4096, 14336),
+                                   (2048, 4096, 4096), (1100, 768, 512), (700, 6144, 4096)])
 def test_gemm_deferred_reduction_matches_oracle(T, N, K):
-    """The engine's T <= 512 path: fp32 stream-K partials summed by the consumer (partials.cuh)."""
+    """The engine's path: complete tiles as bf16, split tiles as fp32 stream-K segments summed by the consumer."""
     from kubeai_b200 import ops
     x, w = rnd(T, K, seed=1), rnd(N, K, scale=1 / math.sqrt(K), seed=2)
     got = ops.gemm_deferred(dev(x), dev(w))
