@@ -118,6 +118,9 @@ int b200_engine_replay(b200_engine* e, int32_t n, int32_t repeat, double* ms_tot
                        int64_t* sampled, int64_t* kv_tokens_read, int64_t* launches);
 /* Recording on (default) = each step's device inputs go to the replay ring; off = ring is frozen. */
 int b200_engine_set_recording(b200_engine* e, int32_t on);
+/* Timing aid: forward() does not launch the kernel classes in `mask` (bit 1 << B200_K_*); outputs are then garbage.
+ * Replaying the same steps with and without a class gives its marginal cost under PDL overlap. */
+int b200_engine_set_skip_mask(b200_engine* e, uint32_t mask);
 /* Kernel classes of the forward pass, for per-class device timing. */
 enum { B200_K_EMBED = 0, B200_K_NORM, B200_K_GEMM_QKV, B200_K_ROPE, B200_K_ATTN_DECODE, B200_K_ATTN_PREFILL,
        B200_K_GEMM_O, B200_K_GEMM_GU, B200_K_SILU, B200_K_GEMM_DOWN, B200_K_GEMM_LM, B200_K_ARGMAX, B200_K_NUM };

@@ -253,6 +253,7 @@ struct Engine {
   bool fatal = false;
   bool recording = true;        // when false, steps use the scratch ring slot and the recorded ones are kept
   // per-kernel-class device timing (b200_engine_profile): events around every launch of a replayed step
+  uint32_t skip_mask = 0;  // debug/timing: kernel classes (1 << B200_K_*) NOT launched by forward() (results are garbage)
   bool profiling = false;
   std::vector<std::pair<int, cudaEvent_t>> prof_events;  // (class, event) in launch order: start, stop pairs
   size_t prof_used = 0;
@@ -492,7 +493,8 @@ int Engine::forward(const StepMeta& m, int32_t* dbuf, bool all_logits, bf16* log
     cudaEventRecord(prof_events[prof_used + 1].second, stream);
     prof_used += 2;
   };
-  P(B200_K_EMBED); rc |= embed_gather(embed, ids, res, T, H, V, stream); Q(); launched(1);
+  auto on = [&](int cls) { return !(skip_mask & (1u << cls)); };
+  P(B200_K_EMBED); if (on(B200_K_EMBED)) rc |= embed_gather(embed, ids, res, T, H, V, stream); Q(); launched(1);
   // T <= 512: every GEMM dumps fp32 stream-K partials and its consumer (norm / rope / silu / argmax) sums them while
   // loading — no in-GEMM reduction handshake.  Larger steps use the in-kernel fix-up and bf16 intermediates.
   static const int defer_max_t = [] {
@@ -505,28 +507,33 @@ int Engine::forward(const StepMeta& m, int32_t* dbuf, bool all_logits, bf16* log
     Layer& ly = layers[l];
     bf16* kv_l = kv + static_cast<size_t>(l) * kv_layer_elems;
     P(B200_K_NORM);
-    if (l == 0) rc |= rmsnorm(res, nullptr, ly.norm1, normed, nullptr, T, H, cfg.rms_eps, stream);
+    if (!on(B200_K_NORM)) {}
+    else if (l == 0) rc |= rmsnorm(res, nullptr, ly.norm1, normed, nullptr, T, H, cfg.rms_eps, stream);
     else rc |= rmsnorm(x, res, ly.norm1, normed, nullptr, T, H, cfg.rms_eps, stream, pv_x);
     Q();
     PartialView pv = no_partials();
     P(B200_K_GEMM_QKV);
-    if (dfr) rc |= gemm_def(ly.p_qkv, xm_normed, qkv, QKV, T, &pv); else rc |= gemm(ly.p_qkv, xm_normed, qkv, QKV, T);
+    if (!on(B200_K_GEMM_QKV)) {}
+    else if (dfr) rc |= gemm_def(ly.p_qkv, xm_normed, qkv, QKV, T, &pv); else rc |= gemm(ly.p_qkv, xm_normed, qkv, QKV, T);
     Q();
-    P(B200_K_ROPE); rc |= rope_kv_write(qkv, pos, slots, cos_sin, kv_l, T, Hq, Hkv, cfg.max_model_len, stream, pv); Q();
+    P(B200_K_ROPE); if (on(B200_K_ROPE)) rc |= rope_kv_write(qkv, pos, slots, cos_sin, kv_l, T, Hq, Hkv, cfg.max_model_len, stream, pv); Q();
     launched(2);
-    if (m.nd) { P(B200_K_ATTN_DECODE); rc |= paged_attention(qkv, QKV, attn, Hq * kD, kv_l, btab, max_blocks_per_seq, dwork, m.nd, Hq, Hkv, scale, 1, stream); Q(); launched(1); }
-    if (m.np) { P(B200_K_ATTN_PREFILL); rc |= paged_attention(qkv, QKV, attn, Hq * kD, kv_l, btab, max_blocks_per_seq, pwork, m.np, Hq, Hkv, scale, 0, stream); Q(); launched(1); }
+    if (m.nd) { P(B200_K_ATTN_DECODE); if (on(B200_K_ATTN_DECODE)) rc |= paged_attention(qkv, QKV, attn, Hq * kD, kv_l, btab, max_blocks_per_seq, dwork, m.nd, Hq, Hkv, scale, 1, stream); Q(); launched(1); }
+    if (m.np) { P(B200_K_ATTN_PREFILL); if (on(B200_K_ATTN_PREFILL)) rc |= paged_attention(qkv, QKV, attn, Hq * kD, kv_l, btab, max_blocks_per_seq, pwork, m.np, Hq, Hkv, scale, 0, stream); Q(); launched(1); }
     P(B200_K_GEMM_O);
-    if (dfr) rc |= gemm_def(ly.p_o, xm_attn, x, H, T, &pv_x); else rc |= gemm(ly.p_o, xm_attn, x, H, T);
+    if (!on(B200_K_GEMM_O)) {}
+    else if (dfr) rc |= gemm_def(ly.p_o, xm_attn, x, H, T, &pv_x); else rc |= gemm(ly.p_o, xm_attn, x, H, T);
     Q();
-    P(B200_K_NORM); rc |= rmsnorm(x, res, ly.norm2, normed, nullptr, T, H, cfg.rms_eps, stream, pv_x); Q();
+    P(B200_K_NORM); if (on(B200_K_NORM)) rc |= rmsnorm(x, res, ly.norm2, normed, nullptr, T, H, cfg.rms_eps, stream, pv_x); Q();
     pv = no_partials();
     P(B200_K_GEMM_GU);
-    if (dfr) rc |= gemm_def(ly.p_gu, xm_normed, gu, 2 * I, T, &pv); else rc |= gemm(ly.p_gu, xm_normed, gu, 2 * I, T);
+    if (!on(B200_K_GEMM_GU)) {}
+    else if (dfr) rc |= gemm_def(ly.p_gu, xm_normed, gu, 2 * I, T, &pv); else rc |= gemm(ly.p_gu, xm_normed, gu, 2 * I, T);
     Q();
-    P(B200_K_SILU); rc |= silu_mul(gu, act, T, I, stream, pv); Q();
+    P(B200_K_SILU); if (on(B200_K_SILU)) rc |= silu_mul(gu, act, T, I, stream, pv); Q();
     P(B200_K_GEMM_DOWN);
-    if (dfr) rc |= gemm_def(ly.p_down, xm_act, x, H, T, &pv_x); else rc |= gemm(ly.p_down, xm_act, x, H, T);
+    if (!on(B200_K_GEMM_DOWN)) {}
+    else if (dfr) rc |= gemm_def(ly.p_down, xm_act, x, H, T, &pv_x); else rc |= gemm(ly.p_down, xm_act, x, H, T);
     Q();
     launched(2);
   }
@@ -1005,6 +1012,12 @@ int b200_engine_replay(b200_engine* e, int32_t n, int32_t repeat, double* ms_tot
   if (sampled) *sampled = sm;
   if (kv_tokens_read) *kv_tokens_read = kvt;
   if (launches) *launches = g.stats.kernel_launches - l0;
+  return 0;
+}
+
+int b200_engine_set_skip_mask(b200_engine* e, uint32_t mask) {
+  if (!e) { set_error("null engine"); return B200_ERR_INVALID; }
+  e->impl.skip_mask = mask;
   return 0;
 }
 

@@ -32,6 +32,7 @@ constexpr int kBlockK = 64;
 constexpr int kUmmaK = 16;
 constexpr int kThreads = 192;
 constexpr int kABytes = kSlab * kBlockK * 2;
+constexpr int kL2PrefetchBlocks = 24;  // 24 x 16 KiB of weights per CTA prefetched into L2 before the dependency resolves
 constexpr uint32_t kPeerMask = 0xFEFFFFFFu;  // clears the CTA-rank bit of a shared::cluster address -> rank 0's copy
 
 template <int BLOCK_N>
@@ -210,6 +211,15 @@ gemm2_streamk_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_cons
         if (leader) mbar_arrive_expect_tx(full_bar(pre), 2u * C::kStageBytes);
         tma_load_2d_pair(smem_base + pre * C::kStageBytes, &tm_w, full_bar(pre), kb * kBlockK,
                          (tile / ntt) * 2 * kSlab + static_cast<int>(rank) * kSlab, w_hint);
+      }
+      // ... and keep HBM busy while we wait for the activations: pull the next weight tiles of this CTA's range
+      // into L2 (up to ~0.4 MB per CTA, ~60 MB per GEMM), so the main loop starts on L2 hits.
+      {
+        int n = 0;
+        for (long long it = it_begin + pre; it < it_end && n < kL2PrefetchBlocks; ++it, ++n) {
+          const int tile = static_cast<int>(it / KB), kb = static_cast<int>(it - static_cast<long long>(tile) * KB);
+          tma_prefetch_l2_2d(&tm_w, kb * kBlockK, (tile / ntt) * 2 * kSlab + static_cast<int>(rank) * kSlab);
+        }
       }
       griddep_wait();
       mark(12);
@@ -506,8 +516,8 @@ int launch2(const GemmPlan& p, const CUtensorMap& tm_x, __nv_bfloat16* out, int 
 
 // out[t, n] = bf16(sum of the tile's segments): the generic consumer of deferred partials.
 __global__ void reduce_partials_kernel(PartialView v, __nv_bfloat16* __restrict__ out, int ldo, int T, int N) {
-  griddep_wait();
   griddep_launch();
+  griddep_wait();
   const int t = blockIdx.y;
   const int n0 = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
   if (n0 >= N) return;
@@ -584,6 +594,7 @@ int gemm_run_deferred(const GemmPlan& p, const CUtensorMap& tm_x, int block_n, v
   view->slot = block_n * kSlab;
   view->ntt = ntt;
   view->block_n = block_n;
+  view->bn_shift = block_n == 32 ? 5 : block_n == 64 ? 6 : block_n == 128 ? 7 : block_n == 256 ? 8 : 9;
   __nv_bfloat16* o = static_cast<__nv_bfloat16*>(out);
   switch (block_n) {
     case 32: return launch2<32>(q, tm_x, o, ldo, T, st, 1);

@@ -23,15 +23,16 @@ struct PartialView {
   int ld_dense;
   int slot;                      // floats per (segment, rank) slot = block_n * 128
   int ntt;                       // token tiles
-  int block_n;                   // tokens per tile
+  int block_n;                   // tokens per tile (power of two)
+  int bn_shift;                  // log2(block_n)
 };
 
-inline PartialView no_partials() { return PartialView{nullptr, nullptr, nullptr, 0, 0, 1, 512}; }
+inline PartialView no_partials() { return PartialView{nullptr, nullptr, nullptr, 0, 0, 1, 512, 9}; }
 
 // Value of the GEMM output for token t, weight rows [n0, n0+8) (n0 % 8 == 0), as bf16-representable floats.
 __device__ __forceinline__ void load8_partials(const PartialView& v, int t, int n0, float (&o)[8]) {
   const int slab2 = n0 >> 8, rank = (n0 >> 7) & 1, row = n0 & 127;
-  const int tt = t / v.block_n, tl = t - tt * v.block_n;
+  const int tt = t >> v.bn_shift, tl = t & (v.block_n - 1);
   const int2 e = __ldg(v.table + slab2 * v.ntt + tt);
   if (e.y == 1) {  // complete tile: already bf16 in the output tensor
     const uint4 u = __ldcg(reinterpret_cast<const uint4*>(v.dense + static_cast<size_t>(t) * v.ld_dense + n0));

@@ -88,6 +88,12 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const void* tmap,
       ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "l"(hint)
       : "memory");
 }
+// Prefetch a 2-D tile into L2 only (no smem, no barrier): keeps HBM streaming while the CTA waits for its inputs.
+__device__ __forceinline__ void tma_prefetch_l2_2d(const void* tmap, int32_t c0, int32_t c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(tmap)),
+               "r"(c0), "r"(c1)
+               : "memory");
+}
 // 1-D bulk copy global -> shared (no tensor map), completion on an mbarrier.
 __device__ __forceinline__ void bulk_load_1d(uint32_t dst_smem, const void* src, uint32_t bytes,
                                              uint32_t bar) {

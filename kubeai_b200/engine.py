@@ -112,6 +112,12 @@ class Engine:
     KERNEL_CLASSES = ["embed", "rmsnorm", "gemm_qkv", "rope_kvwrite", "attn_decode", "attn_prefill", "gemm_o",
                       "gemm_gate_up", "silu_mul", "gemm_down", "gemm_lm_head", "argmax"]
 
+    def set_skip_mask(self, classes=()):
+        mask = 0
+        for c in classes:
+            mask |= 1 << self.KERNEL_CLASSES.index(c)
+        check(self._l.b200_engine_set_skip_mask(self._h, mask))
+
     def set_recording(self, on: bool):
         check(self._l.b200_engine_set_recording(self._h, 1 if on else 0))
 

@@ -4,14 +4,20 @@ sys.path.insert(0, ".")
 from kubeai_b200 import lib, ops
 names = ["entry->prologue", "prologue->first tile done", "first tile->main loop+partials done", "->peers visible (spin)",
          "->bulk pull landed", "->reduce+store done", "->cluster sync+dealloc"]
-for T, N, K in [(128, 4096, 4096), (128, 6144, 4096), (128, 28672, 4096), (128, 4096, 14336), (384, 28672, 4096)]:
+DEF = len(sys.argv) > 1 and sys.argv[1] == "deferred"
+fn = ops.gemm_deferred if DEF else ops.gemm
+shapes = [(128, 4096, 4096), (128, 6144, 4096), (128, 28672, 4096), (128, 4096, 14336), (384, 28672, 4096)]
+if DEF:
+    shapes = [(128, 28672, 4096), (128, 4096, 14336), (2048, 4096, 4096), (2048, 6144, 4096), (2048, 28672, 4096), (2048, 4096, 14336)]
+for T, N, K in shapes:
     x = torch.randn(T, K, device="cuda").bfloat16()
     w = (torch.randn(N, K, device="cuda") / math.sqrt(K)).bfloat16()
     tr = torch.zeros(148, 16, dtype=torch.int64, device="cuda")
     for _ in range(3):
-        ops.gemm(x, w)
+        fn(x, w)
+    torch.cuda.synchronize()
     lib().b200_op_gemm_trace(C.c_void_p(tr.data_ptr()))
-    ops.gemm(x, w)
+    fn(x, w)
     torch.cuda.synchronize()
     lib().b200_op_gemm_trace(None)
     full = tr.cpu().double()

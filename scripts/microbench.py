@@ -90,7 +90,23 @@ def engine_bench():
     print("engine create %.1fs, kv blocks %d" % (time.time() - t0, e.stats().kv_blocks_total))
     rng = np.random.default_rng(0)
     rids = [e.submit(rng.integers(0, 128000, size=int(rng.integers(300, 500))).tolist(), max_tokens=64) for _ in range(128)]
+    groups = {"attention": ["attn_decode", "attn_prefill"], "rmsnorm": ["rmsnorm"], "rope_kvwrite": ["rope_kvwrite"], "silu_mul": ["silu_mul"],
+              "gemm_qkv": ["gemm_qkv"], "gemm_o": ["gemm_o"], "gemm_gate_up": ["gemm_gate_up"], "gemm_down": ["gemm_down"],
+              "all GEMMs": ["gemm_qkv", "gemm_o", "gemm_gate_up", "gemm_down", "gemm_lm_head"],
+              "all elementwise": ["rmsnorm", "rope_kvwrite", "silu_mul", "embed", "argmax"]}
+
+    def marginal(tag, n, rep):
+        base = e.replay(n, rep)["ms"] / (n * rep)
+        print(f"{tag} {base:.3f} ms; marginal cost when removed:")
+        for name, cls in groups.items():
+            e.set_skip_mask(cls)
+            t = e.replay(n, rep)["ms"] / (n * rep)
+            print(f"    {name:18s} {base - t:7.3f} ms")
+        e.set_skip_mask(())
+
     for i in range(60):
+        if i == 6:
+            marginal("prefill step (T=2048, steps 3-5)", 3, 3)
         ran, info = e.step()
         if i < 30 or i % 10 == 0:
             print(f"step {i:3d} T={info.tokens:5d} dec={info.decode_seqs:4d} pre={info.prefill_seqs:3d} "
@@ -100,6 +116,7 @@ def engine_bench():
     byts = 15.009e9 + r["kv_tokens"] / 24 * 131072
     print(f"replay of last 8 decode steps x3: {per:.3f} ms/step, {r['sampled'] / 24 / per * 1e3:.0f} tok/s, "
           f"alg bytes/step {byts / 1e9:.2f} GB -> {byts / per / 1e6:.0f} GB/s ({byts / per / 1e6 / PEAK:.2f} of HBM), launches/step {r['launches'] / 24:.0f}")
+    marginal("decode step", 8, 3)
     toks = e.poll(rids[0]).tokens
     print("first request tokens:", toks[:16])
     e.close()
