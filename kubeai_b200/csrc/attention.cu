@@ -41,8 +41,8 @@ paged_attn_kernel(const __nv_bfloat16* __restrict__ q, int ldq, __nv_bfloat16* _
   constexpr int NT = WT / 8;
   extern __shared__ __align__(128) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
-  griddep_launch();  // the next kernel may start its weight prefetch now; it still waits for our completion
   griddep_wait();
+  griddep_launch();
 
   const AttnWork wk = work[blockIdx.x];
   const int kvh = blockIdx.y;

@@ -32,8 +32,8 @@ __device__ __forceinline__ float warp_sum(float v) {
 // ------------------------------------------------------------------ embedding gather
 __global__ void embed_kernel(const __nv_bfloat16* __restrict__ table, const int* __restrict__ ids,
                              __nv_bfloat16* __restrict__ out, int H, int vocab) {
-  griddep_launch();  // the next kernel may start its weight prefetch now; it still waits for our completion
   griddep_wait();
+  griddep_launch();
   const int t = blockIdx.x;
   int id = ids[t];
   if (id < 0 || id >= vocab) id = 0;
@@ -49,8 +49,8 @@ template <int VPT>  // uint4 vectors per thread (H = VPT * 8 * blockDim)
 __global__ void rmsnorm_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ residual,
                                const __nv_bfloat16* __restrict__ w, __nv_bfloat16* __restrict__ out,
                                const int* __restrict__ row_index, int H, float eps, PartialView pv) {
-  griddep_launch();  // the next kernel may start its weight prefetch now; it still waits for our completion
   griddep_wait();
+  griddep_launch();
   const int s = blockIdx.x;
   const int r = row_index ? row_index[s] : s;
   const uint4* xin = reinterpret_cast<const uint4*>(x + static_cast<size_t>(r) * H);
@@ -121,8 +121,8 @@ __global__ void rmsnorm_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat1
 __global__ void rope_kv_kernel(__nv_bfloat16* __restrict__ qkv, const int* __restrict__ positions,
                                const int* __restrict__ slots, const __nv_bfloat16* __restrict__ cos_sin,
                                __nv_bfloat16* __restrict__ kv, int Hq, int Hkv, int max_pos, PartialView pv) {
-  griddep_launch();  // the next kernel may start its weight prefetch now; it still waits for our completion
   griddep_wait();
+  griddep_launch();
   constexpr int D = 128, HALF = 64;
   const int t = blockIdx.x;
   int pos = positions[t];
@@ -205,8 +205,8 @@ __global__ void rope_kv_kernel(__nv_bfloat16* __restrict__ qkv, const int* __res
 // ------------------------------------------------------------------ SiLU(gate) * up
 __global__ void silu_mul_kernel(const __nv_bfloat16* __restrict__ gu, __nv_bfloat16* __restrict__ out, int I,
                                 int ldi, PartialView pv) {
-  griddep_launch();  // the next kernel may start its weight prefetch now; it still waits for our completion
   griddep_wait();
+  griddep_launch();
   const int t = blockIdx.y;
   const uint4* g = reinterpret_cast<const uint4*>(gu + static_cast<size_t>(t) * ldi);
   const uint4* u = reinterpret_cast<const uint4*>(gu + static_cast<size_t>(t) * ldi + I);
@@ -240,8 +240,8 @@ __global__ void silu_mul_kernel(const __nv_bfloat16* __restrict__ gu, __nv_bfloa
 // ------------------------------------------------------------------ greedy argmax over bf16 logits
 __global__ void argmax_kernel(const __nv_bfloat16* __restrict__ logits, int* __restrict__ out, int V, int ld,
                               PartialView pv) {
-  griddep_launch();  // the next kernel may start its weight prefetch now; it still waits for our completion
   griddep_wait();
+  griddep_launch();
   const int s = blockIdx.x;
   const __nv_bfloat16* row = logits + static_cast<size_t>(s) * ld;
   float best = -INFINITY;

@@ -15,6 +15,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -32,7 +33,6 @@ constexpr int kBlockK = 64;
 constexpr int kUmmaK = 16;
 constexpr int kThreads = 192;
 constexpr int kABytes = kSlab * kBlockK * 2;
-constexpr int kL2PrefetchBlocks = 24;  // 24 x 16 KiB of weights per CTA prefetched into L2 before the dependency resolves
 constexpr uint32_t kPeerMask = 0xFEFFFFFFu;  // clears the CTA-rank bit of a shared::cluster address -> rank 0's copy
 
 template <int BLOCK_N>
@@ -125,7 +125,7 @@ template <int BLOCK_N>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 gemm2_streamk_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_x,
                      __nv_bfloat16* __restrict__ out, int ldo, float* __restrict__ ws, int* __restrict__ counters,
-                     int N, int T, int K, const int2* __restrict__ seg_table, int deferred,
+                     int N, int T, int K, const int2* __restrict__ seg_table, int deferred, int l2_prefetch_blocks,
                      long long* __restrict__ trace) {
   using C = Cfg2<BLOCK_N>;
   // optional phase trace (debug): 16 clock64() stamps per CTA
@@ -216,7 +216,7 @@ gemm2_streamk_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_cons
       // into L2 (up to ~0.4 MB per CTA, ~60 MB per GEMM), so the main loop starts on L2 hits.
       {
         int n = 0;
-        for (long long it = it_begin + pre; it < it_end && n < kL2PrefetchBlocks; ++it, ++n) {
+        for (long long it = it_begin + pre; it < it_end && n < l2_prefetch_blocks; ++it, ++n) {
           const int tile = static_cast<int>(it / KB), kb = static_cast<int>(it - static_cast<long long>(tile) * KB);
           tma_prefetch_l2_2d(&tm_w, kb * kBlockK, (tile / ntt) * 2 * kSlab + static_cast<int>(rank) * kSlab);
         }
@@ -483,6 +483,17 @@ gemm2_streamk_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_cons
   if (threadIdx.x == 64) mark(7);
 }
 
+// B200_L2_PREFETCH=<k-blocks>: weight tiles beyond the smem ring pulled into L2 before the dependency wait
+// (default 0: measured slower on the decode step — the extra HBM reads compete with the running attention kernel)
+int l2_prefetch_blocks() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B200_L2_PREFETCH");
+    v = e ? atoi(e) : 0;
+  }
+  return v;
+}
+
 long long* g_trace = nullptr;  // debug: device buffer of 8 stamps per CTA (b200_op_gemm_trace)
 
 int units_for(const GemmPlan& p, int ntt) {
@@ -510,14 +521,14 @@ int launch2(const GemmPlan& p, const CUtensorMap& tm_x, __nv_bfloat16* out, int 
   const int units = units_for(p, ntt);
   cudaError_t e = launch_pdl(gemm2_streamk_kernel<BLOCK_N>, dim3(2 * units), dim3(kThreads), C::kSmemBytes, st, p.tm_w, tm_x,
                              out, ldo, p.ws, p.counters, p.N, T, p.K, static_cast<const int2*>(p.seg_table), deferred,
-                             g_trace);
+                             l2_prefetch_blocks(), g_trace);
   return e == cudaSuccess ? 0 : -4;
 }
 
 // out[t, n] = bf16(sum of the tile's segments): the generic consumer of deferred partials.
 __global__ void reduce_partials_kernel(PartialView v, __nv_bfloat16* __restrict__ out, int ldo, int T, int N) {
-  griddep_launch();
   griddep_wait();
+  griddep_launch();
   const int t = blockIdx.y;
   const int n0 = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
   if (n0 >= N) return;
