@@ -9,7 +9,7 @@ e = Engine(default_config(manual_step=1, max_batched_tokens=2048, max_num_seqs=1
 rng = np.random.default_rng(0)
 for _ in range(128):
     e.submit(rng.integers(0, 128000, size=ctx).tolist(), max_tokens=16)
-for i in range(2 + (128 * ctx + 2047) // 2048):
+for i in range(5 + (128 * ctx + 2047) // 2048):
     ran, info = e.step()
     print(i, info.tokens, info.decode_seqs, info.prefill_seqs, round(info.device_us))
 e.close()
