@@ -139,6 +139,16 @@ int b200_engine_tensor_write(b200_engine* e, const char* name, const void* host_
  * the pool and returned afterwards) and copy the bf16 logits of every position to host_logits [n, vocab]. */
 int b200_engine_forward_logits(b200_engine* e, const int32_t* ids, int32_t n, void* host_logits_bf16);
 
+/* ------------------------------------------------------------------ checkpoints
+ * HF-layout Llama checkpoints: <dir>/config.json + model.safetensors[.index.json] (BF16/F16/F32 tensors).
+ * The reference mounts such a directory into the backend pod (internal/modelcontroller/model_source.go:231-287). */
+/* Fill the architecture fields of cfg from <dir>/config.json; rejects head_dim != 128 and GQA != 4:1. */
+int b200_config_from_hf(const char* dir, b200_config* cfg);
+/* Replace the seeded weights of an idle engine with the checkpoint's (q/k/v and gate/up fused on load). */
+int b200_engine_load_safetensors(b200_engine* e, const char* path);
+/* JSON listing of the tensors of a checkpoint (dir, shard index or single file); returns the length needed. */
+int64_t b200_safetensors_list(const char* path, char* buf, size_t cap);
+
 /* ------------------------------------------------------------------ router
  * Port of internal/loadbalancer group / CHWBL / LeastLoad (group.go:25-150, balance_chwbl.go:14-162,
  * balance_least_load.go:3-23).  "Endpoints" are GPU replicas; address strings are kept so the
@@ -194,6 +204,10 @@ void b200_server_destroy(b200_server* s);
 /* One request through the handler chain; path includes the "/openai" prefix.  Returns the HTTP status. */
 int b200_server_handle(b200_server* s, const char* method, const char* path, const char* content_type,
                        const char* body, size_t body_len, const b200_response_writer* writer);
+/* apiutils.ParseRequest alone (parity tests): returns 0 or the HTTP status of the error; out_json receives
+ * {"model","adapter","requested_model","prefix"} or {"error": ...}.  prefix_chars < 0 keeps the server's setting. */
+int b200_server_parse_request(b200_server* s, const char* path, const char* content_type, const char* body,
+                              size_t body_len, int32_t prefix_chars, char* out_json, size_t cap);
 /* Plain HTTP/1.1 listener in front of b200_server_handle (thread per connection, chunked SSE). port 0 = ephemeral. */
 int b200_server_listen(b200_server* s, const char* host, int32_t port, int32_t* bound_port);
 /* Prometheus text (kubeai_inference_requests_active + engine gauges); returns the full length. */

@@ -25,6 +25,7 @@ SOURCES = [
     "abi_ops.cu",
     "engine.cu",
     "router.cc",
+    "loader.cc",
     "server.cc",
     "harness.cc",
 ]

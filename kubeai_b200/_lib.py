@@ -117,6 +117,9 @@ SYMBOLS = {
     "b200_engine_tensor_read": (C.c_int, [_vp, C.c_char_p, _vp, _u64]),
     "b200_engine_tensor_write": (C.c_int, [_vp, C.c_char_p, _vp, _u64]),
     "b200_engine_forward_logits": (C.c_int, [_vp, _pi32, _i32, _vp]),
+    "b200_config_from_hf": (C.c_int, [C.c_char_p, C.POINTER(Config)]),
+    "b200_engine_load_safetensors": (C.c_int, [_vp, C.c_char_p]),
+    "b200_safetensors_list": (C.c_int64, [C.c_char_p, C.c_char_p, C.c_size_t]),
     "b200_router_create": (C.c_int, [_i32, C.POINTER(_vp)]),
     "b200_router_destroy": (None, [_vp]),
     "b200_router_set_endpoints": (C.c_int, [_vp, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p),
@@ -131,6 +134,8 @@ SYMBOLS = {
     "b200_server_destroy": (None, [_vp]),
     "b200_server_handle": (C.c_int, [_vp, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_size_t,
                                       C.POINTER(ResponseWriter)]),
+    "b200_server_parse_request": (C.c_int, [_vp, C.c_char_p, C.c_char_p, C.c_char_p, C.c_size_t, _i32, C.c_char_p,
+                                            C.c_size_t]),
     "b200_server_listen": (C.c_int, [_vp, C.c_char_p, _i32, _pi32]),
     "b200_server_metrics": (C.c_int, [_vp, C.c_char_p, C.c_size_t]),
     "b200_server_inject_fault": (C.c_int, [_vp, _i32, _i32]),

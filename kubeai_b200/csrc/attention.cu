@@ -44,8 +44,8 @@ paged_attn_kernel(const __nv_bfloat16* __restrict__ q, int ldq, __nv_bfloat16* _
   griddep_wait();
   griddep_launch();
 
-  const AttnWork wk = work[blockIdx.x];
-  const int kvh = blockIdx.y;
+  const AttnWork wk = work[blockIdx.y];  // work items are sorted longest-first; heads are the fast grid dimension
+  const int kvh = blockIdx.x;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, tq = lane & 3;
 
@@ -269,7 +269,7 @@ int paged_attention(const void* q, int ldq, void* out, int ldo, const void* kv_l
     attr_set = true;
   }
   const float scale_log2 = scale * 1.4426950408889634f;
-  dim3 grid(num_work, Hkv);
+  dim3 grid(Hkv, num_work);
   const __nv_bfloat16* qq = static_cast<const __nv_bfloat16*>(q);
   __nv_bfloat16* oo = static_cast<__nv_bfloat16*>(out);
   const __nv_bfloat16* kk = static_cast<const __nv_bfloat16*>(kv_layer);

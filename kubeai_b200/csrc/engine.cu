@@ -713,6 +713,11 @@ int Engine::step(b200_step_info* info) {
     if (p0 + n == static_cast<int>(s.toks.size())) rows.push_back(tok + n - 1);
     tok += n;
   }
+  // longest-context work first: CTAs are dispatched in blockIdx order, so the tail of the attention grid is made of
+  // the shortest sequences (LPT scheduling) instead of whatever happened to be last
+  auto longer = [](const AttnWork& a, const AttnWork& b) { return a.q_pos0 + a.q_count > b.q_pos0 + b.q_count; };
+  std::stable_sort(dwork.begin(), dwork.end(), longer);
+  std::stable_sort(pwork.begin(), pwork.end(), longer);
   m.nd = static_cast<int>(dwork.size());
   m.np = static_cast<int>(pwork.size());
   m.S = static_cast<int>(rows.size());

@@ -204,7 +204,7 @@ int parse_request(Server& sv, const std::string& path, const std::string& ctype,
     }
   }
   // r.Prefix only under PrefixHash (apiutils/request.go:219-223)
-  pr->prefix = sv.strategy == B200_LB_PREFIX_HASH ? first_n_runes(pr->prefix, sv.prefix_chars) : "";
+  pr->prefix = sv.strategy == B200_LB_PREFIX_HASH ? first_n_runes(pr->prefix, sv.prefix_chars) : "";  // firstNChars (utils.go:5-8)
   if (const JVal* v = root.get("max_completion_tokens"); v && v->type == JVal::Num) pr->max_tokens = static_cast<int>(v->num);
   if (const JVal* v = root.get("max_tokens"); v && v->type == JVal::Num) pr->max_tokens = static_cast<int>(v->num);
   if (const JVal* v = root.get("stream"); v && v->type == JVal::Bool) pr->stream = v->b;
@@ -609,6 +609,27 @@ int b200_server_handle(b200_server* s, const char* method, const char* path, con
   if (!s || !method || !path || !writer) { set_error("b200_server_handle: bad arguments"); return B200_ERR_INVALID; }
   Writer w{writer};
   return handle(s->impl, method, path, content_type ? content_type : "", body ? body : "", body ? body_len : 0, w);
+}
+
+/* apiutils.ParseRequest on its own (for parity tests against internal/apiutils/request_test.go and the Prefix tables):
+ * returns 0 or the HTTP status of the error; out_json gets {"model","adapter","requested_model","prefix"} or {"error"}. */
+int b200_server_parse_request(b200_server* s, const char* path, const char* content_type, const char* body, size_t body_len,
+                              int32_t prefix_chars, char* out_json, size_t cap) {
+  if (!s || !path || !out_json || cap == 0) { set_error("b200_server_parse_request: bad arguments"); return B200_ERR_INVALID; }
+  Server& sv = s->impl;
+  ParsedRequest pr;
+  std::string err;
+  const int saved = sv.prefix_chars;
+  if (prefix_chars >= 0) sv.prefix_chars = prefix_chars;
+  std::string p(path);
+  if (p.rfind("/openai", 0) == 0) p = p.substr(7);
+  const int st = parse_request(sv, p, content_type ? content_type : "", body ? body : "", body ? body_len : 0, &pr, &err);
+  sv.prefix_chars = saved;
+  std::string o = st ? "{\"error\":" + json_str(err) + "}"
+                     : "{\"model\":" + json_str(pr.model) + ",\"adapter\":" + json_str(pr.adapter) + ",\"requested_model\":" +
+                           json_str(pr.requested_model) + ",\"prefix\":" + json_str(pr.prefix) + "}";
+  snprintf(out_json, cap, "%s", o.c_str());
+  return st;
 }
 
 int b200_server_listen(b200_server* s, const char* host, int32_t port, int32_t* bound_port) {

@@ -22,6 +22,21 @@ def default_config(**kw) -> Config:
     return cfg
 
 
+def config_from_hf(model_dir: str, **kw) -> Config:
+    """Engine config whose architecture comes from an HF config.json."""
+    cfg = default_config(**kw)
+    check(lib().b200_config_from_hf(str(model_dir).encode(), C.byref(cfg)))
+    return cfg
+
+
+def safetensors_list(path: str) -> dict:
+    import json
+    n = check(lib().b200_safetensors_list(str(path).encode(), None, 0))
+    buf = C.create_string_buffer(n + 1)
+    lib().b200_safetensors_list(str(path).encode(), buf, n + 1)
+    return json.loads(buf.value)
+
+
 def mini_config(**kw) -> Config:
     """The 2-layer test model of oracle/weights.py ModelCfg()."""
     base = dict(num_layers=2, hidden=512, q_heads=4, kv_heads=1, intermediate=1024, vocab=512,
@@ -142,6 +157,9 @@ class Engine:
     def tensor_write(self, name: str, bits: np.ndarray):
         bits = np.ascontiguousarray(bits, dtype=np.uint16)
         check(self._l.b200_engine_tensor_write(self._h, name.encode(), bits.ctypes.data_as(C.c_void_p), bits.nbytes))
+
+    def load_safetensors(self, path: str):
+        check(self._l.b200_engine_load_safetensors(self._h, str(path).encode()))
 
     def forward_logits(self, ids) -> np.ndarray:
         """fp32 array [n, vocab] of the bf16 logits for one sequence (debug/parity)."""

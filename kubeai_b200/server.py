@@ -86,6 +86,15 @@ class Server:
             resp.status = st
         return resp
 
+    def parse_request(self, path: str, body: bytes | str, content_type: str = "application/json", prefix_chars: int = -1):
+        """(status, dict) of apiutils.ParseRequest; status 0 on success."""
+        if isinstance(body, str):
+            body = body.encode("utf-8")
+        out = C.create_string_buffer(1 << 16)
+        st = self._l.b200_server_parse_request(self._h, path.encode(), content_type.encode(), body, len(body),
+                                               prefix_chars, out, len(out))
+        return st, json.loads(out.value)
+
     def listen(self, host="127.0.0.1", port=0) -> int:
         bound = C.c_int32()
         check(self._l.b200_server_listen(self._h, host.encode(), port, C.byref(bound)))

@@ -67,9 +67,23 @@ class CpuDecodeSample:
 def measure(steps=3, warmup=1, batch=128, ctx=430, shape=None, budget_s=30.0):
     """Returns dict(tok_s, ms_per_step, cores, sample).  One 'step' = one sampled decoder layer."""
     cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
     smp = CpuDecodeSample(shape, batch, ctx)
     L = smp.s["num_layers"]
+    # use the thread count that is fastest on this host (all cores is often slower for these BLAS shapes on big
+    # multi-socket hosts): one calibration layer per candidate, best one is kept and reported as `cores`
+    cands = sorted({c for c in (cores, cores // 2, cores // 4, 32, 16, 8) if 1 <= c <= cores}, reverse=True)
+    best, best_t = cands[0], None
+    for c in cands:
+        torch.set_num_threads(c)
+        smp.layer()                      # warm
+        t0 = time.perf_counter()
+        smp.layer()
+        dt = time.perf_counter() - t0
+        if best_t is None or dt < best_t:
+            best, best_t = c, dt
+        if time.perf_counter() - t0 > budget_s / 3:
+            break
+    torch.set_num_threads(best)
     for _ in range(warmup):
         smp.layer()
     ts = []

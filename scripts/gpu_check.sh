@@ -17,6 +17,8 @@ run ops 300 tests/test_ops_gpu.py -k "not gemm and not attention"
 run attn 400 tests/test_ops_gpu.py -k attention
 run engine 600 tests/test_engine_gpu.py
 run server 400 tests/test_server_gpu.py
+run loader 300 tests/test_loader.py
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke exit $?" | tee -a gpurun_out/summary.txt; tail -2 gpurun_out/smoke.log
 cat gpurun_out/summary.txt
 if [ -n "$MICRO" ]; then
   timeout 900 python scripts/microbench.py $MICRO > gpurun_out/micro.log 2>&1

@@ -106,10 +106,76 @@ def test_harness_arithmetic_against_reference_mock_server():
     assert longest["messages"][1]["content"] == "test chunk text" * 3
 
 
-def test_prefix_extraction_tables():
-    """api/openai/v1/chat_completions_test.go:13-44, completions_test.go:14-38, utils_test.go:10-32 via the
-    observable effect: under PrefixHash the first n runes of the first user message pick the replica.
-    Exercised end-to-end in tests/test_server_gpu.py; here the rune logic through the tokenizer-free path."""
-    from kubeai_b200 import lib
-    # first_n_runes is internal; its Go-semantics are pinned through b200_xxh64 of the routed key in the GPU test.
-    assert lib().b200_xxh64(b"", 0) == 0xEF46DB3751D8E999
+@pytest.fixture()
+def psrv():
+    with Server([None], model="test-model", adapters=["test-adapter", "my-adapter", "my-adapter_extra"], strategy=PREFIX_HASH) as s:
+        yield s
+
+
+def test_chat_prefix_table(psrv):
+    """api/openai/v1/chat_completions_test.go:13-44 (bodies get a "model" because parsing starts at ParseRequest)."""
+    M = '"model": "test-model", '
+    cases = [
+        ('{%s"messages": []}', 9, ""),
+        ('{%s"messages": [{"role": "user", "content": "abc"}]}', 0, ""),
+        ('{%s"messages": [{"role": "user", "content": "abc"}]}', 9, "abc"),
+        ('{%s"messages": [{"role": "user", "content": "abcefghijk"}]}', 9, "abcefghij"),
+        ('{%s"messages": [{"role": "user", "content": "世界"}]}', 0, ""),
+        ('{%s"messages": [{"role": "user", "content": "世界"}]}', 1, "世"),
+        ('{%s"messages": [{"role": "user", "content": "世界"}]}', 2, "世界"),
+        ('{%s"messages": [{"role": "user", "content": "世界"}]}', 3, "世界"),
+        ('{%s"messages": [{"role": "user", "content": "abc"}, {"role": "user", "content": "xyz"}]}', 9, "abc"),
+        ('{%s"messages": [{"role": "system", "content": "abc"}, {"role": "user", "content": "xyz"}]}', 0, ""),
+        ('{%s"messages": [{"role": "system", "content": "abc"}, {"role": "user", "content": "xyz"}]}', 9, "xyz"),
+        ('{%s"messages": [{"role": "system", "content": "abc"}]}', 9, ""),
+        ('{%s"model2": 1}', 9, ""),                                              # no messages at all
+        # content as an array of parts is concatenated (chat_completions.go:531-536); null content is "" not a crash
+        ('{%s"messages": [{"role": "user", "content": [{"type": "text", "text": "ab"}, {"type": "text", "text": "cd"}]}]}', 3, "abc"),
+        ('{%s"messages": [{"role": "user", "content": null}]}', 3, ""),
+    ]
+    for body, n, exp in cases:
+        st, r = psrv.parse_request("/v1/chat/completions", body % M, prefix_chars=n)
+        assert st == 0 and r["prefix"] == exp, (body, n, r)
+
+
+def test_completion_prefix_table_and_first_n_chars(psrv):
+    """completions_test.go:14-38, utils_test.go:10-32, completions.go:139-164 (string | [string] | token ids)."""
+    M = '"model": "test-model"'
+    cases = [('{%s}', 9, ""), ('{%s, "prompt": "abc"}', 0, ""), ('{%s, "prompt": "abc"}', 9, "abc"),
+             ('{%s, "prompt": "abcefghijk"}', 9, "abcefghij"), ('{%s, "prompt": "世界"}', 1, "世"),
+             ('{%s, "prompt": "世界"}', 2, "世界"), ('{%s, "prompt": "世界"}', 3, "世界"),
+             ('{%s, "prompt": ["xyz", "abc"]}', 2, "xy"), ('{%s, "prompt": []}', 2, ""), ('{%s, "prompt": [1, 2, 3]}', 2, "")]
+    for body, n, exp in cases:
+        st, r = psrv.parse_request("/v1/completions", body % M, prefix_chars=n)
+        assert st == 0 and r["prefix"] == exp, (body, n, r)
+    for text, n, exp in [("", 0, ""), ("", 1, ""), ("abc", 0, ""), ("abc", 1, "a"), ("abc", 2, "ab"), ("abc", 3, "abc"),
+                         ("abc", 4, "abc"), ("世界", 1, "世"), ("世界", 2, "世界"), ("世界", 3, "世界")]:
+        st, r = psrv.parse_request("/v1/completions", json.dumps({"model": "test-model", "prompt": text}), prefix_chars=n)
+        assert r["prefix"] == exp
+
+
+def test_parse_request_and_split_model_adapter_tables(psrv):
+    """internal/apiutils/request_test.go:13-84 and model_test.go:10-78."""
+    cases = [
+        ('{"model": "test-model"}', "/v1/chat/completions", "test-model", "", ""),
+        ('{"model": "test-model_test-adapter"}', "/v1/chat/completions", "test-model", "test-adapter", ""),
+        ('{"model": "test-model", "messages": [{"role": "system", "content": "test"}]}', "/v1/chat/completions", "test-model", "", ""),
+        ('{"model": "test-model", "messages": [{"role": "user", "content": "test-prefix"}]}', "/v1/chat/completions", "test-model", "", "test-prefi"),
+        ('{"model": "test-model", "prompt": "test-prefix"}', "/v1/completions", "test-model", "", "test-prefi"),
+    ]
+    for body, path, model, adapter, prefix in cases:
+        st, r = psrv.parse_request(path, body, prefix_chars=10)
+        assert st == 0 and (r["model"], r["adapter"], r["prefix"]) == (model, adapter, prefix), (body, r)
+    # SplitModelAdapter: first "_" splits; the rest belongs to the adapter
+    st, r = psrv.parse_request("/v1/chat/completions", '{"model": "test-model_my-adapter_extra"}')
+    assert st == 0 and (r["model"], r["adapter"]) == ("test-model", "my-adapter_extra")
+    st, r = psrv.parse_request("/v1/chat/completions", '{"model": "test-model_"}')     # trailing separator: no adapter
+    assert st == 0 and (r["model"], r["adapter"]) == ("test-model", "")
+    st, r = psrv.parse_request("/v1/chat/completions", '{"model": ""}')
+    assert st == 400 and r["error"] == "bad request: reading model from body: missing 'model' field"
+    st, r = psrv.parse_request("/v1/rerank", '{"model": "test-model", "query": "q", "documents": ["d"]}')
+    assert st == 400 and "unknown path" in r["error"]     # rerank/embeddings engines are out of scope here
+    # unknown fields (vLLM extensions) never break parsing; \u escapes and surrogate pairs decode to UTF-8
+    st, r = psrv.parse_request("/v1/chat/completions", '{"model":"test-model","top_k":5,"nested":{"a":[1,2,{"b":null}]},'
+                               '"messages":[{"role":"user","content":"\\u4e16\\ud83d\\ude00x"}]}', prefix_chars=2)
+    assert st == 0 and r["prefix"] == "世😀"
