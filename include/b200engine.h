@@ -171,6 +171,9 @@ int b200_router_done(b200_router* r, uint64_t endpoint_token);
 /* group.addInFlight (group.go:147-150) on a named endpoint; used by the replayed reference tests */
 int b200_router_add_inflight(b200_router* r, const char* name, int64_t delta);
 int b200_router_inflight(b200_router* r, const char* name, int64_t* endpoint_inflight, int64_t* total_inflight);
+/* Prometheus text of the hash-lookup metrics (internal/metrics/metrics.go:19-26,51-76: iterations histogram with
+ * buckets 1..1024, per-endpoint initial/final/default counters); returns the length needed. */
+int64_t b200_router_metrics(b200_router* r, char* buf, size_t cap);
 /* cespare/xxhash v1.1.0 Sum64 (seed 0) as used at balance_chwbl.go:140-142 */
 uint64_t b200_xxh64(const void* data, size_t len);
 

@@ -129,6 +129,7 @@ SYMBOLS = {
     "b200_router_done": (C.c_int, [_vp, _u64]),
     "b200_router_add_inflight": (C.c_int, [_vp, C.c_char_p, _i64]),
     "b200_router_inflight": (C.c_int, [_vp, C.c_char_p, C.POINTER(_i64), C.POINTER(_i64)]),
+    "b200_router_metrics": (C.c_int64, [_vp, C.c_char_p, C.c_size_t]),
     "b200_xxh64": (_u64, [_vp, C.c_size_t]),
     "b200_server_create": (C.c_int, [C.POINTER(ServerConfig), C.POINTER(_vp), _i32, C.POINTER(_vp)]),
     "b200_server_destroy": (None, [_vp]),

@@ -7,6 +7,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <array>
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
@@ -47,8 +48,22 @@ struct Router {
   std::mutex tmtx;
   std::vector<std::shared_ptr<std::atomic<int64_t>>> counters;  // token -> in-flight counter (outlives endpoints)
 
-  // metrics (internal/metrics/metrics.go:19-26)
+  // metrics (internal/metrics/metrics.go:16-76): iterations histogram (buckets 1..1024) and per-endpoint
+  // initial / final / default counters, emitted where balance_chwbl.go:24-26,58-61,74-80 emits them
   std::atomic<int64_t> lookups{0}, lookup_iterations{0}, lookup_defaults{0};
+  std::atomic<int64_t> iter_hist[12] = {};  // le 1,2,4,...,1024,+Inf (non-cumulative)
+  std::mutex emtx;
+  std::map<std::string, std::array<int64_t, 3>> ep_metrics;  // endpoint -> {initial, final, default}
+  void count_ep(const std::string& name, int which) {
+    std::lock_guard<std::mutex> lk(emtx);
+    ++ep_metrics[name][which];
+  }
+  void observe_iterations(int64_t n) {
+    lookup_iterations.fetch_add(n, std::memory_order_relaxed);
+    int b = 0;
+    while (b < 11 && n > (1ll << b)) ++b;
+    iter_hist[b].fetch_add(1, std::memory_order_relaxed);
+  }
 
   static uint64_t hash(const std::string& s) { return xxh64(s.data(), s.size(), 0); }
   // chwblEndpointReplicaHashInput: fmt.Sprintf("%s%d", name, replica)
@@ -81,7 +96,9 @@ struct Router {
     size_t i = std::lower_bound(chwbl_sorted.begin(), chwbl_sorted.end(), h) - chwbl_sorted.begin();
     if (i >= chwbl_sorted.size()) i = 0;
     lookups.fetch_add(1, std::memory_order_relaxed);
+    count_ep(chwbl_hashes[chwbl_sorted[i]], 0);
     const RouterEndpoint* def = nullptr;
+    std::string def_name;
     for (size_t n = 0; n < chwbl_sorted.size(); ++n) {
       const std::string& name = chwbl_hashes[chwbl_sorted[i]];
       auto it = endpoints.find(name);
@@ -92,17 +109,23 @@ struct Router {
       const RouterEndpoint& ep = it->second;
       const bool match = adapter.empty() || ep.adapters.count(adapter);
       if (match) {
-        if (!def) def = &ep;
+        if (!def) {
+          def = &ep;
+          def_name = name;
+        }
         if (load_ok(ep.in_flight->load(), total_in_flight.load(), static_cast<int>(endpoints.size()), factor)) {
-          lookup_iterations.fetch_add(static_cast<int64_t>(n + 1), std::memory_order_relaxed);
+          observe_iterations(static_cast<int64_t>(n + 1));
+          count_ep(name, 1);
           return &ep;
         }
       }
       if (++i >= chwbl_sorted.size()) i = 0;
     }
     if (def) {
-      lookup_iterations.fetch_add(static_cast<int64_t>(chwbl_sorted.size()), std::memory_order_relaxed);
+      observe_iterations(static_cast<int64_t>(chwbl_sorted.size()));
       lookup_defaults.fetch_add(1, std::memory_order_relaxed);
+      count_ep(def_name, 1);
+      count_ep(def_name, 2);
     }
     return def;
   }
@@ -274,6 +297,29 @@ int b200_router_add_inflight(b200_router* r, const char* name, int64_t delta) {
   g.total_in_flight.fetch_add(delta);
   it->second.in_flight->fetch_add(delta);
   return 0;
+}
+
+/* Prometheus text of the hash-lookup instruments (names as OtelNameToPromName would render them). */
+int64_t b200_router_metrics(b200_router* r, char* buf, size_t cap) {
+  if (!r) { set_error("null router"); return B200_ERR_INVALID; }
+  Router& g = r->impl;
+  std::string o = "# TYPE kubeai_inference_requests_hash_lookup_iterations histogram\n";
+  int64_t cum = 0;
+  for (int b = 0; b < 12; ++b) {
+    cum += g.iter_hist[b].load();
+    o += "kubeai_inference_requests_hash_lookup_iterations_bucket{le=\"" + (b < 11 ? std::to_string(1 << b) : std::string("+Inf")) + "\"} " + std::to_string(cum) + "\n";
+  }
+  o += "kubeai_inference_requests_hash_lookup_iterations_sum " + std::to_string(g.lookup_iterations.load()) + "\n";
+  o += "kubeai_inference_requests_hash_lookup_iterations_count " + std::to_string(cum) + "\n";
+  static const char* kinds[3] = {"initial", "final", "default"};
+  std::lock_guard<std::mutex> lk(g.emtx);
+  for (int k = 0; k < 3; ++k) {
+    o += std::string("# TYPE kubeai_inference_requests_hash_lookup_") + kinds[k] + " counter\n";
+    for (auto& kv : g.ep_metrics)
+      if (kv.second[k]) o += std::string("kubeai_inference_requests_hash_lookup_") + kinds[k] + "{endpoint=\"" + kv.first + "\"} " + std::to_string(kv.second[k]) + "\n";
+  }
+  if (buf && cap > o.size()) memcpy(buf, o.c_str(), o.size() + 1);
+  return static_cast<int64_t>(o.size());
 }
 
 int b200_router_inflight(b200_router* r, const char* name, int64_t* endpoint_inflight, int64_t* total_inflight) {

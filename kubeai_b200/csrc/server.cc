@@ -382,6 +382,15 @@ static std::string metrics_text(Server& sv) {
     for (auto& kv : sv.active)
       o += "kubeai_inference_requests_active{request_model=" + json_str(kv.first) + ",request_type=\"http\"} " + std::to_string(kv.second) + "\n";
   }
+  {
+    const int64_t n = b200_router_metrics(sv.router, nullptr, 0);
+    if (n > 0) {
+      std::string rm(static_cast<size_t>(n) + 1, '\0');
+      b200_router_metrics(sv.router, &rm[0], rm.size());
+      rm.resize(static_cast<size_t>(n));
+      o += rm;
+    }
+  }
   o += "# TYPE b200_requests_total counter\nb200_requests_total " + std::to_string(sv.requests_total.load()) + "\n";
   o += "# TYPE b200_request_retries_total counter\nb200_request_retries_total " + std::to_string(sv.retries_total.load()) + "\n";
   for (size_t i = 0; i < sv.replicas.size(); ++i) {

@@ -54,6 +54,12 @@ class Router:
     def add_in_flight(self, name: str, delta: int):
         check(self._l.b200_router_add_inflight(self._h, name.encode(), delta))
 
+    def metrics(self) -> str:
+        n = self._l.b200_router_metrics(self._h, None, 0)
+        buf = C.create_string_buffer(n + 1)
+        self._l.b200_router_metrics(self._h, buf, n + 1)
+        return buf.value.decode()
+
     def in_flight(self, name: str | None = None):
         ep, tot = C.c_int64(), C.c_int64()
         check(self._l.b200_router_inflight(self._h, name.encode() if name else None, C.byref(ep), C.byref(tot)))

@@ -233,3 +233,21 @@ def test_blocked_request_wakes_when_endpoint_appears():
     r.reconcile_endpoints({"gpu-1": dict(address="10.9.9.8:1")})
     got["done"]()
     assert r.in_flight()[1] == 0
+
+
+def test_hash_lookup_metrics_follow_the_reference_instruments():
+    """internal/metrics/metrics.go:19-26,51-76 emitted at balance_chwbl.go:24-26,58-61,74-80."""
+    r = Router(1)
+    r.reconcile_endpoints({"pod-a-1": dict(address=A1), "pod-a-2": dict(address=A2)})
+    r.add_in_flight("pod-a-1", 10)
+    r.add_in_flight("pod-a-2", 10)
+    dones = [r.await_best_address(PREFIX_HASH, "", "pod-a-10", 150, timeout_s=0)[1] for _ in range(25)]
+    m = r.metrics()
+    # 25 lookups start at pod-a-1; 24 stay there (threshold table load_balancer_test.go:299-346), one walks to pod-a-2
+    assert 'kubeai_inference_requests_hash_lookup_initial{endpoint="pod-a-1"} 25' in m
+    assert 'kubeai_inference_requests_hash_lookup_final{endpoint="pod-a-1"} 24' in m
+    assert 'kubeai_inference_requests_hash_lookup_final{endpoint="pod-a-2"} 1' in m
+    assert 'kubeai_inference_requests_hash_lookup_iterations_bucket{le="1"} 24' in m
+    assert 'kubeai_inference_requests_hash_lookup_iterations_bucket{le="2"} 25' in m
+    assert "kubeai_inference_requests_hash_lookup_iterations_sum 26" in m and "hash_lookup_default{" not in m
+    [d() for d in dones]
