@@ -56,7 +56,8 @@ def _digest(paths) -> str:
 
 def build(force: bool = False, verbose: bool = False) -> Path:
     srcs = [CSRC / s for s in SOURCES if (CSRC / s).exists()]
-    deps = list(CSRC.glob("*.h")) + list(CSRC.glob("*.cuh")) + [ROOT.parent / "include" / "b200engine.h"]
+    deps = list(CSRC.glob("*.h")) + list(CSRC.glob("*.cuh")) + [ROOT.parent / "include" / "b200engine.h"] + \
+        list((ROOT.parent / "cmd").glob("*.cc"))
     stamp = OBJ / "digest.txt"
     digest = _digest(srcs + deps)
     if not force and LIB.exists() and stamp.exists() and stamp.read_text() == digest:
@@ -80,6 +81,18 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    # the two process entry points (cmd/): server and load generator, linked against the library
+    bindir = ROOT / "bin"
+    bindir.mkdir(exist_ok=True)
+    for name in ("b200serve", "b200bench"):
+        src = ROOT.parent / "cmd" / f"{name}.cc"
+        if not src.exists():
+            continue
+        cmd = [nvcc, "-O2", "-std=c++17", "-x", "cu", str(src), "-o", str(bindir / name), "-L", str(LIB.parent),
+               "-lb200engine", "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN/../lib", "-lcudart", "-lpthread"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"building {name} failed:\n{r.stdout}\n{r.stderr}")
     stamp.write_text(digest)
     return LIB
 

@@ -11,6 +11,8 @@ namespace b200 {
 struct GemmPlan {
   CUtensorMap tm_w;  // weight [N, K] bf16, box 128 x 64, 128B swizzle
   int N, K;
+  const void* w_ptr;  // same tensor, raw pointer (L2 prefetch)
+  int ldw;
   float* ws;      // fp32 partial workspace, gemm_workspace_bytes(max_ctas)
   int* counters;  // 2 ints per output tile, zero-initialised, self-resetting
   int max_ctas;   // persistent grid size cap (SM count)

@@ -453,6 +453,8 @@ int gemm_plan_init(GemmPlan* p, const void* W, int N, int K, int ldw, float* ws,
   memset(p, 0, sizeof(*p));
   p->N = N;
   p->K = K;
+  p->w_ptr = W;
+  p->ldw = ldw;
   p->ws = ws;
   p->counters = counters;
   p->max_ctas = max_ctas > 0 ? max_ctas : num_sms();

@@ -79,3 +79,42 @@ def test_engine_loaded_from_hf_checkpoint_matches_golden(tmp_path, sharded, dtyp
         err = np.abs(got - ref)
         assert (err <= 0.15 + 1.6e-2 * np.abs(ref)).all(), err.max()
         assert e.generate([GOLD["ids"].tolist()], max_tokens=12)[0] == GOLD["greedy"].tolist()
+
+
+@pytest.mark.gpu
+def test_b200serve_and_b200bench_processes_end_to_end(tmp_path):
+    """The two process entry points (cmd/): an HTTP server over a checkpoint-loaded engine, driven by the load generator
+    binary — the standalone equivalent of `kubeai` + `benchmarks/multi-turn-chat-go`."""
+    import re
+    import subprocess
+    import time
+    import urllib.request
+    from kubeai_b200._lib import LIB_PATH
+    bindir = LIB_PATH.parent.parent / "bin"
+    _write_checkpoint(tmp_path, sharded=False)
+    srv = subprocess.Popen([str(bindir / "b200serve"), "--gpus", "1", "--model", "mini", "--model-dir", str(tmp_path), "--port", "0",
+                            "--host", "127.0.0.1", "--max-model-len", "1024", "--max-num-batched-tokens", "512", "--max-num-seqs", "16",
+                            "--gpu-memory-utilization", "0.05", "--strategy", "PrefixHash"], stderr=subprocess.PIPE, text=True)
+    try:
+        port = None
+        t0 = time.time()
+        while time.time() - t0 < 120:
+            line = srv.stderr.readline()
+            m = re.search(r"on http://127.0.0.1:(\d+)/", line or "")
+            if m:
+                port = int(m.group(1))
+                break
+            assert srv.poll() is None, line
+        assert port, "b200serve did not come up"
+        models = json.loads(urllib.request.urlopen(f"http://127.0.0.1:{port}/openai/v1/models", timeout=10).read())
+        assert models["data"][0]["id"] == "mini"
+        out = subprocess.run([str(bindir / "b200bench"), "--base-url", f"http://127.0.0.1:{port}/openai", "--request-model", "mini",
+                              "--synthetic-threads", "5", "--synthetic-words", "6", "--vocab", "512", "--max-concurrent-threads", "3",
+                              "--max-completion-tokens", "5", "--seed", "2"], capture_output=True, text=True, timeout=120)
+        assert out.returncode == 0, out.stdout + out.stderr
+        assert "Failed thread count: 0" in out.stdout and re.search(r"Chunks per request \(mean\): 5\.00", out.stdout)
+        metrics = urllib.request.urlopen(f"http://127.0.0.1:{port}/metrics", timeout=10).read().decode()
+        assert "kubeai_inference_requests_hash_lookup_final" in metrics and "b200_engine_generated_tokens_total" in metrics
+    finally:
+        srv.terminate()
+        srv.wait(20)
