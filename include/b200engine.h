@@ -112,6 +112,11 @@ int b200_stats_get(b200_engine* e, b200_stats* out);
 
 /* manual_step mode: run one scheduler iteration + forward; *info may be NULL. Returns 1 if a step ran, 0 if idle. */
 int b200_engine_step(b200_engine* e, b200_step_info* info);
+/* manual_step mode: up to max_steps iterations back to back on the calling thread, pipelined the way the engine's own
+ * loop thread runs: the tokens of step N are handed to the waiting API threads after step N+1 has been enqueued on the
+ * GPU.  Returns when max_steps steps ran or the engine had nothing to run for idle_timeout_us.  infos (optional) gets
+ * one entry per step, *n_done the number of steps that ran. */
+int b200_engine_run(b200_engine* e, int32_t max_steps, int64_t idle_timeout_us, b200_step_info* infos, int32_t* n_done);
 /* Re-run the forward passes of the last `n` recorded steps from their HBM-resident inputs,
  * `repeat` times back to back; returns CUDA-event milliseconds and what those steps carried. */
 int b200_engine_replay(b200_engine* e, int32_t n, int32_t repeat, double* ms_total, int64_t* tokens,
@@ -282,6 +287,14 @@ int b200_op_argmax(const void* logits, int32_t* out, int32_t S, int32_t V, int32
 int b200_op_paged_attn(const void* q, int32_t ldq, void* out, int32_t ldo, const void* kv_layer,
                        const int32_t* block_tables, int32_t max_blocks, const int32_t* work, int32_t num_work,
                        int32_t q_heads, int32_t kv_heads, float scale, int32_t decode, void* stream);
+/* Decode attention with RoPE + KV write fused in (K5 + K6 in one launch; every work item has q_count == 1): reads the
+ * un-rotated q|k|v rows of `qkv`, writes the rotated k and v into kv_layer at the token's page slot
+ * (block_tables[seq][pos >> 4], pos & 15) and attends over [0, pos].  Bit-identical to b200_op_rope_kvwrite followed by
+ * b200_op_paged_attn(decode=1); `qkv` itself is left un-rotated. */
+int b200_op_paged_attn_rope_decode(const void* qkv, int32_t ldq, void* out, int32_t ldo, void* kv_layer,
+                                   const int32_t* block_tables, int32_t max_blocks, const int32_t* work,
+                                   int32_t num_work, int32_t q_heads, int32_t kv_heads, float scale,
+                                   const void* cos_sin, int32_t max_pos, void* stream);
 int b200_op_init_uniform(void* p, uint64_t n, uint32_t seed, float scale, float offset, void* stream);
 
 #ifdef __cplusplus

@@ -107,6 +107,7 @@ SYMBOLS = {
     "b200_release": (C.c_int, [_vp, _u64]),
     "b200_stats_get": (C.c_int, [_vp, C.POINTER(Stats)]),
     "b200_engine_step": (C.c_int, [_vp, C.POINTER(StepInfo)]),
+    "b200_engine_run": (C.c_int, [_vp, _i32, _i64, C.POINTER(StepInfo), C.POINTER(_i32)]),
     "b200_engine_replay": (C.c_int, [_vp, _i32, _i32, C.POINTER(C.c_double), C.POINTER(_i64), C.POINTER(_i64),
                                       C.POINTER(_i64), C.POINTER(_i64)]),
     "b200_engine_reset_prefix_cache": (C.c_int, [_vp]),
@@ -156,6 +157,8 @@ SYMBOLS = {
     "b200_op_silu_mul": (C.c_int, [_vp, _vp, _i32, _i32, _vp]),
     "b200_op_argmax": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp]),
     "b200_op_paged_attn": (C.c_int, [_vp, _i32, _vp, _i32, _vp, _vp, _i32, _vp, _i32, _i32, _i32, _f, _i32, _vp]),
+    "b200_op_paged_attn_rope_decode": (C.c_int, [_vp, _i32, _vp, _i32, _vp, _vp, _i32, _vp, _i32, _i32, _i32, _f, _vp,
+                                                 _i32, _vp]),
     "b200_op_init_uniform": (C.c_int, [_vp, _u64, C.c_uint32, _f, _f, _vp]),
 }
 

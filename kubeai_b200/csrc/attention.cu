@@ -20,6 +20,7 @@
 
 #include "kernels.h"
 #include "launch.h"
+#include "partials.cuh"
 #include "ptx.cuh"
 
 namespace b200 {
@@ -31,19 +32,36 @@ constexpr int kTile = 64;                       // tokens per smem tile
 constexpr int kTileBytes = kTile * kD * 2;      // 16 KiB for K, same for V
 constexpr int kStageBytes = 2 * kTileBytes;     // K + V
 constexpr int kAttnSmem = 2 * kStageBytes;      // double buffered: 64 KiB
+constexpr int kFusedStage = (4 + 2) * kD * 2;   // fused decode: rotated q (4 heads), new k, new v rows (bf16)
 
-template <bool DECODE>
+__constant__ int c_early_trigger = 0;  // B200_EARLY_TRIGGER (see griddep_enter)
+
+struct Vec8 {
+  union {
+    uint4 u;
+    __nv_bfloat16 h[8];
+  };
+};
+
+// FUSED (decode only): the kernel also does this token's RoPE + KV write (K5), reading q|k|v straight from the
+// QKV GEMM's output (bf16 or deferred fp32 partials): q is rotated into smem, the new k/v row goes to the paged
+// cache for later steps and is patched into the last smem tile for this one — one launch fewer per layer, and the
+// gather of the cached context starts before the QKV GEMM has drained (those pages were written by earlier steps).
+template <bool DECODE, bool FUSED>
 __global__ void __launch_bounds__(128)  // 178 regs -> 2 CTAs/SM; forcing 3 (168 regs, spills) measured no faster
 paged_attn_kernel(const __nv_bfloat16* __restrict__ q, int ldq, __nv_bfloat16* __restrict__ out, int ldo,
-                  const __nv_bfloat16* __restrict__ kv, const int* __restrict__ block_tables, int max_blocks,
-                  const AttnWork* __restrict__ work, int Hkv, float scale_log2) {
+                  __nv_bfloat16* __restrict__ kv, const int* __restrict__ block_tables, int max_blocks,
+                  const AttnWork* __restrict__ work, int Hkv, float scale_log2,
+                  const __nv_bfloat16* __restrict__ cos_sin, int max_pos, PartialView pv) {
+  static_assert(DECODE || !FUSED, "the fused RoPE/KV-write prologue exists for decode only");
   constexpr int WT = DECODE ? 16 : 64;  // tokens of each tile handled by one warp
   constexpr int NT = WT / 8;
   extern __shared__ __align__(128) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
-  griddep_wait();
-  griddep_launch();
+  if (!FUSED) griddep_enter(c_early_trigger);
 
+  // FUSED: work[] and block_tables were uploaded before the first kernel of the step, i.e. at least three kernels
+  // upstream, so they (and every cached page) are safe to read ahead of griddepcontrol.wait.
   const AttnWork wk = work[blockIdx.y];  // work items are sorted longest-first; heads are the fast grid dimension
   const int kvh = blockIdx.x;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -55,9 +73,105 @@ paged_attn_kernel(const __nv_bfloat16* __restrict__ q, int ldq, __nv_bfloat16* _
   const size_t head_page = static_cast<size_t>(16) * kD;            // elements per (page, head)
   const size_t kv_page = static_cast<size_t>(Hkv) * head_page;      // elements per K (or V) page
 
+  // tokens [0, kv_stored) are gathered from the paged cache; FUSED keeps the newest one in smem instead
+  const int kv_stored = FUSED ? kv_end - 1 : kv_end;
+  auto load_tile = [&](int tile, int stage) {
+    const uint32_t kdst = sbase + stage * kStageBytes;
+    const uint32_t vdst = kdst + kTileBytes;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int r = j * 8 + (tid >> 4);  // token row inside the tile
+      const int cc = tid & 15;           // 16-byte chunk inside the 256-byte row
+      const int tok = tile * kTile + r;
+      const bool valid = tok < kv_stored;
+      const int blk = valid ? __ldg(btab + (tok >> 4)) : 0;
+      const __nv_bfloat16* ksrc =
+          kv + (static_cast<size_t>(blk) * 2) * kv_page + kvh * head_page + (tok & 15) * kD + cc * 8;
+      const uint32_t off = r * 256 + ((cc ^ (r & 7)) << 4);
+      cp_async_16(kdst + off, ksrc, valid);
+      cp_async_16(vdst + off, ksrc + kv_page, valid);
+    }
+  };
+  load_tile(0, 0);
+  cp_async_commit();
+
   // ---- Q fragments (A operand, 16 rows x 128 d as 8 k-steps)
   uint32_t qf[8][4];
-  {
+  if (FUSED) {
+    __nv_bfloat16* stg = reinterpret_cast<__nv_bfloat16*>(smem + kAttnSmem);  // [4 q heads | k | v][128]
+    griddep_enter(c_early_trigger);
+    const int Hq = 4 * Hkv, HALF = kD / 2;
+    const int t = wk.q_tok0;
+    const int posr = wk.q_pos0;
+    const int pos = posr < 0 ? 0 : (posr >= max_pos ? max_pos - 1 : posr);
+    const int blk = __ldg(btab + (posr >> 4));
+    __nv_bfloat16* kdst = kv + (static_cast<size_t>(blk) * 2) * kv_page + kvh * head_page + (posr & 15) * kD;
+    if (tid < 40) {  // 5 heads (4 q + k) x 8 rotation tasks; arithmetic identical to rope_kv_kernel (elementwise.cu)
+      const int h5 = tid >> 3, c = tid & 7;
+      const int col = (h5 < 4 ? kvh * 4 + h5 : Hq + kvh) * kD;
+      float xa[8], xb[8];
+      if (pv.ws) {
+        load8_partials(pv, t, col + c * 8, xa);
+        load8_partials(pv, t, col + HALF + c * 8, xb);
+      } else {
+        Vec8 x1, x2;
+        const __nv_bfloat16* hp = q + static_cast<size_t>(t) * ldq + col;
+        x1.u = *reinterpret_cast<const uint4*>(hp + c * 8);
+        x2.u = *reinterpret_cast<const uint4*>(hp + HALF + c * 8);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          xa[j] = __bfloat162float(x1.h[j]);
+          xb[j] = __bfloat162float(x2.h[j]);
+        }
+      }
+      Vec8 co, si, o1, o2;
+      const __nv_bfloat16* cs = cos_sin + static_cast<size_t>(pos) * kD;
+      co.u = __ldg(reinterpret_cast<const uint4*>(cs + c * 8));
+      si.u = __ldg(reinterpret_cast<const uint4*>(cs + HALF + c * 8));
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float a = xa[j], b = xb[j];
+        const float cc = __bfloat162float(co.h[j]), sn = __bfloat162float(si.h[j]);
+        const float ac = __bfloat162float(__float2bfloat16_rn(__fmul_rn(a, cc)));
+        const float bs = __bfloat162float(__float2bfloat16_rn(__fmul_rn(b, sn)));
+        const float bc = __bfloat162float(__float2bfloat16_rn(__fmul_rn(b, cc)));
+        const float as = __bfloat162float(__float2bfloat16_rn(__fmul_rn(a, sn)));
+        o1.h[j] = __float2bfloat16_rn(ac - bs);
+        o2.h[j] = __float2bfloat16_rn(bc + as);
+      }
+      *reinterpret_cast<uint4*>(stg + h5 * kD + c * 8) = o1.u;
+      *reinterpret_cast<uint4*>(stg + h5 * kD + HALF + c * 8) = o2.u;
+      if (h5 == 4) {
+        *reinterpret_cast<uint4*>(kdst + c * 8) = o1.u;
+        *reinterpret_cast<uint4*>(kdst + HALF + c * 8) = o2.u;
+      }
+    } else if (tid < 56) {  // the v row: 16 chunks
+      const int c = tid - 40;
+      const int col = (Hq + Hkv + kvh) * kD + c * 8;
+      uint4 val;
+      if (pv.ws) {
+        float f[8];
+        load8_partials(pv, t, col, f);
+        val.x = pack_bf16x2(f[0], f[1]);
+        val.y = pack_bf16x2(f[2], f[3]);
+        val.z = pack_bf16x2(f[4], f[5]);
+        val.w = pack_bf16x2(f[6], f[7]);
+      } else {
+        val = *reinterpret_cast<const uint4*>(q + static_cast<size_t>(t) * ldq + col);
+      }
+      *reinterpret_cast<uint4*>(stg + 5 * kD + c * 8) = val;
+      *reinterpret_cast<uint4*>(kdst + kv_page + c * 8) = val;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks) {
+      const int d = ks * 16 + tq * 2;
+      qf[ks][0] = g < 4 ? *reinterpret_cast<const uint32_t*>(stg + g * kD + d) : 0u;
+      qf[ks][1] = 0u;
+      qf[ks][2] = g < 4 ? *reinterpret_cast<const uint32_t*>(stg + g * kD + d + 8) : 0u;
+      qf[ks][3] = 0u;
+    }
+  } else {
     const __nv_bfloat16* r0p = nullptr;
     const __nv_bfloat16* r1p = nullptr;
     if (DECODE) {
@@ -77,36 +191,28 @@ paged_attn_kernel(const __nv_bfloat16* __restrict__ q, int ldq, __nv_bfloat16* _
     }
   }
 
-  auto load_tile = [&](int tile, int stage) {
-    const uint32_t kdst = sbase + stage * kStageBytes;
-    const uint32_t vdst = kdst + kTileBytes;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int r = j * 8 + (tid >> 4);  // token row inside the tile
-      const int cc = tid & 15;           // 16-byte chunk inside the 256-byte row
-      const int tok = tile * kTile + r;
-      const bool valid = tok < kv_end;
-      const int blk = valid ? __ldg(btab + (tok >> 4)) : 0;
-      const __nv_bfloat16* ksrc =
-          kv + (static_cast<size_t>(blk) * 2) * kv_page + kvh * head_page + (tok & 15) * kD + cc * 8;
-      const uint32_t off = r * 256 + ((cc ^ (r & 7)) << 4);
-      cp_async_16(kdst + off, ksrc, valid);
-      cp_async_16(vdst + off, ksrc + kv_page, valid);
-    }
-  };
-
   float o[16][4];
 #pragma unroll
   for (int i = 0; i < 16; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
   float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
   const int wo = DECODE ? warp * 16 : 0;  // this warp's token offset inside a tile
 
-  load_tile(0, 0);
-  cp_async_commit();
   for (int t = 0; t < ntiles; ++t) {
     if (t + 1 < ntiles) load_tile(t + 1, (t + 1) & 1);
     cp_async_commit();
     cp_async_wait<1>();
+    if (FUSED && t == ntiles - 1) {
+      // the newest token's k/v row lives in the staging area: the thread that zero-filled its chunk overwrites it
+      const int r = kv_end - 1 - t * kTile;
+      if ((r & 7) == (tid >> 4)) {
+        const int cc = tid & 15;
+        const uint8_t* stg = smem + kAttnSmem + 4 * kD * 2;
+        uint8_t* kt = smem + (t & 1) * kStageBytes;
+        const uint32_t off = r * 256 + ((cc ^ (r & 7)) << 4);
+        *reinterpret_cast<uint4*>(kt + off) = *reinterpret_cast<const uint4*>(stg + cc * 16);
+        *reinterpret_cast<uint4*>(kt + kTileBytes + off) = *reinterpret_cast<const uint4*>(stg + kD * 2 + cc * 16);
+      }
+    }
     __syncthreads();
 
     const int tok_base = t * kTile + wo;
@@ -254,31 +360,57 @@ paged_attn_kernel(const __nv_bfloat16* __restrict__ q, int ldq, __nv_bfloat16* _
 
 }  // namespace
 
+int attention_set_early_trigger(int on) {
+  return cudaMemcpyToSymbol(c_early_trigger, &on, sizeof(int)) == cudaSuccess ? 0 : -2;
+}
+
+static int attn_attrs() {
+  static int state = 0;  // 0 = not set, 1 = ok, -1 = failed
+  if (state == 0) {
+    const bool ok =
+        cudaFuncSetAttribute(paged_attn_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem) ==
+            cudaSuccess &&
+        cudaFuncSetAttribute(paged_attn_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem) ==
+            cudaSuccess &&
+        cudaFuncSetAttribute(paged_attn_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             kAttnSmem + kFusedStage) == cudaSuccess;
+    state = ok ? 1 : -1;
+  }
+  return state == 1 ? 0 : -3;
+}
+
 int paged_attention(const void* q, int ldq, void* out, int ldo, const void* kv_layer, const int* block_tables,
                     int max_blocks, const AttnWork* work, int num_work, int Hq, int Hkv, float scale,
                     int decode, cudaStream_t st) {
   if (num_work <= 0) return 0;
   if (Hq != 4 * Hkv) return -1;
-  static bool attr_set = false;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(paged_attn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem) !=
-            cudaSuccess ||
-        cudaFuncSetAttribute(paged_attn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem) !=
-            cudaSuccess)
-      return -3;
-    attr_set = true;
-  }
+  if (int rc = attn_attrs()) return rc;
   const float scale_log2 = scale * 1.4426950408889634f;
   dim3 grid(Hkv, num_work);
   const __nv_bfloat16* qq = static_cast<const __nv_bfloat16*>(q);
   __nv_bfloat16* oo = static_cast<__nv_bfloat16*>(out);
-  const __nv_bfloat16* kk = static_cast<const __nv_bfloat16*>(kv_layer);
+  __nv_bfloat16* kk = const_cast<__nv_bfloat16*>(static_cast<const __nv_bfloat16*>(kv_layer));
+  const __nv_bfloat16* none = nullptr;
   if (decode)
-    launch_pdl(paged_attn_kernel<true>, grid, dim3(128), kAttnSmem, st, qq, ldq, oo, ldo, kk, block_tables,
-               max_blocks, work, Hkv, scale_log2);
+    launch_pdl(paged_attn_kernel<true, false>, grid, dim3(128), kAttnSmem, st, qq, ldq, oo, ldo, kk, block_tables,
+               max_blocks, work, Hkv, scale_log2, none, 0, no_partials());
   else
-    launch_pdl(paged_attn_kernel<false>, grid, dim3(128), kAttnSmem, st, qq, ldq, oo, ldo, kk, block_tables,
-               max_blocks, work, Hkv, scale_log2);
+    launch_pdl(paged_attn_kernel<false, false>, grid, dim3(128), kAttnSmem, st, qq, ldq, oo, ldo, kk, block_tables,
+               max_blocks, work, Hkv, scale_log2, none, 0, no_partials());
+  return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+int paged_attention_rope_decode(const void* qkv, int ldq, void* out, int ldo, void* kv_layer, const int* block_tables,
+                                int max_blocks, const AttnWork* work, int num_work, int Hq, int Hkv, float scale,
+                                const void* cos_sin, int max_pos, cudaStream_t st, PartialView pv) {
+  if (num_work <= 0) return 0;
+  if (Hq != 4 * Hkv) return -1;
+  if (int rc = attn_attrs()) return rc;
+  const float scale_log2 = scale * 1.4426950408889634f;
+  launch_pdl(paged_attn_kernel<true, true>, dim3(Hkv, num_work), dim3(128), kAttnSmem + kFusedStage, st,
+             static_cast<const __nv_bfloat16*>(qkv), ldq, static_cast<__nv_bfloat16*>(out), ldo,
+             static_cast<__nv_bfloat16*>(kv_layer), block_tables, max_blocks, work, Hkv, scale_log2,
+             static_cast<const __nv_bfloat16*>(cos_sin), max_pos, pv);
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 

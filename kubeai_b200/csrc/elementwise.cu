@@ -18,6 +18,8 @@ namespace b200 {
 
 namespace {
 
+__constant__ int c_early_trigger = 0;  // B200_EARLY_TRIGGER (see griddep_enter)
+
 union Vec8 {
   uint4 u;
   __nv_bfloat16 h[8];
@@ -32,8 +34,7 @@ __device__ __forceinline__ float warp_sum(float v) {
 // ------------------------------------------------------------------ embedding gather
 __global__ void embed_kernel(const __nv_bfloat16* __restrict__ table, const int* __restrict__ ids,
                              __nv_bfloat16* __restrict__ out, int H, int vocab) {
-  griddep_wait();
-  griddep_launch();
+  griddep_enter(c_early_trigger);
   const int t = blockIdx.x;
   int id = ids[t];
   if (id < 0 || id >= vocab) id = 0;
@@ -49,8 +50,7 @@ template <int VPT>  // uint4 vectors per thread (H = VPT * 8 * blockDim)
 __global__ void rmsnorm_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ residual,
                                const __nv_bfloat16* __restrict__ w, __nv_bfloat16* __restrict__ out,
                                const int* __restrict__ row_index, int H, float eps, PartialView pv) {
-  griddep_wait();
-  griddep_launch();
+  griddep_enter(c_early_trigger);
   const int s = blockIdx.x;
   const int r = row_index ? row_index[s] : s;
   const uint4* xin = reinterpret_cast<const uint4*>(x + static_cast<size_t>(r) * H);
@@ -121,8 +121,7 @@ __global__ void rmsnorm_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat1
 __global__ void rope_kv_kernel(__nv_bfloat16* __restrict__ qkv, const int* __restrict__ positions,
                                const int* __restrict__ slots, const __nv_bfloat16* __restrict__ cos_sin,
                                __nv_bfloat16* __restrict__ kv, int Hq, int Hkv, int max_pos, PartialView pv) {
-  griddep_wait();
-  griddep_launch();
+  griddep_enter(c_early_trigger);
   constexpr int D = 128, HALF = 64;
   const int t = blockIdx.x;
   int pos = positions[t];
@@ -203,35 +202,45 @@ __global__ void rope_kv_kernel(__nv_bfloat16* __restrict__ qkv, const int* __res
 }
 
 // ------------------------------------------------------------------ SiLU(gate) * up
+template <int VPT>  // uint4 vectors per thread: 1 for decode (latency), 4 for prefill bursts (bytes in flight)
 __global__ void silu_mul_kernel(const __nv_bfloat16* __restrict__ gu, __nv_bfloat16* __restrict__ out, int I,
                                 int ldi, PartialView pv) {
-  griddep_wait();
-  griddep_launch();
+  griddep_enter(c_early_trigger);
   const int t = blockIdx.y;
   const uint4* g = reinterpret_cast<const uint4*>(gu + static_cast<size_t>(t) * ldi);
   const uint4* u = reinterpret_cast<const uint4*>(gu + static_cast<size_t>(t) * ldi + I);
   uint4* o = reinterpret_cast<uint4*>(out + static_cast<size_t>(t) * I);
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < I / 8; i += gridDim.x * blockDim.x) {
-    Vec8 r;
-    float ga[8], ua[8];
+  const int nvec = I / 8;
+  const int i0 = blockIdx.x * blockDim.x * VPT + threadIdx.x;
+  float ga[VPT][8], ua[VPT][8];
+#pragma unroll
+  for (int k = 0; k < VPT; ++k) {
+    const int i = i0 + k * blockDim.x;
+    if (i >= nvec) continue;
     if (pv.ws) {
-      load8_partials(pv, t, i * 8, ga);
-      load8_partials(pv, t, I + i * 8, ua);
+      load8_partials(pv, t, i * 8, ga[k]);
+      load8_partials(pv, t, I + i * 8, ua[k]);
     } else {
       Vec8 a, b;
       a.u = g[i];
       b.u = u[i];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        ga[j] = __bfloat162float(a.h[j]);
-        ua[j] = __bfloat162float(b.h[j]);
+        ga[k][j] = __bfloat162float(a.h[j]);
+        ua[k][j] = __bfloat162float(b.h[j]);
       }
     }
+  }
+#pragma unroll
+  for (int k = 0; k < VPT; ++k) {
+    const int i = i0 + k * blockDim.x;
+    if (i >= nvec) continue;
+    Vec8 r;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float x = ga[j];
+      const float x = ga[k][j];
       const __nv_bfloat16 s = __float2bfloat16_rn(x / (1.0f + expf(-x)));
-      r.h[j] = __float2bfloat16_rn(__bfloat162float(s) * ua[j]);
+      r.h[j] = __float2bfloat16_rn(__bfloat162float(s) * ua[k][j]);
     }
     o[i] = r.u;
   }
@@ -240,8 +249,7 @@ __global__ void silu_mul_kernel(const __nv_bfloat16* __restrict__ gu, __nv_bfloa
 // ------------------------------------------------------------------ greedy argmax over bf16 logits
 __global__ void argmax_kernel(const __nv_bfloat16* __restrict__ logits, int* __restrict__ out, int V, int ld,
                               PartialView pv) {
-  griddep_wait();
-  griddep_launch();
+  griddep_enter(c_early_trigger);
   const int s = blockIdx.x;
   const __nv_bfloat16* row = logits + static_cast<size_t>(s) * ld;
   float best = -INFINITY;
@@ -382,9 +390,12 @@ int rope_kv_write(void* qkv, const int* positions, const int* slots, const void*
 int silu_mul(const void* gate_up, void* out, int T, int I, cudaStream_t st, PartialView pv) {
   if (T <= 0) return 0;
   if (I % 8) return -1;
-  dim3 grid((I / 8 + 255) / 256, T);
-  launch_pdl(silu_mul_kernel, grid, dim3(256), 0, st, static_cast<const __nv_bfloat16*>(gate_up),
-             static_cast<__nv_bfloat16*>(out), I, 2 * I, pv);
+  const __nv_bfloat16* gu = static_cast<const __nv_bfloat16*>(gate_up);
+  __nv_bfloat16* o = static_cast<__nv_bfloat16*>(out);
+  if (T >= 512)
+    launch_pdl(silu_mul_kernel<4>, dim3((I / 8 + 1023) / 1024, T), dim3(256), 0, st, gu, o, I, 2 * I, pv);
+  else
+    launch_pdl(silu_mul_kernel<1>, dim3((I / 8 + 255) / 256, T), dim3(256), 0, st, gu, o, I, 2 * I, pv);
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 
@@ -393,6 +404,10 @@ int argmax_rows(const void* logits, int* out, int S, int V, int ld, cudaStream_t
   if (ld % 8 || (pv.ws && V % 8)) return -1;
   launch_pdl(argmax_kernel, dim3(S), dim3(1024), 0, st, static_cast<const __nv_bfloat16*>(logits), out, V, ld, pv);
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+int elementwise_set_early_trigger(int on) {
+  return cudaMemcpyToSymbol(c_early_trigger, &on, sizeof(int)) == cudaSuccess ? 0 : -2;
 }
 
 int init_uniform(void* p, size_t n, uint32_t seed, float scale, float offset, cudaStream_t st) {

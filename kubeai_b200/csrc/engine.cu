@@ -31,6 +31,7 @@
 #include "errors.h"
 #include "gemm.h"
 #include "kernels.h"
+#include "hostutil.h"
 #include "xxh64.h"
 
 namespace b200 {
@@ -169,13 +170,34 @@ struct Seq {
   bool ignore_eos = false;
   std::vector<int32_t> stop_ids;
   int n_generated = 0;
-  int n_cached = -1;  // prefix-hit tokens at first admission
+  std::atomic<int> n_cached{-1};  // prefix-hit tokens at first admission
   bool admitted = false;
-  // shared with API threads (guarded by Engine::mu_)
+  bool leaving = false;  // finished in the step being completed: swept out of the running list
+  // shared with API threads: guarded by m (one lock per request, so a step's 128 wake-ups do not convoy on one mutex)
+  std::mutex m;
+  std::condition_variable cv;
   std::vector<int32_t> out;
   size_t drained = 0;
   int finished = 0;
-  bool abort_requested = false;
+  std::atomic<bool> abort_requested{false};
+};
+
+struct Sched {
+  std::shared_ptr<Seq> s;
+  int n;
+};
+// a launched, not yet completed step
+struct InFlight {
+  std::vector<Sched> sched;
+  int words = 0, ndec_seq = 0, npre_seq = 0;
+  double t_enter = 0, t_packed = 0, t_launched = 0;
+};
+// a result not yet visible to the API threads (published while the next step runs on the GPU)
+struct Pub {
+  std::shared_ptr<Seq> s;
+  int32_t tok;
+  bool has_tok;
+  int code;
 };
 
 struct StepMeta {
@@ -243,7 +265,7 @@ struct Engine {
 
   // shared state
   std::mutex mu_;
-  std::condition_variable cv_work_, cv_out_;
+  std::condition_variable cv_work_;
   std::deque<std::shared_ptr<Seq>> incoming;
   std::unordered_map<uint64_t, std::shared_ptr<Seq>> requests;
   uint64_t next_id = 1;
@@ -253,6 +275,8 @@ struct Engine {
   bool fatal = false;
   bool recording = true;        // when false, steps use the scratch ring slot and the recorded ones are kept
   // per-kernel-class device timing (b200_engine_profile): events around every launch of a replayed step
+  double step_timing[7] = {0, 0, 0, 0, 0, 0, 0};  // B200_STEP_TIMING accumulators (decode-only steps)
+  double step_timing_last_end = 0;
   uint32_t skip_mask = 0;  // debug/timing: kernel classes (1 << B200_K_*) NOT launched by forward() (results are garbage)
   bool profiling = false;
   std::vector<std::pair<int, cudaEvent_t>> prof_events;  // (class, event) in launch order: start, stop pairs
@@ -262,8 +286,18 @@ struct Engine {
   int init(const b200_config& c);
   int alloc_all();
   int forward(const StepMeta& m, int32_t* dbuf, bool all_logits, bf16* logits_out);
+  // one scheduler iteration = launch (schedule, pack, H2D, kernels, D2H enqueue) + complete (sync, apply) + publish
+  int launch(InFlight* f, StepMeta* m);
+  int complete(InFlight& f, const StepMeta& m, b200_step_info* info);
+  void publish();
   int step(b200_step_info* info);
+  int run(int max_steps, int64_t idle_timeout_us, b200_step_info* infos, int* n_done);
+  void fail_all();
   void loop();
+  std::vector<Pub> pending_pub;
+  InFlight inflight_;
+  std::vector<AttnWork> dwork_, pwork_;  // packing scratch (kept across steps: no per-step allocation)
+  std::vector<int> rows_;
   bool ensure_blocks(Seq& s, int upto);
   void release_blocks(Seq& s);
   void preempt(std::shared_ptr<Seq> s);
@@ -287,6 +321,14 @@ Engine::~Engine() {
   stop = true;
   cv_work_.notify_all();
   if (worker.joinable()) worker.join();
+  if (step_timing[0] > 0) {
+    const double n = step_timing[0], us = 1e6 / n;
+    fprintf(stderr,
+            "[b200engine] decode-only steps %.0f: schedule+pack %.1f us, launch %.1f us, wait %.1f us, apply %.1f us, "
+            "device %.1f us, between calls %.1f us\n",
+            n, step_timing[1] * us, step_timing[2] * us, step_timing[3] * us, step_timing[4] * us, step_timing[5] * us,
+            step_timing[6] * us);
+  }
   cudaSetDevice(cfg.device);
   if (stream) cudaStreamSynchronize(stream);
   void* frees[] = {weights_blob, res, x, normed, qkv, attn, gu, act, last_hidden, logits, sampled, gemm_ws,
@@ -403,6 +445,11 @@ int Engine::alloc_all() {
   }
   if (plan(&p_lm, lm_head, V, H)) return cuda_fail("gemm_plan_init(lm_head)", -2);
   deferred_ok = gemm_variant() == 2;
+  {
+    const char* e = getenv("B200_EARLY_TRIGGER");  // A/B knob, see ptx.cuh griddep_enter
+    const int early = e ? atoi(e) : 0;
+    if (elementwise_set_early_trigger(early) || attention_set_early_trigger(early)) return cuda_fail("early trigger", -2);
+  }
   const int bns[kGemmNumBlockN] = {32, 64, 128, 256, 512};
   for (int i = 0; i < kGemmNumBlockN; ++i) {
     if (gemm_make_x_map(&xm_normed.m[i], normed, Tcap, H, H, bns[i]) ||
@@ -502,6 +549,12 @@ int Engine::forward(const StepMeta& m, int32_t* dbuf, bool all_logits, bf16* log
     return e ? atoi(e) : (1 << 30);
   }();
   const bool dfr = deferred_ok && !all_logits && T <= defer_max_t;
+  static const bool fuse_rope_env = [] {
+    const char* e = getenv("B200_FUSE_ROPE");  // A/B knob: 1 folds RoPE + KV write into the decode attention kernel
+    return e && atoi(e) != 0;  // default off: measured 6.14 vs 6.01 ms per decode step (the prologue's latency chain
+                               // costs every attention CTA more than the saved launch)
+  }();
+  const bool fuse_rope = fuse_rope_env && m.np == 0 && m.nd == T && !all_logits;
   PartialView pv_x = no_partials();  // partials of the GEMM whose output is `x` (o_proj / down_proj)
   for (int l = 0; l < L && !rc; ++l) {
     Layer& ly = layers[l];
@@ -516,10 +569,20 @@ int Engine::forward(const StepMeta& m, int32_t* dbuf, bool all_logits, bf16* log
     if (!on(B200_K_GEMM_QKV)) {}
     else if (dfr) rc |= gemm_def(ly.p_qkv, xm_normed, qkv, QKV, T, &pv); else rc |= gemm(ly.p_qkv, xm_normed, qkv, QKV, T);
     Q();
+    if (fuse_rope) {
+      // pure-decode step: RoPE + KV write ride in the attention kernel's prologue (one launch fewer per layer)
+      P(B200_K_ATTN_DECODE);
+      if (on(B200_K_ATTN_DECODE))
+        rc |= paged_attention_rope_decode(qkv, QKV, attn, Hq * kD, kv_l, btab, max_blocks_per_seq, dwork, m.nd, Hq, Hkv,
+                                          scale, cos_sin, cfg.max_model_len, stream, pv);
+      Q();
+      launched(2);
+    } else {
     P(B200_K_ROPE); if (on(B200_K_ROPE)) rc |= rope_kv_write(qkv, pos, slots, cos_sin, kv_l, T, Hq, Hkv, cfg.max_model_len, stream, pv); Q();
     launched(2);
     if (m.nd) { P(B200_K_ATTN_DECODE); if (on(B200_K_ATTN_DECODE)) rc |= paged_attention(qkv, QKV, attn, Hq * kD, kv_l, btab, max_blocks_per_seq, dwork, m.nd, Hq, Hkv, scale, 1, stream); Q(); launched(1); }
     if (m.np) { P(B200_K_ATTN_PREFILL); if (on(B200_K_ATTN_PREFILL)) rc |= paged_attention(qkv, QKV, attn, Hq * kD, kv_l, btab, max_blocks_per_seq, pwork, m.np, Hq, Hkv, scale, 0, stream); Q(); launched(1); }
+    }
     P(B200_K_GEMM_O);
     if (!on(B200_K_GEMM_O)) {}
     else if (dfr) rc |= gemm_def(ly.p_o, xm_attn, x, H, T, &pv_x); else rc |= gemm(ly.p_o, xm_attn, x, H, T);
@@ -582,8 +645,21 @@ void Engine::preempt(std::shared_ptr<Seq> s) {
 
 void Engine::finish(std::shared_ptr<Seq> s, int code) {
   release_blocks(*s);
-  std::lock_guard<std::mutex> lk(mu_);
-  s->finished = code;
+  pending_pub.push_back({std::move(s), 0, false, code});
+}
+
+// Make the last step's tokens / finish codes visible to the API threads and wake them.  Called right after the NEXT
+// step has been enqueued, so the wake-ups (one futex per streaming client) overlap GPU work instead of delaying it.
+void Engine::publish() {
+  for (auto& p : pending_pub) {
+    {
+      std::lock_guard<std::mutex> lk(p.s->m);
+      if (p.has_tok) p.s->out.push_back(p.tok);
+      if (p.code) p.s->finished = p.code;
+    }
+    p.s->cv.notify_all();
+  }
+  pending_pub.clear();
 }
 
 void Engine::admit_prefix(Seq& s) {
@@ -603,16 +679,20 @@ void Engine::admit_prefix(Seq& s) {
   s.n_computed = hit * kPage;
   s.n_published = hit;
   s.chain_uid = parent;
-  if (s.n_cached < 0) {
+  if (s.n_cached.load() < 0) {
     s.n_cached = s.n_computed;
-    stats.cached_prompt_tokens += s.n_cached;
+    stats.cached_prompt_tokens += s.n_computed;
     stats.prompt_tokens += s.n_prompt;
   }
 }
 
 // ------------------------------------------------------------------ one scheduler iteration + forward
-int Engine::step(b200_step_info* info) {
-  if (info) memset(info, 0, sizeof(*info));
+// launch(): schedule (running first, then admissions, vLLM v1 order), pack the step's device inputs, enqueue the
+// H2D copy, the kernels and the D2H of the sampled ids.  Returns 0 when there is nothing to run, 1 when a step is
+// in flight, negative on error.
+int Engine::launch(InFlight* f, StepMeta* mp) {
+  static const bool timing = [] { const char* e = getenv("B200_STEP_TIMING"); return e && atoi(e) != 0; }();
+  f->t_enter = timing ? now_s() : 0.0;
   {
     std::lock_guard<std::mutex> lk(mu_);
     while (!incoming.empty()) {
@@ -622,29 +702,29 @@ int Engine::step(b200_step_info* info) {
   }
   // aborted requests leave first
   {
-    std::vector<std::shared_ptr<Seq>> keep;
-    for (auto& s : running) {
-      bool ab;
-      { std::lock_guard<std::mutex> lk(mu_); ab = s->abort_requested; }
-      if (ab) finish(s, B200_FINISH_ABORTED); else keep.push_back(s);
+    size_t k = 0;
+    for (size_t i = 0; i < running.size(); ++i) {
+      if (running[i]->abort_requested.load(std::memory_order_relaxed)) finish(running[i], B200_FINISH_ABORTED);
+      else running[k++] = running[i];
     }
-    running.swap(keep);
-    std::deque<std::shared_ptr<Seq>> wkeep;
-    for (auto& s : waiting) {
-      bool ab;
-      { std::lock_guard<std::mutex> lk(mu_); ab = s->abort_requested; }
-      if (ab) finish(s, B200_FINISH_ABORTED); else wkeep.push_back(s);
+    running.resize(k);
+    for (auto it = waiting.begin(); it != waiting.end();) {
+      if ((*it)->abort_requested.load(std::memory_order_relaxed)) {
+        finish(*it, B200_FINISH_ABORTED);
+        it = waiting.erase(it);
+      } else {
+        ++it;
+      }
     }
-    waiting.swap(wkeep);
   }
 
-  struct Sched { std::shared_ptr<Seq> s; int n; };
-  std::vector<Sched> sched;
+  std::vector<Sched>& sched = f->sched;
+  sched.clear();
   int budget = cfg.max_batched_tokens;
   bool preempted = false;
   // 1. running requests first (decodes and in-progress prefills)
   for (size_t i = 0; i < running.size() && budget > 0;) {
-    auto s = running[i];
+    auto& s = running[i];
     int n = std::min(static_cast<int>(s->toks.size()) - s->n_computed, budget);
     if (n <= 0) { ++i; continue; }
     bool ok = true;
@@ -687,11 +767,13 @@ int Engine::step(b200_step_info* info) {
   StepMeta m;
   m.nseq = static_cast<int>(sched.size());
   for (auto& sc : sched) m.T += sc.n;
-  std::vector<AttnWork> dwork, pwork;
-  std::vector<int> rows;
+  dwork_.clear();
+  pwork_.clear();
+  rows_.clear();
   int32_t* h = stage_host;
   m.off_ids = 0; m.off_pos = m.T; m.off_slots = 2 * m.T;
-  int tok = 0, ndec_seq = 0, npre_seq = 0;
+  int tok = 0;
+  f->ndec_seq = f->npre_seq = 0;
   for (int si = 0; si < m.nseq; ++si) {
     Seq& s = *sched[si].s;
     const int n = sched[si].n, p0 = s.n_computed;
@@ -702,31 +784,31 @@ int Engine::step(b200_step_info* info) {
       h[m.off_slots + tok + j] = s.blocks[p / kPage] * kPage + (p % kPage);
     }
     if (n == 1) {
-      dwork.push_back({tok, 1, p0, si});
+      dwork_.push_back({tok, 1, p0, si});
       m.kv_tokens += p0 + 1;
-      ++ndec_seq;
+      ++f->ndec_seq;
     } else {
-      for (int j = 0; j < n; j += 16) pwork.push_back({tok + j, std::min(16, n - j), p0 + j, si});
+      for (int j = 0; j < n; j += 16) pwork_.push_back({tok + j, std::min(16, n - j), p0 + j, si});
       m.kv_tokens += p0 + n;  // unique K/V tokens this sequence streams from HBM (query tiles re-read them from L2)
-      ++npre_seq;
+      ++f->npre_seq;
     }
-    if (p0 + n == static_cast<int>(s.toks.size())) rows.push_back(tok + n - 1);
+    if (p0 + n == static_cast<int>(s.toks.size())) rows_.push_back(tok + n - 1);
     tok += n;
   }
   // longest-context work first: CTAs are dispatched in blockIdx order, so the tail of the attention grid is made of
   // the shortest sequences (LPT scheduling) instead of whatever happened to be last
   auto longer = [](const AttnWork& a, const AttnWork& b) { return a.q_pos0 + a.q_count > b.q_pos0 + b.q_count; };
-  std::stable_sort(dwork.begin(), dwork.end(), longer);
-  std::stable_sort(pwork.begin(), pwork.end(), longer);
-  m.nd = static_cast<int>(dwork.size());
-  m.np = static_cast<int>(pwork.size());
-  m.S = static_cast<int>(rows.size());
+  std::stable_sort(dwork_.begin(), dwork_.end(), longer);
+  std::stable_sort(pwork_.begin(), pwork_.end(), longer);
+  m.nd = static_cast<int>(dwork_.size());
+  m.np = static_cast<int>(pwork_.size());
+  m.S = static_cast<int>(rows_.size());
   m.out_tokens = m.S;
   int w = 3 * m.T;
-  m.off_rows = w; memcpy(h + w, rows.data(), rows.size() * 4); w += m.S;
+  m.off_rows = w; memcpy(h + w, rows_.data(), rows_.size() * 4); w += m.S;
   w = (w + 3) & ~3;
-  m.off_dwork = w; memcpy(h + w, dwork.data(), dwork.size() * 16); w += 4 * m.nd;
-  m.off_pwork = w; memcpy(h + w, pwork.data(), pwork.size() * 16); w += 4 * m.np;
+  m.off_dwork = w; memcpy(h + w, dwork_.data(), dwork_.size() * 16); w += 4 * m.nd;
+  m.off_pwork = w; memcpy(h + w, pwork_.data(), pwork_.size() * 16); w += 4 * m.np;
   m.off_btab = w;
   for (int si = 0; si < m.nseq; ++si) {
     Seq& s = *sched[si].s;
@@ -747,23 +829,34 @@ int Engine::step(b200_step_info* info) {
   }
   ring_meta[slot] = m;
   int32_t* dbuf = stage_dev[slot];
+  f->t_packed = timing ? now_s() : 0.0;
   CK(cudaMemcpyAsync(dbuf, h, static_cast<size_t>(w) * 4, cudaMemcpyHostToDevice, stream));
   CK(cudaEventRecord(ev0, stream));
   if (int rc = forward(m, dbuf, false, nullptr)) return rc;
   CK(cudaEventRecord(ev1, stream));
   if (m.S) CK(cudaMemcpyAsync(sampled_host, sampled, static_cast<size_t>(m.S) * 4, cudaMemcpyDeviceToHost, stream));
+  f->t_launched = timing ? now_s() : 0.0;
+  f->words = w;
+  *mp = m;
+  return 1;
+}
+
+// complete(): wait for the step, apply the sampled ids to the engine-private sequence state, queue what the API
+// threads must see (tokens, finish codes) for publish().
+int Engine::complete(InFlight& f, const StepMeta& m, b200_step_info* info) {
+  static const bool timing = [] { const char* e = getenv("B200_STEP_TIMING"); return e && atoi(e) != 0; }();
   CK(cudaStreamSynchronize(stream));
+  const double ht3 = timing ? now_s() : 0.0;
   float ms = 0.f;
   cudaEventElapsedTime(&ms, ev0, ev1);
 
-  // ---- apply results
   int ri = 0;
   int64_t gen = 0;
-  std::vector<std::pair<std::shared_ptr<Seq>, int>> done;
+  bool any_done = false;
   for (int si = 0; si < m.nseq; ++si) {
-    auto sp = sched[si].s;
+    const std::shared_ptr<Seq>& sp = f.sched[si].s;
     Seq& s = *sp;
-    const int n = sched[si].n;
+    const int n = f.sched[si].n;
     const bool samples = (s.n_computed + n == static_cast<int>(s.toks.size()));
     s.n_computed += n;
     // publish newly full blocks to the prefix cache
@@ -782,15 +875,18 @@ int Engine::step(b200_step_info* info) {
     for (int sid : s.stop_ids) if (t == sid) code = B200_FINISH_STOP;
     if (!code && s.n_generated >= s.max_tokens) code = B200_FINISH_LENGTH;
     if (!code && static_cast<int>(s.toks.size()) >= cfg.max_model_len) code = B200_FINISH_LENGTH;
-    {
-      std::lock_guard<std::mutex> lk(mu_);
-      s.out.push_back(t);
+    pending_pub.push_back({sp, t, true, code});
+    if (code) {
+      release_blocks(s);
+      s.leaving = true;
+      any_done = true;
     }
-    if (code) done.push_back({sp, code});
   }
-  for (auto& d : done) {
-    running.erase(std::find(running.begin(), running.end(), d.first));
-    finish(d.first, d.second);
+  if (any_done) {
+    size_t k = 0;
+    for (size_t i = 0; i < running.size(); ++i)
+      if (!running[i]->leaving) running[k++] = running[i];
+    running.resize(k);
   }
   {
     std::lock_guard<std::mutex> lk(mu_);
@@ -799,17 +895,26 @@ int Engine::step(b200_step_info* info) {
     stats.last_step_device_us = ms * 1000.0;
     stats.total_device_us += ms * 1000.0;
     stats.last_step_tokens = m.T;
-    stats.h2d_bytes += static_cast<int64_t>(w) * 4;
+    stats.h2d_bytes += static_cast<int64_t>(f.words) * 4;
     stats.d2h_bytes += static_cast<int64_t>(m.S) * 4;
     stats.running = static_cast<int>(running.size());
     stats.waiting = static_cast<int>(waiting.size());
     stats.kv_blocks_free = pool.free_count();
   }
-  cv_out_.notify_all();
+  if (timing) {
+    const double ht4 = now_s();
+    if (m.np == 0) {
+      double* a = step_timing;
+      a[0] += 1; a[1] += f.t_packed - f.t_enter; a[2] += f.t_launched - f.t_packed; a[3] += ht3 - f.t_launched;
+      a[4] += ht4 - ht3; a[5] += ms * 1e-3;
+      if (step_timing_last_end > 0) a[6] += f.t_enter - step_timing_last_end;
+    }
+    step_timing_last_end = ht4;
+  }
   if (info) {
     info->tokens = m.T;
-    info->decode_seqs = ndec_seq;
-    info->prefill_seqs = npre_seq;
+    info->decode_seqs = f.ndec_seq;
+    info->prefill_seqs = f.npre_seq;
     info->sampled = m.S;
     info->kv_tokens_read = m.kv_tokens;
     info->device_us = ms * 1000.0;
@@ -817,26 +922,79 @@ int Engine::step(b200_step_info* info) {
   return 1;
 }
 
+// One synchronous iteration (tests, debugging): results are visible to poll() when it returns.
+int Engine::step(b200_step_info* info) {
+  if (info) memset(info, 0, sizeof(*info));
+  InFlight& f = inflight_;
+  StepMeta m;
+  int rc = launch(&f, &m);
+  if (rc == 1) rc = complete(f, m, info);
+  publish();
+  return rc;
+}
+
+// Up to max_steps iterations back to back: step N's tokens are published to the API threads after step N+1 has been
+// enqueued.  Stops early when the engine has had nothing to run for idle_timeout_us.
+int Engine::run(int max_steps, int64_t idle_timeout_us, b200_step_info* infos, int* n_done) {
+  int done = 0, rc = 0;
+  double idle_since = -1.0;
+  InFlight& f = inflight_;
+  while (done < max_steps) {
+    StepMeta m;
+    rc = launch(&f, &m);
+    publish();
+    if (rc < 0) break;
+    if (rc == 0) {
+      const double now = now_s();
+      if (idle_since < 0) idle_since = now;
+      if ((now - idle_since) * 1e6 >= static_cast<double>(idle_timeout_us)) break;
+      std::unique_lock<std::mutex> lk(mu_);
+      cv_work_.wait_for(lk, std::chrono::microseconds(200), [this] { return stop.load() || !incoming.empty(); });
+      continue;
+    }
+    idle_since = -1.0;
+    b200_step_info* info = infos ? infos + done : nullptr;
+    if (info) memset(info, 0, sizeof(*info));
+    rc = complete(f, m, info);
+    if (rc < 0) break;
+    ++done;
+  }
+  publish();
+  if (n_done) *n_done = done;
+  return rc < 0 ? rc : 0;
+}
+
+// A CUDA failure poisons this replica: fail everything in flight (the router retries elsewhere,
+// internal/modelproxy/handler.go:127-155)
+void Engine::fail_all() {
+  std::vector<std::shared_ptr<Seq>> all(running.begin(), running.end());
+  all.insert(all.end(), waiting.begin(), waiting.end());
+  running.clear();
+  waiting.clear();
+  {
+    std::lock_guard<std::mutex> lk(mu_);
+    fatal = true;
+    all.insert(all.end(), incoming.begin(), incoming.end());
+    incoming.clear();
+  }
+  pending_pub.clear();
+  for (auto& s : all) {
+    { std::lock_guard<std::mutex> lk(s->m); s->finished = B200_FINISH_ERROR; }
+    s->cv.notify_all();
+  }
+}
+
 void Engine::loop() {
   cudaSetDevice(cfg.device);
+  InFlight& f = inflight_;
   while (!stop) {
-    int rc = step(nullptr);
+    StepMeta m;
+    int rc = launch(&f, &m);
+    publish();  // the previous step's tokens reach the clients while this one runs
+    if (rc == 1) rc = complete(f, m, nullptr);
     if (rc < 0) {
-      // a CUDA failure poisons this replica: fail everything in flight (the router retries elsewhere,
-      // internal/modelproxy/handler.go:127-155)
       fprintf(stderr, "[b200engine] step failed: %s\n", b200_last_error());
-      std::vector<std::shared_ptr<Seq>> all(running.begin(), running.end());
-      all.insert(all.end(), waiting.begin(), waiting.end());
-      running.clear();
-      waiting.clear();
-      {
-        std::lock_guard<std::mutex> lk(mu_);
-        fatal = true;
-        for (auto& s : all) s->finished = B200_FINISH_ERROR;
-        for (auto& s : incoming) s->finished = B200_FINISH_ERROR;
-        incoming.clear();
-      }
-      cv_out_.notify_all();
+      fail_all();
       return;
     }
     if (rc == 0) {
@@ -844,6 +1002,7 @@ void Engine::loop() {
       cv_work_.wait_for(lk, std::chrono::milliseconds(50), [this] { return stop.load() || !incoming.empty(); });
     }
   }
+  publish();
 }
 
 }  // namespace b200
@@ -923,17 +1082,22 @@ int b200_poll(b200_engine* e, uint64_t req_id, int32_t* out_ids, int32_t cap, in
               b200_usage* usage) {
   if (!e || !n_out) { set_error("b200_poll: bad arguments"); return B200_ERR_INVALID; }
   Engine& g = e->impl;
-  std::lock_guard<std::mutex> lk(g.mu_);
-  auto s = find_req(g, req_id);
+  std::shared_ptr<Seq> s;
+  {
+    std::lock_guard<std::mutex> lk(g.mu_);
+    s = find_req(g, req_id);
+  }
   if (!s) { set_error("unknown request %llu", static_cast<unsigned long long>(req_id)); return B200_ERR_NOT_FOUND; }
+  std::lock_guard<std::mutex> lk(s->m);
   int n = static_cast<int>(std::min<size_t>(s->out.size() - s->drained, cap > 0 && out_ids ? cap : 0));
   if (n > 0) memcpy(out_ids, s->out.data() + s->drained, static_cast<size_t>(n) * 4);
   s->drained += n;
   *n_out = n;
   if (finished) *finished = (s->drained == s->out.size()) ? s->finished : 0;
   if (usage) {
+    const int nc = s->n_cached.load();
     usage->prompt_tokens = s->n_prompt;
-    usage->cached_tokens = s->n_cached < 0 ? 0 : s->n_cached;
+    usage->cached_tokens = nc < 0 ? 0 : nc;
     usage->completion_tokens = static_cast<int>(s->out.size());
   }
   return 0;
@@ -942,12 +1106,16 @@ int b200_poll(b200_engine* e, uint64_t req_id, int32_t* out_ids, int32_t cap, in
 int b200_wait(b200_engine* e, uint64_t req_id, int64_t timeout_us) {
   if (!e) { set_error("null engine"); return B200_ERR_INVALID; }
   Engine& g = e->impl;
-  std::unique_lock<std::mutex> lk(g.mu_);
-  auto s = find_req(g, req_id);
+  std::shared_ptr<Seq> s;
+  {
+    std::lock_guard<std::mutex> lk(g.mu_);
+    s = find_req(g, req_id);
+  }
   if (!s) { set_error("unknown request"); return B200_ERR_NOT_FOUND; }
+  std::unique_lock<std::mutex> lk(s->m);
   auto ready = [&] { return s->out.size() > s->drained || s->finished != 0; };
-  if (timeout_us < 0) { g.cv_out_.wait(lk, ready); return 0; }
-  if (!g.cv_out_.wait_for(lk, std::chrono::microseconds(timeout_us), ready)) { set_error("timeout"); return B200_ERR_TIMEOUT; }
+  if (timeout_us < 0) { s->cv.wait(lk, ready); return 0; }
+  if (!s->cv.wait_for(lk, std::chrono::microseconds(timeout_us), ready)) { set_error("timeout"); return B200_ERR_TIMEOUT; }
   return 0;
 }
 
@@ -958,7 +1126,7 @@ int b200_abort(b200_engine* e, uint64_t req_id) {
     std::lock_guard<std::mutex> lk(g.mu_);
     auto s = find_req(g, req_id);
     if (!s) { set_error("unknown request"); return B200_ERR_NOT_FOUND; }
-    s->abort_requested = true;
+    s->abort_requested.store(true);
   }
   g.cv_work_.notify_one();
   return 0;
@@ -967,11 +1135,17 @@ int b200_abort(b200_engine* e, uint64_t req_id) {
 int b200_release(b200_engine* e, uint64_t req_id) {
   if (!e) { set_error("null engine"); return B200_ERR_INVALID; }
   Engine& g = e->impl;
-  std::lock_guard<std::mutex> lk(g.mu_);
-  auto it = g.requests.find(req_id);
-  if (it == g.requests.end()) { set_error("unknown request"); return B200_ERR_NOT_FOUND; }
-  if (!it->second->finished) it->second->abort_requested = true;
-  g.requests.erase(it);
+  std::shared_ptr<Seq> s;
+  {
+    std::lock_guard<std::mutex> lk(g.mu_);
+    auto it = g.requests.find(req_id);
+    if (it == g.requests.end()) { set_error("unknown request"); return B200_ERR_NOT_FOUND; }
+    s = it->second;
+    g.requests.erase(it);
+  }
+  bool fin;
+  { std::lock_guard<std::mutex> lk(s->m); fin = s->finished != 0; }
+  if (!fin) s->abort_requested.store(true);  // released while running: the engine drops it at the next step
   return 0;
 }
 
@@ -987,6 +1161,16 @@ int b200_engine_step(b200_engine* e, b200_step_info* info) {
   if (!e->impl.cfg.manual_step) { set_error("engine was not created with manual_step"); return B200_ERR_INVALID; }
   cudaSetDevice(e->impl.cfg.device);
   return e->impl.step(info);
+}
+
+int b200_engine_run(b200_engine* e, int32_t max_steps, int64_t idle_timeout_us, b200_step_info* infos, int32_t* n_done) {
+  if (!e || max_steps <= 0) { set_error("b200_engine_run: bad arguments"); return B200_ERR_INVALID; }
+  if (!e->impl.cfg.manual_step) { set_error("engine was not created with manual_step"); return B200_ERR_INVALID; }
+  cudaSetDevice(e->impl.cfg.device);
+  int done = 0;
+  int rc = e->impl.run(max_steps, idle_timeout_us, infos, &done);
+  if (n_done) *n_done = done;
+  return rc;
 }
 
 int b200_engine_replay(b200_engine* e, int32_t n, int32_t repeat, double* ms_total, int64_t* tokens, int64_t* sampled,

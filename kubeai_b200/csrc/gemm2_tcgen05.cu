@@ -125,12 +125,16 @@ template <int BLOCK_N>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 gemm2_streamk_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_x,
                      __nv_bfloat16* __restrict__ out, int ldo, float* __restrict__ ws, int* __restrict__ counters,
-                     int N, int T, int K, const int2* __restrict__ seg_table, int deferred, int l2_prefetch_blocks,
-                     const __nv_bfloat16* __restrict__ w_ptr, int ldw, long long* __restrict__ trace) {
+                     int N, int T, int K, const int2* __restrict__ seg_table, int deferred,
+                     long long* __restrict__ trace) {
   using C = Cfg2<BLOCK_N>;
-  // optional phase trace (debug): 16 clock64() stamps per CTA
+  // optional phase trace (debug): 16 %globaltimer stamps (ns, one clock for the whole GPU) per CTA
   auto mark = [&](int i) {
-    if (trace) trace[static_cast<size_t>(blockIdx.x) * 16 + i] = clock64();
+    if (trace) {
+      long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      trace[static_cast<size_t>(blockIdx.x) * 16 + i] = t;
+    }
   };
   if (threadIdx.x == 64) mark(0);
   extern __shared__ uint8_t smem_raw[];
@@ -287,17 +291,6 @@ gemm2_streamk_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_cons
     // ------------------------------------------------------------ epilogue warps (both CTAs, own 128 rows)
     const int q = warp & 3;
     const int row = q * 32 + lane;
-    if (l2_prefetch_blocks > 0) {
-      // Idle until the first accumulator is ready: use the LSU (not the TMA queue, which must stay free for the
-      // activation loads) to pull this CTA's next weight tiles into L2 while the dependency is still outstanding.
-      int n = 0;
-      for (long long it = it_begin + C::kStages; it < it_end && n < l2_prefetch_blocks; ++it, ++n) {
-        const int tile = static_cast<int>(it / KB), kb = static_cast<int>(it - static_cast<long long>(tile) * KB);
-        const int wrow = (tile / ntt) * 2 * kSlab + static_cast<int>(rank) * kSlab + row;
-        if (wrow < N)
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(w_ptr + static_cast<size_t>(wrow) * ldw + kb * kBlockK));
-      }
-    }
     griddep_wait();
     const int epi_tid = threadIdx.x - 64;
     constexpr int kSlot = BLOCK_N * kSlab;
@@ -485,18 +478,6 @@ gemm2_streamk_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_cons
   if (threadIdx.x == 64) mark(7);
 }
 
-// B200_L2_PREFETCH=<k-blocks>: weight tiles beyond the smem ring pulled into L2 (prefetch.global.L2 from the idle
-// epilogue warps) before the dependency wait.  Default 0; the TMA-queue variant measured slower (it delayed the
-// activation loads behind the prefetches).
-int l2_prefetch_blocks() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("B200_L2_PREFETCH");
-    v = e ? atoi(e) : 0;
-  }
-  return v;
-}
-
 long long* g_trace = nullptr;  // debug: device buffer of 8 stamps per CTA (b200_op_gemm_trace)
 
 int units_for(const GemmPlan& p, int ntt) {
@@ -524,7 +505,7 @@ int launch2(const GemmPlan& p, const CUtensorMap& tm_x, __nv_bfloat16* out, int 
   const int units = units_for(p, ntt);
   cudaError_t e = launch_pdl(gemm2_streamk_kernel<BLOCK_N>, dim3(2 * units), dim3(kThreads), C::kSmemBytes, st, p.tm_w, tm_x,
                              out, ldo, p.ws, p.counters, p.N, T, p.K, static_cast<const int2*>(p.seg_table), deferred,
-                             l2_prefetch_blocks(), static_cast<const __nv_bfloat16*>(p.w_ptr), p.ldw, g_trace);
+                             g_trace);
   return e == cudaSuccess ? 0 : -4;
 }
 

@@ -22,6 +22,11 @@ int silu_mul(const void* gate_up, void* out, int T, int I, cudaStream_t st, Part
 int argmax_rows(const void* logits, int* out, int S, int V, int ld, cudaStream_t st, PartialView pv = no_partials());
 int init_uniform(void* p, size_t n, uint32_t seed, float scale, float offset, cudaStream_t st);
 
+// PDL ordering knob (B200_EARLY_TRIGGER): non-zero makes these kernels release their dependent launch before waiting
+// for their own producer (ptx.cuh griddep_enter).
+int elementwise_set_early_trigger(int on);
+int attention_set_early_trigger(int on);
+
 // One unit of attention work: q_count query tokens of one sequence starting at row q_tok0 of the
 // step's token batch; the first of them sits at absolute position q_pos0 in the sequence.
 struct AttnWork {
@@ -38,5 +43,12 @@ struct AttnWork {
 int paged_attention(const void* q, int ldq, void* out, int ldo, const void* kv_layer, const int* block_tables,
                     int max_blocks, const AttnWork* work, int num_work, int Hq, int Hkv, float scale,
                     int decode, cudaStream_t st);
+
+// Decode attention with the token's RoPE + KV write fused in (every work item has q_count == 1): q|k|v rows come from
+// the QKV GEMM output `qkv` (or its deferred partials `pv`), the rotated k and v are written to the paged cache at
+// (block_tables[seq][pos >> 4], pos & 15), pos = work.q_pos0.  Bit-identical to rope_kv_write + paged_attention.
+int paged_attention_rope_decode(const void* qkv, int ldq, void* out, int ldo, void* kv_layer, const int* block_tables,
+                                int max_blocks, const AttnWork* work, int num_work, int Hq, int Hkv, float scale,
+                                const void* cos_sin, int max_pos, cudaStream_t st, PartialView pv = no_partials());
 
 }  // namespace b200

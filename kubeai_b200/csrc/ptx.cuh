@@ -35,6 +35,18 @@ __device__ __forceinline__ bool elect_one() {
 // at its own griddepcontrol.wait for our completion before touching dependent data).
 __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// Entry sequence of every non-GEMM kernel.  early == 0: wait for the producer, then let the consumer launch (its
+// prologue overlaps only this kernel).  early != 0: release the consumer first, so a GEMM two launches downstream can
+// take SMs (and prefetch weights) as soon as the GEMM upstream of this kernel drains; it still waits for us to finish.
+__device__ __forceinline__ void griddep_enter(int early) {
+  if (early) {
+    griddep_launch();
+    griddep_wait();
+  } else {
+    griddep_wait();
+    griddep_launch();
+  }
+}
 
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {

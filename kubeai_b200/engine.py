@@ -113,6 +113,13 @@ class Engine:
         rc = check(self._l.b200_engine_step(self._h, C.byref(info)))
         return rc == 1, info
 
+    def run(self, max_steps: int, idle_timeout_us: int = 20000):
+        """Up to max_steps pipelined iterations (b200_engine_run); returns the StepInfo of every step that ran."""
+        infos = (StepInfo * max_steps)()
+        n = C.c_int32()
+        check(self._l.b200_engine_run(self._h, max_steps, idle_timeout_us, infos, C.byref(n)))
+        return [infos[i] for i in range(n.value)]
+
     def stats(self) -> Stats:
         s = Stats()
         check(self._l.b200_stats_get(self._h, C.byref(s)))

@@ -186,3 +186,45 @@ def test_stop_token_and_eos():
                 fin = pr.finished
                 break
         assert toks == full[:3] and fin == "stop"
+
+
+def test_pipelined_run_matches_single_steps_and_delivers_to_waiting_threads():
+    """b200_engine_run (tokens of step N published after step N+1 is enqueued) yields the same tokens as one
+    synchronous b200_engine_step at a time, streams them to threads blocked in b200_wait, and honours aborts."""
+    from kubeai_b200.engine import Engine, mini_config
+    g = torch.Generator().manual_seed(5)
+    prompts = [torch.randint(0, 512, (n,), generator=g).tolist() for n in (5, 33, 70, 16, 121)]
+    with Engine(mini_config()) as e:
+        want = e.generate(prompts, max_tokens=20)
+    with Engine(mini_config()) as e:
+        rids = [e.submit(p, max_tokens=20) for p in prompts]
+        victim = e.submit(prompts[0], max_tokens=200)
+        got = [[] for _ in rids]
+
+        def client(i):
+            while True:
+                e.wait(rids[i], 5.0)
+                pr = e.poll(rids[i])
+                got[i] += pr.tokens
+                if pr.finished is not None:
+                    return
+
+        ths = [threading.Thread(target=client, args=(i,)) for i in range(len(rids))]
+        for t in ths:
+            t.start()
+        infos = e.run(3)
+        assert len(infos) == 3 and infos[0].tokens > 0
+        e.abort(victim)
+        total = 3
+        while any(t.is_alive() for t in ths) and total < 400:
+            total += len(e.run(8, 2000))
+        for t in ths:
+            t.join(timeout=10)
+        assert got == want
+        pr = e.poll(victim)
+        while pr.finished is None:
+            e.run(1, 1000)
+            pr = e.poll(victim)
+        assert pr.finished == "aborted"
+        st = e.stats()
+        assert st.running == 0 and st.waiting == 0

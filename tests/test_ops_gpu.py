@@ -159,7 +159,7 @@ def test_rope_bit_exact():
     assert not kv.any(), "slot -1 must not write the cache"
 
 
-def _paged_setup(seq_lens, q_lens, Hq=4, Hkv=1, seed=0, nblocks=64):
+def _paged_setup(seq_lens, q_lens, Hq=4, Hkv=1, seed=0, nblocks=64, want_raw=False):
     """Random q/k/v for several sequences; writes K/V through the rope_kvwrite kernel into a
     shuffled page pool.  Returns everything needed to call paged_attn and the oracle."""
     from kubeai_b200 import ops
@@ -171,7 +171,7 @@ def _paged_setup(seq_lens, q_lens, Hq=4, Hkv=1, seed=0, nblocks=64):
     max_blocks = (max(seq_lens) + 15) // 16
     btab = torch.zeros(len(seq_lens), max_blocks, dtype=torch.int32)
     kv = torch.zeros(nblocks, 2, Hkv, 16, D, dtype=torch.bfloat16).cuda()
-    seqs = []
+    seqs, raws = [], []
     for s, L in enumerate(seq_lens):
         nb = (L + 15) // 16
         blocks = [perm.pop() for _ in range(nb)]
@@ -180,6 +180,7 @@ def _paged_setup(seq_lens, q_lens, Hq=4, Hkv=1, seed=0, nblocks=64):
         pos = torch.arange(L, dtype=torch.int32)
         slots = torch.tensor([blocks[p // 16] * 16 + p % 16 for p in range(L)], dtype=torch.int32)
         dq = dev(qkv)
+        raws.append(qkv)
         ops.rope_kvwrite(dq, pos.cuda(), slots.cuda(), dev(cs), kv, Hq, Hkv)
         q = O.rope_neox(qkv[:, :Hq * D].reshape(L, Hq, D), pos.long(), cs)
         k = O.rope_neox(qkv[:, Hq * D:(Hq + Hkv) * D].reshape(L, Hkv, D), pos.long(), cs)
@@ -199,6 +200,8 @@ def _paged_setup(seq_lens, q_lens, Hq=4, Hkv=1, seed=0, nblocks=64):
         for p in (0, L // 2, L - 1):
             assert torch.equal(kvc[blocks[p // 16], 0, :, p % 16], k[p]), "K page write"
             assert torch.equal(kvc[blocks[p // 16], 1, :, p % 16], v[p]), "V page write"
+    if want_raw:
+        return kv, btab.cuda(), seqs, raws, cs
     return kv, btab.cuda(), seqs
 
 
@@ -217,6 +220,31 @@ def test_paged_attention_decode(seq_lens, Hkv):
         _, q, k, v, _ = seqs[i]
         want = O.attention(q[-1:], k, v, torch.tensor([L - 1]), 128 ** -0.5).reshape(1, Hq * 128)
         close(got[i:i + 1], want, atol=4e-3, what=f"decode attn seq {i} len {L}")
+
+
+@pytest.mark.parametrize("seq_lens", [[1], [16, 17], [64, 65, 128, 129], [200, 3, 129, 500, 1]])
+@pytest.mark.parametrize("Hkv", [1, 2])
+def test_paged_attention_decode_fused_rope_is_bit_identical(seq_lens, Hkv):
+    """K5+K6 in one launch == rope_kvwrite followed by decode attention: same output bits, same cache bits."""
+    from kubeai_b200 import ops
+    Hq = 4 * Hkv
+    kv, btab, seqs, raws, cs = _paged_setup(seq_lens, None, Hq, Hkv, seed=13,
+                                            nblocks=sum((l + 15) // 16 for l in seq_lens) + 5, want_raw=True)
+    work = torch.tensor([[i, 1, L - 1, i] for i, L in enumerate(seq_lens)], dtype=torch.int32).cuda()
+    rotated = torch.cat([s[0][-1:] for s in seqs], dim=0).contiguous()
+    want = ops.paged_attn(rotated, kv, btab, work, Hq, Hkv, decode=True)
+    # same cache with every sequence's newest row wiped: the fused kernel must restore exactly those rows
+    kv2 = kv.clone()
+    for i, L in enumerate(seq_lens):
+        blk = seqs[i][4][(L - 1) // 16]
+        kv2[blk, :, :, (L - 1) % 16] = 0
+    raw = dev(torch.cat([r[-1:] for r in raws], dim=0).contiguous())
+    raw_before = raw.clone()
+    got = ops.paged_attn_rope_decode(raw, kv2, btab, work, dev(cs), Hq, Hkv)
+    torch.cuda.synchronize()
+    assert torch.equal(got, want)
+    assert torch.equal(kv2, kv)
+    assert torch.equal(raw, raw_before), "the qkv buffer is read-only for the fused kernel"
 
 
 @pytest.mark.parametrize("case", [
