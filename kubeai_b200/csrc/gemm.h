@@ -11,7 +11,7 @@ namespace b200 {
 struct GemmPlan {
   CUtensorMap tm_w;  // weight [N, K] bf16, box 128 x 64, 128B swizzle
   int N, K;
-  const void* w_ptr;  // same tensor, raw pointer (L2 prefetch)
+  const void* w_ptr;  // same tensor, raw pointer
   int ldw;
   float* ws;      // fp32 partial workspace, gemm_workspace_bytes(max_ctas)
   int* counters;  // 2 ints per output tile, zero-initialised, self-resetting
@@ -36,6 +36,8 @@ size_t gemm_workspace_bytes(int max_ctas);
 int gemm_plan_init(GemmPlan* p, const void* W, int N, int K, int ldw, float* ws, int* counters, int max_ctas);
 // Activation map over X row-major [rows, K] (rows = buffer capacity), for a given token-tile size.
 int gemm_make_x_map(CUtensorMap* tm, const void* X, int rows, int K, int ldx, int block_n);
+// Output map (TMA-store epilogue of the pair kernel): out row-major [rows, N], rows = the T of the launch.
+int gemm_make_out_map(CUtensorMap* tm, const void* out, int rows, int N, int ldo);
 // variant-2 internals (gemm2_tcgen05.cu)
 int gemm2_block_n_for(int T);
 int gemm2_x_box_rows(int block_n);

@@ -18,6 +18,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <mutex>
+#include <unordered_map>
 #include <vector>
 
 #include "gemm.h"
@@ -46,7 +48,9 @@ struct Cfg2 {
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
   static constexpr int kAccStages = (2 * BLOCK_N <= 512) ? 2 : 1;
   static constexpr int kTmemCols = kAccStages * BLOCK_N < 32 ? 32 : kAccStages * BLOCK_N;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+  static constexpr int kStoreBuf = 32 * kSlab * 4;        // one staging buffer: [32 tokens][128 rows], fp32 or bf16
+  static constexpr int kStoreStage = 2 * kStoreBuf;       // double buffered
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256 + kStoreStage;
 };
 
 struct Seg {
@@ -124,7 +128,7 @@ __device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t cta) {
 template <int BLOCK_N>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 gemm2_streamk_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_x,
-                     __nv_bfloat16* __restrict__ out, int ldo, float* __restrict__ ws, int* __restrict__ counters,
+                     const __grid_constant__ CUtensorMap tm_out, int tma_store, __nv_bfloat16* __restrict__ out, int ldo, float* __restrict__ ws, int* __restrict__ counters,
                      int N, int T, int K, const int2* __restrict__ seg_table, int deferred,
                      long long* __restrict__ trace) {
   using C = Cfg2<BLOCK_N>;
@@ -166,6 +170,7 @@ gemm2_streamk_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_cons
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_w);
     tma_prefetch_desc(&tm_x);
+    if (tma_store) tma_prefetch_desc(&tm_out);
   }
   if (warp == 1) {
     if (lane == 0) {
@@ -297,6 +302,14 @@ gemm2_streamk_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_cons
     int acc = 0;
     uint32_t acc_phase = 0;
     int fix_tile[2] = {-1, -1};
+    // complete tiles leave through smem: bf16 rows staged as [32 tokens][128 weight rows] and written by TMA, so the
+    // accumulator drain is tcgen05.ld + st.shared only (scalar 2-byte global stores measured 15-18 us per 512-token
+    // tile and left the tensor pipe idle a third of the time at T=2048)
+    // (deferred) split tiles leave the same way: fp32 [32 tokens][128 rows] chunks are contiguous in the workspace
+    // slot, so each is one cp.async.bulk store.
+    const uint32_t store_stage = bar_base + 256;
+    uint8_t* store_ptr = smem_raw + (store_stage - smem_u32(smem_raw));
+    int sbuf = 0;
     for (long long it = it_begin; it < it_end;) {
       Seg sg = seg_at(it);
       const int slab2 = sg.tile / ntt, tt = sg.tile - slab2 * ntt;
@@ -325,7 +338,37 @@ gemm2_streamk_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_cons
         uint32_t v[32];
         tmem_ld_32x32(taddr + c0, v);
         tmem_ld_wait();
-        if (complete) {
+        if (complete && tma_store) {
+          if (epi_tid == 0) bulk_wait_group_read<1>();  // the store issued two chunks ago has left its buffer
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          __nv_bfloat16* sb = reinterpret_cast<__nv_bfloat16*>(store_ptr + sbuf * C::kStoreBuf);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) sb[j * kSlab + row] = __float2bfloat16_rn(__uint_as_float(v[j]));
+          fence_proxy_async();
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (epi_tid == 0) {
+            // rows t >= T and columns n >= N are clipped by the tensor map
+            tma_store_2d(&tm_out, store_stage + sbuf * C::kStoreBuf, (slab2 * 2 + static_cast<int>(rank)) * kSlab,
+                         t0 + c0);
+            bulk_commit_group();
+          }
+          sbuf ^= 1;
+        } else if (!complete && deferred && tma_store) {
+          if (epi_tid == 0) bulk_wait_group_read<1>();
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          float* sf = reinterpret_cast<float*>(store_ptr + sbuf * C::kStoreBuf);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) sf[j * kSlab + row] = __uint_as_float(v[j]);
+          fence_proxy_async();
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (epi_tid == 0) {
+            const int cols = (n_eff - c0) < 32 ? (n_eff - c0) : 32;
+            bulk_store_1d(wslot + static_cast<size_t>(c0) * kSlab, store_stage + sbuf * C::kStoreBuf,
+                          static_cast<uint32_t>(cols) * kSlab * 4);
+            bulk_commit_group();
+          }
+          sbuf ^= 1;
+        } else if (complete) {
           if (n < N) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
@@ -468,7 +511,10 @@ gemm2_streamk_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_cons
     }
   }
 
-  if (threadIdx.x == 64) mark(6);
+  if (threadIdx.x == 64) {
+    bulk_wait_group<0>();  // thread 64 (epi_tid 0) issued every TMA store of this CTA
+    mark(6);
+  }
   tc_fence_before();
   cluster_sync();  // neither CTA may exit (or free TMEM) while the peer can still signal its barriers / read its smem
   if (warp == 1) {
@@ -490,6 +536,39 @@ int units_for(const GemmPlan& p, int ntt) {
   return static_cast<int>(u < max_units ? u : max_units);
 }
 
+// Output tensor maps, one per (buffer, rows, N, ld): a handful in the engine (x, qkv, gate_up, logits x the T of the
+// step); encoding is a host-only driver call.  B200_GEMM_TMA_STORE=0 falls back to per-thread stores.
+CUtensorMap out_map_for(const void* out, int T, int N, int ldo, int* ok) {
+  struct Key {
+    const void* p;
+    int T, N, ld;
+    bool operator==(const Key& o) const { return p == o.p && T == o.T && N == o.N && ld == o.ld; }
+  };
+  struct KeyHash {
+    size_t operator()(const Key& k) const {
+      return std::hash<const void*>()(k.p) ^ (static_cast<size_t>(k.T) * 0x9E3779B97F4A7C15ull) ^
+             (static_cast<size_t>(k.N) << 20) ^ static_cast<size_t>(k.ld);
+    }
+  };
+  static const bool enabled = [] { const char* e = getenv("B200_GEMM_TMA_STORE"); return !e || atoi(e) != 0; }();
+  static std::unordered_map<Key, CUtensorMap, KeyHash> cache;
+  static std::mutex mu;
+  const CUtensorMap dummy = {};
+  *ok = 0;
+  if (!enabled) return dummy;
+  std::lock_guard<std::mutex> lk(mu);
+  const Key k{out, T, N, ldo};
+  auto it = cache.find(k);
+  if (it == cache.end()) {
+    CUtensorMap tm;
+    if (gemm_make_out_map(&tm, out, T, N, ldo) != 0) return dummy;
+    if (cache.size() > 16384) cache.clear();
+    it = cache.emplace(k, tm).first;
+  }
+  *ok = 1;
+  return it->second;
+}
+
 template <int BLOCK_N>
 int launch2(const GemmPlan& p, const CUtensorMap& tm_x, __nv_bfloat16* out, int ldo, int T, cudaStream_t st,
             int deferred = 0) {
@@ -503,8 +582,10 @@ int launch2(const GemmPlan& p, const CUtensorMap& tm_x, __nv_bfloat16* out, int 
   }
   const int ntt = (T + BLOCK_N - 1) / BLOCK_N;
   const int units = units_for(p, ntt);
+  int tma_store = 0;
+  const CUtensorMap tm_out = out_map_for(out, T, p.N, ldo, &tma_store);
   cudaError_t e = launch_pdl(gemm2_streamk_kernel<BLOCK_N>, dim3(2 * units), dim3(kThreads), C::kSmemBytes, st, p.tm_w, tm_x,
-                             out, ldo, p.ws, p.counters, p.N, T, p.K, static_cast<const int2*>(p.seg_table), deferred,
+                             tm_out, tma_store, out, ldo, p.ws, p.counters, p.N, T, p.K, static_cast<const int2*>(p.seg_table), deferred,
                              g_trace);
   return e == cudaSuccess ? 0 : -4;
 }
@@ -575,6 +656,7 @@ size_t gemm_deferred_ws_bytes(int max_ctas) {
 int gemm_run_deferred(const GemmPlan& p, const CUtensorMap& tm_x, int block_n, void* out, int ldo, int T, cudaStream_t st,
                       PartialView* view) {
   if (T <= 0 || !p.seg_table) return -8;
+  if (ldo % 8 != 0) return -5;  // consumers read the dense tiles with 16-byte loads
   const int ntt = (T + block_n - 1) / block_n;
   if (ntt > 1 && block_n != 512) return -8;   // tables are built for 512-token tiles when there are several
   if (ntt > p.max_ntt) return -8;

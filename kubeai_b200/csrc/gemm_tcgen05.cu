@@ -465,6 +465,22 @@ int gemm_plan_init(GemmPlan* p, const void* W, int N, int K, int ldw, float* ws,
   return make_tmap(&p->tm_w, W, N, K, ldw, kSlab);
 }
 
+// Output map for the TMA-store epilogue of the pair kernel: out row-major [rows, N] bf16, box = 32 rows x 128 cols,
+// no swizzle (the staging tile in smem is plain row-major); rows/cols outside the tensor are clipped by the hardware.
+int gemm_make_out_map(CUtensorMap* tm, const void* out, int rows, int N, int ldo) {
+  if (ldo % 8 != 0 || (reinterpret_cast<uintptr_t>(out) & 15) != 0) return -5;
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return -1;
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(N), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ldo) * 2};
+  cuuint32_t box[2] = {128, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(out), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -2;
+}
+
 int gemm_make_x_map(CUtensorMap* tm, const void* X, int rows, int K, int ldx, int block_n) {
   if (ldx % 8 != 0) return -5;
   return make_tmap(tm, X, rows, K, ldx, gemm_x_box_rows(block_n));

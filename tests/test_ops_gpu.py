@@ -50,6 +50,7 @@ def gemm_variant(request):
     (128, 6144, 4096),    # qkv shape
     (100, 1000, 520),     # ragged N (not /128), K not /64, T not /16
     (300, 512, 1024),     # two token tiles (256 + 44)
+    (50, 1004, 256),      # output leading dimension not a multiple of 8: per-thread stores instead of TMA
     (700, 640, 384),      # three token tiles
     (64, 4096, 14336),    # down_proj shape (deep K)
     (33, 130, 72),
@@ -70,7 +71,8 @@ def test_gemm_matches_oracle(T, N, K, gemm_variant):
 
 @pytest.mark.parametrize("T,N,K", [(128, 4096, 4096), (1, 512, 512), (40, 768, 512), (100, 1000, 520), (384, 2048, 1024),
                                    (512, 28672, 4096), (128, 128256, 4096), (17, 4096, 14336),
-                                   (2048, 4096, 4096), (1100, 768, 512), (700, 6144, 4096)])
+                                   (2048, 4096, 4096), (1100, 768, 512), (700, 6144, 4096),
+                                   (2048, 6144, 4096), (1800, 28672, 4096)])
 def test_gemm_deferred_reduction_matches_oracle(T, N, K):
     """The engine's path: complete tiles as bf16, split tiles as fp32 stream-K segments summed by the consumer."""
     from kubeai_b200 import ops
@@ -88,6 +90,13 @@ def test_gemm_repeatable_and_counters_reset(gemm_variant):
     for _ in range(5):
         b = ops.gemm(x, w)
         assert torch.equal(a, b), "stream-K fix-up must be deterministic and self-resetting"
+
+
+def test_gemm_deferred_rejects_unaligned_output_rows():
+    """Consumers of deferred partials read the dense tiles 16 bytes at a time: N % 8 != 0 is refused, not mis-read."""
+    from kubeai_b200 import B200Error, ops
+    with pytest.raises(B200Error):
+        ops.gemm_deferred(dev(rnd(50, 256, seed=1)), dev(rnd(1004, 256, seed=2)))
 
 
 @pytest.mark.parametrize("rows,H", [(7, 512), (128, 4096), (3, 1024)])
