@@ -57,32 +57,40 @@ __global__ void rmsnorm_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat1
   uint4* res = residual ? reinterpret_cast<uint4*>(residual + static_cast<size_t>(r) * H) : nullptr;
   float v[VPT][8];
   float ss = 0.f;
+  // all of this thread's loads are issued before the first use: residual vectors, then the GEMM output vectors
+  Vec8 rb[VPT];
+  if (res) {
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) rb[i].u = res[threadIdx.x + i * blockDim.x];
+  }
+  float xa[VPT][8];
+  if (pv.ws) {
+    int n0[VPT];
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) n0[i] = (threadIdx.x + i * blockDim.x) * 8;
+    load8xM_partials<VPT>(pv, r, n0, xa);  // x = bf16(sum of the GEMM's stream-K segments)
+  } else {
+    uint4 raw[VPT];
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) raw[i] = xin[threadIdx.x + i * blockDim.x];
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) unpack8_bf16(raw[i], xa[i]);
+  }
 #pragma unroll
   for (int i = 0; i < VPT; ++i) {
     const int idx = threadIdx.x + i * blockDim.x;
-    float xa[8];
-    if (pv.ws) {
-      load8_partials(pv, r, idx * 8, xa);  // x = bf16(sum of the GEMM's stream-K segments)
-    } else {
-      Vec8 a;
-      a.u = xin[idx];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) xa[j] = __bfloat162float(a.h[j]);
-    }
     if (res) {
-      Vec8 b;
-      b.u = res[idx];
       Vec8 o;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        float f = xa[j] + __bfloat162float(b.h[j]);
+        float f = xa[i][j] + __bfloat162float(rb[i].h[j]);
         o.h[j] = __float2bfloat16_rn(f);  // residual stored in input dtype ...
         v[i][j] = f;                      // ... variance from the fp32 sum (layernorm.py:51-56)
       }
       if (!row_index) res[idx] = o.u;
     } else {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[i][j] = xa[j];
+      for (int j = 0; j < 8; ++j) v[i][j] = xa[i][j];
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) ss += v[i][j] * v[i][j];
@@ -144,8 +152,14 @@ __global__ void rope_kv_kernel(__nv_bfloat16* __restrict__ qkv, const int* __res
     Vec8 co, si, o1, o2;
     float xa[8], xb[8];
     if (pv.ws) {
-      load8_partials(pv, t, head * D + c * 8, xa);
-      load8_partials(pv, t, head * D + HALF + c * 8, xb);
+      const int n0[2] = {head * D + c * 8, head * D + HALF + c * 8};
+      float xx[2][8];
+      load8xM_partials<2>(pv, t, n0, xx);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        xa[j] = xx[0][j];
+        xb[j] = xx[1][j];
+      }
     } else {
       Vec8 x1, x2;
       x1.u = *reinterpret_cast<const uint4*>(hp + c * 8);
@@ -202,7 +216,7 @@ __global__ void rope_kv_kernel(__nv_bfloat16* __restrict__ qkv, const int* __res
 }
 
 // ------------------------------------------------------------------ SiLU(gate) * up
-template <int VPT>  // uint4 vectors per thread: 1 for decode (latency), 4 for prefill bursts (bytes in flight)
+template <int VPT>  // uint4 output vectors per thread
 __global__ void silu_mul_kernel(const __nv_bfloat16* __restrict__ gu, __nv_bfloat16* __restrict__ out, int I,
                                 int ldi, PartialView pv) {
   griddep_enter(c_early_trigger);
@@ -212,24 +226,26 @@ __global__ void silu_mul_kernel(const __nv_bfloat16* __restrict__ gu, __nv_bfloa
   uint4* o = reinterpret_cast<uint4*>(out + static_cast<size_t>(t) * I);
   const int nvec = I / 8;
   const int i0 = blockIdx.x * blockDim.x * VPT + threadIdx.x;
-  float ga[VPT][8], ua[VPT][8];
+  float x[2 * VPT][8];  // gate vectors, then up vectors
+  if (pv.ws) {
+    int n0[2 * VPT];
 #pragma unroll
-  for (int k = 0; k < VPT; ++k) {
-    const int i = i0 + k * blockDim.x;
-    if (i >= nvec) continue;
-    if (pv.ws) {
-      load8_partials(pv, t, i * 8, ga[k]);
-      load8_partials(pv, t, I + i * 8, ua[k]);
-    } else {
-      Vec8 a, b;
-      a.u = g[i];
-      b.u = u[i];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        ga[k][j] = __bfloat162float(a.h[j]);
-        ua[k][j] = __bfloat162float(b.h[j]);
-      }
+    for (int k = 0; k < VPT; ++k) {
+      const int i = min(i0 + k * static_cast<int>(blockDim.x), nvec - 1);
+      n0[k] = i * 8;
+      n0[VPT + k] = I + i * 8;
     }
+    load8xM_partials<2 * VPT>(pv, t, n0, x);
+  } else {
+    uint4 raw[2 * VPT];
+#pragma unroll
+    for (int k = 0; k < VPT; ++k) {
+      const int i = min(i0 + k * static_cast<int>(blockDim.x), nvec - 1);
+      raw[k] = g[i];
+      raw[VPT + k] = u[i];
+    }
+#pragma unroll
+    for (int k = 0; k < 2 * VPT; ++k) unpack8_bf16(raw[k], x[k]);
   }
 #pragma unroll
   for (int k = 0; k < VPT; ++k) {
@@ -238,9 +254,9 @@ __global__ void silu_mul_kernel(const __nv_bfloat16* __restrict__ gu, __nv_bfloa
     Vec8 r;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float x = ga[k][j];
-      const __nv_bfloat16 s = __float2bfloat16_rn(x / (1.0f + expf(-x)));
-      r.h[j] = __float2bfloat16_rn(__bfloat162float(s) * ua[k][j]);
+      const float gv = x[k][j];
+      const __nv_bfloat16 s = __float2bfloat16_rn(gv / (1.0f + expf(-gv)));
+      r.h[j] = __float2bfloat16_rn(__bfloat162float(s) * x[VPT + k][j]);
     }
     o[i] = r.u;
   }
@@ -392,9 +408,11 @@ int silu_mul(const void* gate_up, void* out, int T, int I, cudaStream_t st, Part
   if (I % 8) return -1;
   const __nv_bfloat16* gu = static_cast<const __nv_bfloat16*>(gate_up);
   __nv_bfloat16* o = static_cast<__nv_bfloat16*>(out);
-  // one vector per thread at every T: 4 per thread measured 44% slower at T=2048 (each load is a table lookup + a
-  // data-dependent branch, so a thread's loads do not batch; occupancy hides the latency instead)
-  launch_pdl(silu_mul_kernel<1>, dim3((I / 8 + 255) / 256, T), dim3(256), 0, st, gu, o, I, 2 * I, pv);
+  // decode: one output vector per thread (2 loads in flight); prefill bursts: two (4 batched loads in flight)
+  if (T >= 512)
+    launch_pdl(silu_mul_kernel<2>, dim3((I / 8 + 511) / 512, T), dim3(256), 0, st, gu, o, I, 2 * I, pv);
+  else
+    launch_pdl(silu_mul_kernel<1>, dim3((I / 8 + 255) / 256, T), dim3(256), 0, st, gu, o, I, 2 * I, pv);
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 

@@ -29,22 +29,28 @@ struct PartialView {
 
 inline PartialView no_partials() { return PartialView{nullptr, nullptr, nullptr, 0, 0, 1, 512, 9}; }
 
-// Value of the GEMM output for token t, weight rows [n0, n0+8) (n0 % 8 == 0), as bf16-representable floats.
-__device__ __forceinline__ void load8_partials(const PartialView& v, int t, int n0, float (&o)[8]) {
-  const int slab2 = n0 >> 8, rank = (n0 >> 7) & 1, row = n0 & 127;
-  const int tt = t >> v.bn_shift, tl = t & (v.block_n - 1);
-  const int2 e = __ldg(v.table + slab2 * v.ntt + tt);
-  if (e.y == 1) {  // complete tile: already bf16 in the output tensor
-    const uint4 u = __ldcg(reinterpret_cast<const uint4*>(v.dense + static_cast<size_t>(t) * v.ld_dense + n0));
-    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+__device__ __forceinline__ int2 partial_entry(const PartialView& v, int t, int n0) {
+  return __ldg(v.table + (n0 >> 8) * v.ntt + (t >> v.bn_shift));
+}
+__device__ __forceinline__ void unpack8_bf16(const uint4& u, float (&o)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float2 f = __bfloat1622float2(h[j]);
-      o[2 * j] = f.x;
-      o[2 * j + 1] = f.y;
-    }
+  for (int j = 0; j < 4; ++j) {
+    const float2 f = __bfloat1622float2(h[j]);
+    o[2 * j] = f.x;
+    o[2 * j + 1] = f.y;
+  }
+}
+
+// Value of the GEMM output for token t, weight rows [n0, n0+8) (n0 % 8 == 0), as bf16-representable floats, given the
+// tile's table entry e.
+__device__ __forceinline__ void load8_entry(const PartialView& v, const int2 e, int t, int n0, float (&o)[8]) {
+  if (e.y == 1) {  // complete tile: already bf16 in the output tensor
+    unpack8_bf16(__ldcg(reinterpret_cast<const uint4*>(v.dense + static_cast<size_t>(t) * v.ld_dense + n0)), o);
     return;
   }
+  const int rank = (n0 >> 7) & 1, row = n0 & 127;
+  const int tl = t & (v.block_n - 1);
   const size_t stride = 2 * static_cast<size_t>(v.slot);
   const float* p = v.ws + (static_cast<size_t>(e.x) * 2 + rank) * v.slot + static_cast<size_t>(tl) * 128 + row;
   float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
@@ -76,6 +82,35 @@ __device__ __forceinline__ void load8_partials(const PartialView& v, int t, int 
   o[5] = __bfloat162float(__float2bfloat16_rn(b.y));
   o[6] = __bfloat162float(__float2bfloat16_rn(b.z));
   o[7] = __bfloat162float(__float2bfloat16_rn(b.w));
+}
+
+__device__ __forceinline__ void load8_partials(const PartialView& v, int t, int n0, float (&o)[8]) {
+  load8_entry(v, partial_entry(v, t, n0), t, n0, o);
+}
+
+// M vectors of one token at once: the table entries are looked up first and, when every tile involved is complete
+// (the common case at large T), the M 16-byte loads are issued back to back — M memory round trips overlap instead
+// of chaining lookup -> branch -> load per vector.
+template <int M>
+__device__ __forceinline__ void load8xM_partials(const PartialView& v, int t, const int (&n0)[M], float (&o)[M][8]) {
+  int2 e[M];
+  bool dense = true;
+#pragma unroll
+  for (int i = 0; i < M; ++i) {
+    e[i] = partial_entry(v, t, n0[i]);
+    dense = dense && e[i].y == 1;
+  }
+  if (dense) {
+    uint4 u[M];
+#pragma unroll
+    for (int i = 0; i < M; ++i)
+      u[i] = __ldcg(reinterpret_cast<const uint4*>(v.dense + static_cast<size_t>(t) * v.ld_dense + n0[i]));
+#pragma unroll
+    for (int i = 0; i < M; ++i) unpack8_bf16(u[i], o[i]);
+    return;
+  }
+#pragma unroll
+  for (int i = 0; i < M; ++i) load8_entry(v, e[i], t, n0[i], o[i]);
 }
 
 }  // namespace b200
