@@ -34,8 +34,6 @@ constexpr int kStageBytes = 2 * kTileBytes;     // K + V
 constexpr int kAttnSmem = 2 * kStageBytes;      // double buffered: 64 KiB
 constexpr int kFusedStage = (4 + 2) * kD * 2;   // fused decode: rotated q (4 heads), new k, new v rows (bf16)
 
-__constant__ int c_early_trigger = 0;  // B200_EARLY_TRIGGER (see griddep_enter)
-
 struct Vec8 {
   union {
     uint4 u;
@@ -58,10 +56,8 @@ paged_attn_kernel(const __nv_bfloat16* __restrict__ q, int ldq, __nv_bfloat16* _
   constexpr int NT = WT / 8;
   extern __shared__ __align__(128) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
-  if (!FUSED) griddep_enter(c_early_trigger);
 
-  // FUSED: work[] and block_tables were uploaded before the first kernel of the step, i.e. at least three kernels
-  // upstream, so they (and every cached page) are safe to read ahead of griddepcontrol.wait.
+  // work[] and block_tables were uploaded before the first kernel of the step: readable ahead of the dependency wait.
   const AttnWork wk = work[blockIdx.y];  // work items are sorted longest-first; heads are the fast grid dimension
   const int kvh = blockIdx.x;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -92,14 +88,31 @@ paged_attn_kernel(const __nv_bfloat16* __restrict__ q, int ldq, __nv_bfloat16* _
       cp_async_16(vdst + off, ksrc + kv_page, valid);
     }
   };
+  // Both stages are put in flight as early as the data allows.  Decode: every cached token except the newest was
+  // written by an earlier step, and work[] / block_tables are step inputs, so tiles that end before the newest token are
+  // gathered BEFORE the dependency wait (ptx.cuh griddep_enter) and overlap the RoPE/KV-write kernel upstream.
+  // FUSED never reads the newest row from the cache; prefill tiles may hold rows written by this step: wait first.
+  const int safe_tiles = FUSED ? ntiles : (DECODE ? wk.q_pos0 / kTile : 0);
+  bool waited = FUSED;  // FUSED waits inside its prologue below
+  if (!waited && safe_tiles < 1) {
+    griddep_enter();
+    waited = true;
+  }
   load_tile(0, 0);
   cp_async_commit();
+  if (!waited && safe_tiles < 2) {
+    griddep_enter();
+    waited = true;
+  }
+  if (ntiles > 1) load_tile(1, 1);
+  cp_async_commit();
+  if (!waited) griddep_enter();
 
   // ---- Q fragments (A operand, 16 rows x 128 d as 8 k-steps)
   uint32_t qf[8][4];
   if (FUSED) {
     __nv_bfloat16* stg = reinterpret_cast<__nv_bfloat16*>(smem + kAttnSmem);  // [4 q heads | k | v][128]
-    griddep_enter(c_early_trigger);
+    griddep_enter();
     const int Hq = 4 * Hkv, HALF = kD / 2;
     const int t = wk.q_tok0;
     const int posr = wk.q_pos0;
@@ -198,9 +211,7 @@ paged_attn_kernel(const __nv_bfloat16* __restrict__ q, int ldq, __nv_bfloat16* _
   const int wo = DECODE ? warp * 16 : 0;  // this warp's token offset inside a tile
 
   for (int t = 0; t < ntiles; ++t) {
-    if (t + 1 < ntiles) load_tile(t + 1, (t + 1) & 1);
-    cp_async_commit();
-    cp_async_wait<1>();
+    cp_async_wait<1>();  // tile t has landed; tile t+1 may still be in flight
     if (FUSED && t == ntiles - 1) {
       // the newest token's k/v row lives in the staging area: the thread that zero-filled its chunk overwrites it
       const int r = kv_end - 1 - t * kTile;
@@ -298,6 +309,8 @@ paged_attn_kernel(const __nv_bfloat16* __restrict__ q, int ldq, __nv_bfloat16* _
       }
     }
     __syncthreads();
+    if (t + 2 < ntiles) load_tile(t + 2, t & 1);  // refill the stage just consumed
+    cp_async_commit();
   }
   cp_async_wait<0>();
 
@@ -359,10 +372,6 @@ paged_attn_kernel(const __nv_bfloat16* __restrict__ q, int ldq, __nv_bfloat16* _
 }
 
 }  // namespace
-
-int attention_set_early_trigger(int on) {
-  return cudaMemcpyToSymbol(c_early_trigger, &on, sizeof(int)) == cudaSuccess ? 0 : -2;
-}
 
 static int attn_attrs() {
   static int state = 0;  // 0 = not set, 1 = ok, -1 = failed

@@ -18,8 +18,6 @@ namespace b200 {
 
 namespace {
 
-__constant__ int c_early_trigger = 0;  // B200_EARLY_TRIGGER (see griddep_enter)
-
 union Vec8 {
   uint4 u;
   __nv_bfloat16 h[8];
@@ -34,7 +32,7 @@ __device__ __forceinline__ float warp_sum(float v) {
 // ------------------------------------------------------------------ embedding gather
 __global__ void embed_kernel(const __nv_bfloat16* __restrict__ table, const int* __restrict__ ids,
                              __nv_bfloat16* __restrict__ out, int H, int vocab) {
-  griddep_enter(c_early_trigger);
+  griddep_enter();
   const int t = blockIdx.x;
   int id = ids[t];
   if (id < 0 || id >= vocab) id = 0;
@@ -50,25 +48,30 @@ template <int VPT>  // uint4 vectors per thread (H = VPT * 8 * blockDim)
 __global__ void rmsnorm_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ residual,
                                const __nv_bfloat16* __restrict__ w, __nv_bfloat16* __restrict__ out,
                                const int* __restrict__ row_index, int H, float eps, PartialView pv) {
-  griddep_enter(c_early_trigger);
+  // ---- before the dependency wait (ptx.cuh griddep_enter): everything that does not come from the producer GEMM —
+  // the row index (step input), the residual (written four or more launches upstream), the norm weight and the
+  // partial-segment table entries (static)
   const int s = blockIdx.x;
   const int r = row_index ? row_index[s] : s;
   const uint4* xin = reinterpret_cast<const uint4*>(x + static_cast<size_t>(r) * H);
   uint4* res = residual ? reinterpret_cast<uint4*>(residual + static_cast<size_t>(r) * H) : nullptr;
   float v[VPT][8];
   float ss = 0.f;
-  // all of this thread's loads are issued before the first use: residual vectors, then the GEMM output vectors
-  Vec8 rb[VPT];
-  if (res) {
+  Vec8 rb[VPT], ww[VPT];
+  int n0[VPT];
+  int2 ent[VPT];
 #pragma unroll
-    for (int i = 0; i < VPT; ++i) rb[i].u = res[threadIdx.x + i * blockDim.x];
+  for (int i = 0; i < VPT; ++i) {
+    const int idx = threadIdx.x + i * blockDim.x;
+    n0[i] = idx * 8;
+    ww[i].u = __ldg(reinterpret_cast<const uint4*>(w) + idx);
+    if (res) rb[i].u = res[idx];
   }
+  if (pv.ws) partial_entries<VPT>(pv, r, n0, ent);
+  griddep_enter();
   float xa[VPT][8];
   if (pv.ws) {
-    int n0[VPT];
-#pragma unroll
-    for (int i = 0; i < VPT; ++i) n0[i] = (threadIdx.x + i * blockDim.x) * 8;
-    load8xM_partials<VPT>(pv, r, n0, xa);  // x = bf16(sum of the GEMM's stream-K segments)
+    load8xM_entries<VPT>(pv, ent, r, n0, xa);  // x = bf16(sum of the GEMM's stream-K segments)
   } else {
     uint4 raw[VPT];
 #pragma unroll
@@ -106,18 +109,16 @@ __global__ void rmsnorm_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat1
   }
   __syncthreads();
   const float inv = rsqrtf(red[0] / static_cast<float>(H) + eps);
-  const uint4* wv = reinterpret_cast<const uint4*>(w);
   uint4* o4 = reinterpret_cast<uint4*>(out + static_cast<size_t>(s) * H);
 #pragma unroll
   for (int i = 0; i < VPT; ++i) {
     const int idx = threadIdx.x + i * blockDim.x;
-    Vec8 ww, o;
-    ww.u = __ldg(wv + idx);
+    Vec8 o;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       // normalised value rounded to bf16 BEFORE the weight multiply (layernorm.py:19)
       __nv_bfloat16 nb = __float2bfloat16_rn(v[i][j] * inv);
-      o.h[j] = __float2bfloat16_rn(__bfloat162float(nb) * __bfloat162float(ww.h[j]));
+      o.h[j] = __float2bfloat16_rn(__bfloat162float(nb) * __bfloat162float(ww[i].h[j]));
     }
     o4[idx] = o.u;
   }
@@ -129,9 +130,10 @@ __global__ void rmsnorm_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat1
 __global__ void rope_kv_kernel(__nv_bfloat16* __restrict__ qkv, const int* __restrict__ positions,
                                const int* __restrict__ slots, const __nv_bfloat16* __restrict__ cos_sin,
                                __nv_bfloat16* __restrict__ kv, int Hq, int Hkv, int max_pos, PartialView pv) {
-  griddep_enter(c_early_trigger);
   constexpr int D = 128, HALF = 64;
   const int t = blockIdx.x;
+  // ---- before the dependency wait: step inputs (positions, slots), cos/sin rows and table entries (static).  The
+  // first task of every thread is prepared here; later tasks (only when blockDim < tasks) look theirs up afterwards.
   int pos = positions[t];
   pos = pos < 0 ? 0 : (pos >= max_pos ? max_pos - 1 : pos);
   const int slot = slots[t];
@@ -145,16 +147,36 @@ __global__ void rope_kv_kernel(__nv_bfloat16* __restrict__ qkv, const int* __res
 
   const int rot_tasks = (Hq + Hkv) * (HALF / 8);  // 8 elements of x1 (and the matching 8 of x2) per task
   const int v_tasks = Hkv * (D / 8);
+  Vec8 co0, si0;
+  int2 ent0[2] = {make_int2(0, 1), make_int2(0, 1)};
+  if (static_cast<int>(threadIdx.x) < rot_tasks) {
+    const int head = threadIdx.x >> 3, c = threadIdx.x & 7;
+    co0.u = __ldg(reinterpret_cast<const uint4*>(cs + c * 8));
+    si0.u = __ldg(reinterpret_cast<const uint4*>(cs + HALF + c * 8));
+    if (pv.ws) {
+      const int n0[2] = {head * D + c * 8, head * D + HALF + c * 8};
+      partial_entries<2>(pv, t, n0, ent0);
+    }
+  }
+  griddep_enter();
   // rotation tasks and V-copy tasks share one index space so that a 512-thread CTA gives every thread one task
   for (int task = threadIdx.x; task < rot_tasks; task += blockDim.x) {
     const int head = task >> 3, c = task & 7;
+    const bool first = task == static_cast<int>(threadIdx.x);
     __nv_bfloat16* hp = row + head * D;
     Vec8 co, si, o1, o2;
     float xa[8], xb[8];
     if (pv.ws) {
       const int n0[2] = {head * D + c * 8, head * D + HALF + c * 8};
+      int2 ent[2];
+      if (first) {
+        ent[0] = ent0[0];
+        ent[1] = ent0[1];
+      } else {
+        partial_entries<2>(pv, t, n0, ent);
+      }
       float xx[2][8];
-      load8xM_partials<2>(pv, t, n0, xx);
+      load8xM_entries<2>(pv, ent, t, n0, xx);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         xa[j] = xx[0][j];
@@ -170,8 +192,13 @@ __global__ void rope_kv_kernel(__nv_bfloat16* __restrict__ qkv, const int* __res
         xb[j] = __bfloat162float(x2.h[j]);
       }
     }
-    co.u = __ldg(reinterpret_cast<const uint4*>(cs + c * 8));
-    si.u = __ldg(reinterpret_cast<const uint4*>(cs + HALF + c * 8));
+    if (first) {
+      co = co0;
+      si = si0;
+    } else {
+      co.u = __ldg(reinterpret_cast<const uint4*>(cs + c * 8));
+      si.u = __ldg(reinterpret_cast<const uint4*>(cs + HALF + c * 8));
+    }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float a = xa[j], b = xb[j];
@@ -219,7 +246,6 @@ __global__ void rope_kv_kernel(__nv_bfloat16* __restrict__ qkv, const int* __res
 template <int VPT>  // uint4 output vectors per thread
 __global__ void silu_mul_kernel(const __nv_bfloat16* __restrict__ gu, __nv_bfloat16* __restrict__ out, int I,
                                 int ldi, PartialView pv) {
-  griddep_enter(c_early_trigger);
   const int t = blockIdx.y;
   const uint4* g = reinterpret_cast<const uint4*>(gu + static_cast<size_t>(t) * ldi);
   const uint4* u = reinterpret_cast<const uint4*>(gu + static_cast<size_t>(t) * ldi + I);
@@ -227,22 +253,24 @@ __global__ void silu_mul_kernel(const __nv_bfloat16* __restrict__ gu, __nv_bfloa
   const int nvec = I / 8;
   const int i0 = blockIdx.x * blockDim.x * VPT + threadIdx.x;
   float x[2 * VPT][8];  // gate vectors, then up vectors
-  if (pv.ws) {
-    int n0[2 * VPT];
+  int n0[2 * VPT];
+  int2 ent[2 * VPT];
 #pragma unroll
-    for (int k = 0; k < VPT; ++k) {
-      const int i = min(i0 + k * static_cast<int>(blockDim.x), nvec - 1);
-      n0[k] = i * 8;
-      n0[VPT + k] = I + i * 8;
-    }
-    load8xM_partials<2 * VPT>(pv, t, n0, x);
+  for (int k = 0; k < VPT; ++k) {
+    const int i = min(i0 + k * static_cast<int>(blockDim.x), nvec - 1);
+    n0[k] = i * 8;
+    n0[VPT + k] = I + i * 8;
+  }
+  if (pv.ws) partial_entries<2 * VPT>(pv, t, n0, ent);  // static table: looked up before the dependency wait
+  griddep_enter();
+  if (pv.ws) {
+    load8xM_entries<2 * VPT>(pv, ent, t, n0, x);
   } else {
     uint4 raw[2 * VPT];
 #pragma unroll
     for (int k = 0; k < VPT; ++k) {
-      const int i = min(i0 + k * static_cast<int>(blockDim.x), nvec - 1);
-      raw[k] = g[i];
-      raw[VPT + k] = u[i];
+      raw[k] = g[n0[k] >> 3];
+      raw[VPT + k] = u[n0[k] >> 3];
     }
 #pragma unroll
     for (int k = 0; k < 2 * VPT; ++k) unpack8_bf16(raw[k], x[k]);
@@ -265,7 +293,7 @@ __global__ void silu_mul_kernel(const __nv_bfloat16* __restrict__ gu, __nv_bfloa
 // ------------------------------------------------------------------ greedy argmax over bf16 logits
 __global__ void argmax_kernel(const __nv_bfloat16* __restrict__ logits, int* __restrict__ out, int V, int ld,
                               PartialView pv) {
-  griddep_enter(c_early_trigger);
+  griddep_enter();
   const int s = blockIdx.x;
   const __nv_bfloat16* row = logits + static_cast<size_t>(s) * ld;
   float best = -INFINITY;
@@ -421,10 +449,6 @@ int argmax_rows(const void* logits, int* out, int S, int V, int ld, cudaStream_t
   if (ld % 8 || (pv.ws && V % 8)) return -1;
   launch_pdl(argmax_kernel, dim3(S), dim3(1024), 0, st, static_cast<const __nv_bfloat16*>(logits), out, V, ld, pv);
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
-}
-
-int elementwise_set_early_trigger(int on) {
-  return cudaMemcpyToSymbol(c_early_trigger, &on, sizeof(int)) == cudaSuccess ? 0 : -2;
 }
 
 int init_uniform(void* p, size_t n, uint32_t seed, float scale, float offset, cudaStream_t st) {

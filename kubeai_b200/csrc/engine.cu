@@ -445,11 +445,6 @@ int Engine::alloc_all() {
   }
   if (plan(&p_lm, lm_head, V, H)) return cuda_fail("gemm_plan_init(lm_head)", -2);
   deferred_ok = gemm_variant() == 2;
-  {
-    const char* e = getenv("B200_EARLY_TRIGGER");  // A/B knob, see ptx.cuh griddep_enter
-    const int early = e ? atoi(e) : 0;
-    if (elementwise_set_early_trigger(early) || attention_set_early_trigger(early)) return cuda_fail("early trigger", -2);
-  }
   const int bns[kGemmNumBlockN] = {32, 64, 128, 256, 512};
   for (int i = 0; i < kGemmNumBlockN; ++i) {
     if (gemm_make_x_map(&xm_normed.m[i], normed, Tcap, H, H, bns[i]) ||

@@ -512,7 +512,9 @@ gemm2_streamk_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_cons
   }
 
   if (threadIdx.x == 64) {
-    bulk_wait_group<0>();  // thread 64 (epi_tid 0) issued every TMA store of this CTA
+    // thread 64 (epi_tid 0) issued every bulk store of this CTA: its smem source must outlive the reads; the writes
+    // themselves are ordered before the dependent kernel by grid completion (as in any TMA-store epilogue)
+    bulk_wait_group_read<0>();
     mark(6);
   }
   tc_fence_before();
@@ -524,7 +526,15 @@ gemm2_streamk_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_cons
   if (threadIdx.x == 64) mark(7);
 }
 
-long long* g_trace = nullptr;  // debug: device buffer of 8 stamps per CTA (b200_op_gemm_trace)
+// debug (b200_op_gemm_trace): device buffer of B200_GEMM_TRACE_LAUNCHES (default 1) blocks of 148 x 16 stamps;
+// launch i after the buffer was set writes block i mod that count
+long long* g_trace = nullptr;
+int g_trace_launch = 0;
+long long* trace_block() {
+  static const int blocks = [] { const char* e = getenv("B200_GEMM_TRACE_LAUNCHES"); return e && atoi(e) > 0 ? atoi(e) : 1; }();
+  if (!g_trace) return nullptr;
+  return g_trace + static_cast<size_t>(g_trace_launch++ % blocks) * 148 * 16;
+}
 
 int units_for(const GemmPlan& p, int ntt) {
   const int pairs_n = (p.N + 2 * kSlab - 1) / (2 * kSlab);
@@ -586,7 +596,7 @@ int launch2(const GemmPlan& p, const CUtensorMap& tm_x, __nv_bfloat16* out, int 
   const CUtensorMap tm_out = out_map_for(out, T, p.N, ldo, &tma_store);
   cudaError_t e = launch_pdl(gemm2_streamk_kernel<BLOCK_N>, dim3(2 * units), dim3(kThreads), C::kSmemBytes, st, p.tm_w, tm_x,
                              tm_out, tma_store, out, ldo, p.ws, p.counters, p.N, T, p.K, static_cast<const int2*>(p.seg_table), deferred,
-                             g_trace);
+                             trace_block());
   return e == cudaSuccess ? 0 : -4;
 }
 
@@ -690,7 +700,10 @@ int reduce_partials(const PartialView& v, void* out, int ldo, int T, int N, cuda
   return e == cudaSuccess ? 0 : -4;
 }
 
-void gemm2_set_trace(long long* dev_ptr) { g_trace = dev_ptr; }
+void gemm2_set_trace(long long* dev_ptr) {
+  g_trace = dev_ptr;
+  g_trace_launch = 0;
+}
 
 int gemm2_block_n_for(int T) { return T <= 32 ? 32 : T <= 64 ? 64 : T <= 128 ? 128 : T <= 256 ? 256 : 512; }
 int gemm2_x_box_rows(int block_n) { return (block_n > 256 ? 256 : block_n) / 2; }

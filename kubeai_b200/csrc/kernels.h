@@ -22,11 +22,6 @@ int silu_mul(const void* gate_up, void* out, int T, int I, cudaStream_t st, Part
 int argmax_rows(const void* logits, int* out, int S, int V, int ld, cudaStream_t st, PartialView pv = no_partials());
 int init_uniform(void* p, size_t n, uint32_t seed, float scale, float offset, cudaStream_t st);
 
-// PDL ordering knob (B200_EARLY_TRIGGER): non-zero makes these kernels release their dependent launch before waiting
-// for their own producer (ptx.cuh griddep_enter).
-int elementwise_set_early_trigger(int on);
-int attention_set_early_trigger(int on);
-
 // One unit of attention work: q_count query tokens of one sequence starting at row q_tok0 of the
 // step's token batch; the first of them sits at absolute position q_pos0 in the sequence.
 struct AttnWork {

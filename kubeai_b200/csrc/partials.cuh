@@ -88,18 +88,22 @@ __device__ __forceinline__ void load8_partials(const PartialView& v, int t, int 
   load8_entry(v, partial_entry(v, t, n0), t, n0, o);
 }
 
-// M vectors of one token at once: the table entries are looked up first and, when every tile involved is complete
-// (the common case at large T), the M 16-byte loads are issued back to back — M memory round trips overlap instead
-// of chaining lookup -> branch -> load per vector.
+// M vectors of one token at once.  The table entries are static per (plan, token-tile count), so a kernel looks them
+// up BEFORE its dependency wait (partial_entries) and only the data loads follow it (load8xM_entries).  When every tile
+// involved is complete (the common case at large T) the M 16-byte loads are issued back to back — M memory round
+// trips overlap instead of chaining lookup -> branch -> load per vector.
 template <int M>
-__device__ __forceinline__ void load8xM_partials(const PartialView& v, int t, const int (&n0)[M], float (&o)[M][8]) {
-  int2 e[M];
+__device__ __forceinline__ void partial_entries(const PartialView& v, int t, const int (&n0)[M], int2 (&e)[M]) {
+#pragma unroll
+  for (int i = 0; i < M; ++i) e[i] = partial_entry(v, t, n0[i]);
+}
+
+template <int M>
+__device__ __forceinline__ void load8xM_entries(const PartialView& v, const int2 (&e)[M], int t, const int (&n0)[M],
+                                                float (&o)[M][8]) {
   bool dense = true;
 #pragma unroll
-  for (int i = 0; i < M; ++i) {
-    e[i] = partial_entry(v, t, n0[i]);
-    dense = dense && e[i].y == 1;
-  }
+  for (int i = 0; i < M; ++i) dense = dense && e[i].y == 1;
   if (dense) {
     uint4 u[M];
 #pragma unroll
@@ -111,6 +115,13 @@ __device__ __forceinline__ void load8xM_partials(const PartialView& v, int t, co
   }
 #pragma unroll
   for (int i = 0; i < M; ++i) load8_entry(v, e[i], t, n0[i], o[i]);
+}
+
+template <int M>
+__device__ __forceinline__ void load8xM_partials(const PartialView& v, int t, const int (&n0)[M], float (&o)[M][8]) {
+  int2 e[M];
+  partial_entries<M>(v, t, n0, e);
+  load8xM_entries<M>(v, e, t, n0, o);
 }
 
 }  // namespace b200

@@ -35,17 +35,15 @@ __device__ __forceinline__ bool elect_one() {
 // at its own griddepcontrol.wait for our completion before touching dependent data).
 __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-// Entry sequence of every non-GEMM kernel.  early == 0: wait for the producer, then let the consumer launch (its
-// prologue overlaps only this kernel).  early != 0: release the consumer first, so a GEMM two launches downstream can
-// take SMs (and prefetch weights) as soon as the GEMM upstream of this kernel drains; it still waits for us to finish.
-__device__ __forceinline__ void griddep_enter(int early) {
-  if (early) {
-    griddep_launch();
-    griddep_wait();
-  } else {
-    griddep_wait();
-    griddep_launch();
-  }
+// Dependency point of every non-GEMM kernel: wait for the producer, THEN let the consumer launch.  GEMMs release their
+// consumer at entry (before their own wait).  Consequence used by the kernels' pre-wait prologues: code that runs
+// before griddep_enter() in kernel K_n may read
+//   * anything written by K_{n-2} or earlier when K_{n-1} is a non-GEMM kernel,
+//   * anything written by K_{n-3} or earlier when K_{n-1} is a GEMM (two GEMMs are never adjacent),
+//   * per-step inputs uploaded before the step's first kernel, and static tables (weights, cos/sin, segment tables).
+__device__ __forceinline__ void griddep_enter() {
+  griddep_wait();
+  griddep_launch();
 }
 
 // ---------------------------------------------------------------- mbarrier
