@@ -287,14 +287,6 @@ int b200_op_argmax(const void* logits, int32_t* out, int32_t S, int32_t V, int32
 int b200_op_paged_attn(const void* q, int32_t ldq, void* out, int32_t ldo, const void* kv_layer,
                        const int32_t* block_tables, int32_t max_blocks, const int32_t* work, int32_t num_work,
                        int32_t q_heads, int32_t kv_heads, float scale, int32_t decode, void* stream);
-/* Decode attention with RoPE + KV write fused in (K5 + K6 in one launch; every work item has q_count == 1): reads the
- * un-rotated q|k|v rows of `qkv`, writes the rotated k and v into kv_layer at the token's page slot
- * (block_tables[seq][pos >> 4], pos & 15) and attends over [0, pos].  Bit-identical to b200_op_rope_kvwrite followed by
- * b200_op_paged_attn(decode=1); `qkv` itself is left un-rotated. */
-int b200_op_paged_attn_rope_decode(const void* qkv, int32_t ldq, void* out, int32_t ldo, void* kv_layer,
-                                   const int32_t* block_tables, int32_t max_blocks, const int32_t* work,
-                                   int32_t num_work, int32_t q_heads, int32_t kv_heads, float scale,
-                                   const void* cos_sin, int32_t max_pos, void* stream);
 int b200_op_init_uniform(void* p, uint64_t n, uint32_t seed, float scale, float offset, void* stream);
 
 #ifdef __cplusplus

@@ -179,17 +179,6 @@ int b200_op_paged_attn(const void* q, int32_t ldq, void* out, int32_t ldo, const
   return rc ? cuda_fail("paged_attention", rc) : 0;
 }
 
-int b200_op_paged_attn_rope_decode(const void* qkv, int32_t ldq, void* out, int32_t ldo, void* kv_layer,
-                                   const int32_t* block_tables, int32_t max_blocks, const int32_t* work,
-                                   int32_t num_work, int32_t q_heads, int32_t kv_heads, float scale,
-                                   const void* cos_sin, int32_t max_pos, void* stream) {
-  if (int rc = require_device()) return rc;
-  int rc = paged_attention_rope_decode(qkv, ldq, out, ldo, kv_layer, block_tables, max_blocks,
-                                       reinterpret_cast<const AttnWork*>(work), num_work, q_heads, kv_heads, scale,
-                                       cos_sin, max_pos, static_cast<cudaStream_t>(stream));
-  return rc ? cuda_fail("paged_attention_rope_decode", rc) : 0;
-}
-
 int b200_op_init_uniform(void* p, uint64_t n, uint32_t seed, float scale, float offset, void* stream) {
   if (int rc = require_device()) return rc;
   int rc = init_uniform(p, n, seed, scale, offset, static_cast<cudaStream_t>(stream));

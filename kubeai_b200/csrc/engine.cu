@@ -470,6 +470,8 @@ int Engine::alloc_all() {
   if (nblocks > (1 << 27)) nblocks = 1 << 27;
   kv_layer_elems = static_cast<size_t>(nblocks) * 2 * Hkv * kPage * kD;
   CK(cudaMalloc(&kv, kv_layer_elems * 2 * L));
+  // the attention kernel gathers whole pages and masks the rows past a sequence's end: those rows must be finite
+  CK(cudaMemsetAsync(kv, 0, kv_layer_elems * 2 * L, stream));
   pool.init(nblocks, cfg.enable_prefix_caching != 0);
 
   // ---- step input ring
@@ -544,12 +546,6 @@ int Engine::forward(const StepMeta& m, int32_t* dbuf, bool all_logits, bf16* log
     return e ? atoi(e) : (1 << 30);
   }();
   const bool dfr = deferred_ok && !all_logits && T <= defer_max_t;
-  static const bool fuse_rope_env = [] {
-    const char* e = getenv("B200_FUSE_ROPE");  // A/B knob: 1 folds RoPE + KV write into the decode attention kernel
-    return e && atoi(e) != 0;  // default off: measured 6.14 vs 6.01 ms per decode step (the prologue's latency chain
-                               // costs every attention CTA more than the saved launch)
-  }();
-  const bool fuse_rope = fuse_rope_env && m.np == 0 && m.nd == T && !all_logits;
   PartialView pv_x = no_partials();  // partials of the GEMM whose output is `x` (o_proj / down_proj)
   for (int l = 0; l < L && !rc; ++l) {
     Layer& ly = layers[l];
@@ -564,20 +560,10 @@ int Engine::forward(const StepMeta& m, int32_t* dbuf, bool all_logits, bf16* log
     if (!on(B200_K_GEMM_QKV)) {}
     else if (dfr) rc |= gemm_def(ly.p_qkv, xm_normed, qkv, QKV, T, &pv); else rc |= gemm(ly.p_qkv, xm_normed, qkv, QKV, T);
     Q();
-    if (fuse_rope) {
-      // pure-decode step: RoPE + KV write ride in the attention kernel's prologue (one launch fewer per layer)
-      P(B200_K_ATTN_DECODE);
-      if (on(B200_K_ATTN_DECODE))
-        rc |= paged_attention_rope_decode(qkv, QKV, attn, Hq * kD, kv_l, btab, max_blocks_per_seq, dwork, m.nd, Hq, Hkv,
-                                          scale, cos_sin, cfg.max_model_len, stream, pv);
-      Q();
-      launched(2);
-    } else {
     P(B200_K_ROPE); if (on(B200_K_ROPE)) rc |= rope_kv_write(qkv, pos, slots, cos_sin, kv_l, T, Hq, Hkv, cfg.max_model_len, stream, pv); Q();
     launched(2);
     if (m.nd) { P(B200_K_ATTN_DECODE); if (on(B200_K_ATTN_DECODE)) rc |= paged_attention(qkv, QKV, attn, Hq * kD, kv_l, btab, max_blocks_per_seq, dwork, m.nd, Hq, Hkv, scale, 1, stream); Q(); launched(1); }
     if (m.np) { P(B200_K_ATTN_PREFILL); if (on(B200_K_ATTN_PREFILL)) rc |= paged_attention(qkv, QKV, attn, Hq * kD, kv_l, btab, max_blocks_per_seq, pwork, m.np, Hq, Hkv, scale, 0, stream); Q(); launched(1); }
-    }
     P(B200_K_GEMM_O);
     if (!on(B200_K_GEMM_O)) {}
     else if (dfr) rc |= gemm_def(ly.p_o, xm_attn, x, H, T, &pv_x); else rc |= gemm(ly.p_o, xm_attn, x, H, T);

@@ -36,6 +36,9 @@ size_t gemm_workspace_bytes(int max_ctas);
 int gemm_plan_init(GemmPlan* p, const void* W, int N, int K, int ldw, float* ws, int* counters, int max_ctas);
 // Activation map over X row-major [rows, K] (rows = buffer capacity), for a given token-tile size.
 int gemm_make_x_map(CUtensorMap* tm, const void* X, int rows, int K, int ldx, int block_n);
+// Generic 2-D bf16 tensor map (used by the attention kernel for the paged KV cache).
+int tmap_encode_bf16_2d(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, int box_rows,
+                        int box_cols, int swizzle128);
 // Output map (TMA-store epilogue of the pair kernel): out row-major [rows, N], rows = the T of the launch.
 int gemm_make_out_map(CUtensorMap* tm, const void* out, int rows, int N, int ldo);
 // variant-2 internals (gemm2_tcgen05.cu)

@@ -465,6 +465,22 @@ int gemm_plan_init(GemmPlan* p, const void* W, int N, int K, int ldw, float* ws,
   return make_tmap(&p->tm_w, W, N, K, ldw, kSlab);
 }
 
+// Generic 2-D bf16 map: row-major [rows, cols] with leading dimension ld (elements), box = box_rows x box_cols,
+// 128-byte swizzle when box_cols * 2 == 128 and swizzle128 != 0.
+int tmap_encode_bf16_2d(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, int box_rows,
+                        int box_cols, int swizzle128) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return -1;
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -2;
+}
+
 // Output map for the TMA-store epilogue of the pair kernel: out row-major [rows, N] bf16, box = 32 rows x 128 cols,
 // no swizzle (the staging tile in smem is plain row-major); rows/cols outside the tensor are clipped by the hardware.
 int gemm_make_out_map(CUtensorMap* tm, const void* out, int rows, int N, int ldo) {

@@ -39,11 +39,4 @@ int paged_attention(const void* q, int ldq, void* out, int ldo, const void* kv_l
                     int max_blocks, const AttnWork* work, int num_work, int Hq, int Hkv, float scale,
                     int decode, cudaStream_t st);
 
-// Decode attention with the token's RoPE + KV write fused in (every work item has q_count == 1): q|k|v rows come from
-// the QKV GEMM output `qkv` (or its deferred partials `pv`), the rotated k and v are written to the paged cache at
-// (block_tables[seq][pos >> 4], pos & 15), pos = work.q_pos0.  Bit-identical to rope_kv_write + paged_attention.
-int paged_attention_rope_decode(const void* qkv, int ldq, void* out, int ldo, void* kv_layer, const int* block_tables,
-                                int max_blocks, const AttnWork* work, int num_work, int Hq, int Hkv, float scale,
-                                const void* cos_sin, int max_pos, cudaStream_t st, PartialView pv = no_partials());
-
 }  // namespace b200

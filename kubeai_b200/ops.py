@@ -91,17 +91,6 @@ def paged_attn(qkv, kv_layer, block_tables, work, q_heads, kv_heads, decode: boo
     return out
 
 
-def paged_attn_rope_decode(qkv, kv_layer, block_tables, work, cos_sin, q_heads, kv_heads, out=None):
-    """Fused K5+K6: `qkv` holds the un-rotated q|k|v rows; kv_layer receives each token's rotated k and v."""
-    _chk(qkv), _chk(kv_layer), _chk(block_tables, torch.int32), _chk(work, torch.int32), _chk(cos_sin)
-    if out is None:
-        out = torch.zeros(qkv.shape[0], q_heads * 128, dtype=torch.bfloat16, device=qkv.device)
-    check(lib().b200_op_paged_attn_rope_decode(_p(qkv), qkv.shape[1], _p(out), out.shape[1], _p(kv_layer),
-                                               _p(block_tables), block_tables.shape[1], _p(work), work.shape[0],
-                                               q_heads, kv_heads, 128 ** -0.5, _p(cos_sin), cos_sin.shape[0], _stream()))
-    return out
-
-
 def init_uniform(n, seed, scale, offset, device="cuda"):
     out = torch.empty(n, dtype=torch.bfloat16, device=device)
     check(lib().b200_op_init_uniform(_p(out), n, seed & 0xFFFFFFFF, scale, offset, _stream()))
