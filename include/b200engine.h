@@ -132,6 +132,11 @@ enum { B200_K_EMBED = 0, B200_K_NORM, B200_K_GEMM_QKV, B200_K_ROPE, B200_K_ATTN_
 /* Re-run the last `n` recorded steps with a CUDA-event pair around every launch (on the engine's
  * stream) and return total microseconds and launch counts per kernel class (arrays of B200_K_NUM). */
 int b200_engine_profile(b200_engine* e, int32_t n, double* class_us, int64_t* class_launches, int32_t num_classes);
+/* Same, restricted to the recorded steps whose token count lies in [min_tokens, max_tokens] (decode-only steps vs
+ * prefill bursts); also returns how many steps matched and their token / sampled-row / KV-token totals. */
+int b200_engine_profile_range(b200_engine* e, int32_t n, int32_t min_tokens, int32_t max_tokens, double* class_us,
+                              int64_t* class_launches, int32_t num_classes, int64_t* steps, int64_t* tokens,
+                              int64_t* sampled, int64_t* kv_tokens_read);
 /* Drop every cached prefix block (after a replay, which clobbers KV contents). */
 int b200_engine_reset_prefix_cache(b200_engine* e);
 

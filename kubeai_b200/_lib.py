@@ -114,6 +114,8 @@ SYMBOLS = {
     "b200_engine_set_skip_mask": (C.c_int, [_vp, C.c_uint32]),
     "b200_engine_set_recording": (C.c_int, [_vp, _i32]),
     "b200_engine_profile": (C.c_int, [_vp, _i32, C.POINTER(C.c_double), C.POINTER(_i64), _i32]),
+    "b200_engine_profile_range": (C.c_int, [_vp, _i32, _i32, _i32, C.POINTER(C.c_double), C.POINTER(_i64), _i32,
+                                            C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64)]),
     "b200_engine_tensor_info": (C.c_int, [_vp, C.c_char_p, C.POINTER(_u64), C.POINTER(_vp)]),
     "b200_engine_tensor_read": (C.c_int, [_vp, C.c_char_p, _vp, _u64]),
     "b200_engine_tensor_write": (C.c_int, [_vp, C.c_char_p, _vp, _u64]),

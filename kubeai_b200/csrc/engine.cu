@@ -1197,19 +1197,24 @@ int b200_engine_set_recording(b200_engine* e, int32_t on) {
   return 0;
 }
 
-int b200_engine_profile(b200_engine* e, int32_t n, double* class_us, int64_t* class_launches, int32_t num_classes) {
+int b200_engine_profile_range(b200_engine* e, int32_t n, int32_t min_tokens, int32_t max_tokens, double* class_us,
+                              int64_t* class_launches, int32_t num_classes, int64_t* steps, int64_t* tokens,
+                              int64_t* sampled, int64_t* kv_tokens_read) {
   if (!e || n <= 0 || !class_us || !class_launches || num_classes < B200_K_NUM) { set_error("b200_engine_profile: bad arguments"); return B200_ERR_INVALID; }
   Engine& g = e->impl;
   if (!g.cfg.manual_step) { set_error("profile needs manual_step"); return B200_ERR_INVALID; }
   if (n > g.ring_n - 1 || n > g.recorded) { set_error("only %lld steps recorded", static_cast<long long>(g.recorded)); return B200_ERR_INVALID; }
   cudaSetDevice(g.cfg.device);
   for (int i = 0; i < num_classes; ++i) { class_us[i] = 0; class_launches[i] = 0; }
+  int64_t ns = 0, nt = 0, nsm = 0, nkv = 0;
   const int rn = g.ring_n - 1;
   for (int i = n; i >= 1; --i) {
     const int slot = ((g.ring_pos - i) % rn + rn) % rn;
+    const StepMeta& m = g.ring_meta[slot];
+    if (m.T < min_tokens || m.T > max_tokens) continue;
     g.profiling = true;
     g.prof_used = 0;
-    int rc = g.forward(g.ring_meta[slot], g.stage_dev[slot], false, nullptr);
+    int rc = g.forward(m, g.stage_dev[slot], false, nullptr);
     g.profiling = false;
     if (rc) return rc;
     CK(cudaStreamSynchronize(g.stream));
@@ -1219,8 +1224,18 @@ int b200_engine_profile(b200_engine* e, int32_t n, double* class_us, int64_t* cl
       class_us[g.prof_events[k].first] += ms * 1000.0;
       class_launches[g.prof_events[k].first] += 1;
     }
+    ++ns; nt += m.T; nsm += m.S; nkv += m.kv_tokens;
   }
+  if (steps) *steps = ns;
+  if (tokens) *tokens = nt;
+  if (sampled) *sampled = nsm;
+  if (kv_tokens_read) *kv_tokens_read = nkv;
   return 0;
+}
+
+int b200_engine_profile(b200_engine* e, int32_t n, double* class_us, int64_t* class_launches, int32_t num_classes) {
+  return b200_engine_profile_range(e, n, 0, 1 << 30, class_us, class_launches, num_classes, nullptr, nullptr, nullptr,
+                                   nullptr);
 }
 
 int b200_engine_reset_prefix_cache(b200_engine* e) {

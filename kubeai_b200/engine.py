@@ -150,6 +150,16 @@ class Engine:
         check(self._l.b200_engine_profile(self._h, n, us, ln, k))
         return {name: dict(us=us[i], launches=ln[i]) for i, name in enumerate(self.KERNEL_CLASSES)}
 
+    def profile_range(self, n: int, min_tokens: int, max_tokens: int):
+        """profile() over the recorded steps with min_tokens <= T <= max_tokens; returns (per-class dict, totals dict)."""
+        k = len(self.KERNEL_CLASSES)
+        us, ln = (C.c_double * k)(), (C.c_int64 * k)()
+        st, tk, sm, kv = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64()
+        check(self._l.b200_engine_profile_range(self._h, n, min_tokens, max_tokens, us, ln, k, C.byref(st), C.byref(tk),
+                                                C.byref(sm), C.byref(kv)))
+        return ({name: dict(us=us[i], launches=ln[i]) for i, name in enumerate(self.KERNEL_CLASSES)},
+                dict(steps=st.value, tokens=tk.value, sampled=sm.value, kv_tokens=kv.value))
+
     def reset_prefix_cache(self):
         check(self._l.b200_engine_reset_prefix_cache(self._h))
 
