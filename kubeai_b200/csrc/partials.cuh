@@ -54,12 +54,13 @@ __device__ __forceinline__ void load8_entry(const PartialView& v, const int2 e, 
   const size_t stride = 2 * static_cast<size_t>(v.slot);
   const float* p = v.ws + (static_cast<size_t>(e.x) * 2 + rank) * v.slot + static_cast<size_t>(tl) * 128 + row;
   float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
-  // four segments' loads are issued before the first add (independent L2 round trips), the adds stay in
-  // segment order so the result does not depend on the unrolling
-  for (int s = 0; s < e.y; s += 4, p += 4 * stride) {
-    float4 x[4], y[4];
+  // eight segments' loads are issued before the first add (independent L2 round trips: the o_proj / down_proj tiles of a
+  // decode step have 5-6 segments, one round instead of two), the adds stay in segment order so the result does not
+  // depend on the unrolling
+  for (int s = 0; s < e.y; s += 8, p += 8 * stride) {
+    float4 x[8], y[8];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < 8; ++u) {
       if (s + u < e.y) {
         x[u] = __ldcg(reinterpret_cast<const float4*>(p + u * stride));
         y[u] = __ldcg(reinterpret_cast<const float4*>(p + u * stride + 4));
@@ -69,7 +70,7 @@ __device__ __forceinline__ void load8_entry(const PartialView& v, const int2 e, 
       }
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < 8; ++u) {
       a.x += x[u].x; a.y += x[u].y; a.z += x[u].z; a.w += x[u].w;
       b.x += y[u].x; b.y += y[u].y; b.z += y[u].z; b.w += y[u].w;
     }

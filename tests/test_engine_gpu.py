@@ -228,3 +228,43 @@ def test_pipelined_run_matches_single_steps_and_delivers_to_waiting_threads():
         assert pr.finished == "aborted"
         st = e.stats()
         assert st.running == 0 and st.waiting == 0
+
+
+def test_full_size_llama3_8b_run_is_deterministic_and_accounts_prefix_reuse():
+    """BASELINE config 2 shape (Llama-3-8B, 128 sequences, <=2k context) — too big for the CPU oracle, so checked through
+    size-independent properties: two independent engines produce identical token streams for the same multi-turn
+    workload (fixed schedules, no atomics in any reduction), every id is a vocabulary id, each request yields exactly
+    max_tokens ids, and the second turn's cached prefix is what the block-hash chain must give."""
+    from kubeai_b200.engine import Engine, default_config
+    g = torch.Generator().manual_seed(11)
+    first = [torch.randint(0, 128000, (int(n),), generator=g).tolist() for n in torch.randint(40, 300, (128,), generator=g)]
+    follow = [torch.randint(0, 128000, (int(n),), generator=g).tolist() for n in torch.randint(20, 90, (128,), generator=g)]
+
+    def run():
+        cfg = default_config(manual_step=1, max_num_seqs=128, max_batched_tokens=2048, max_model_len=2048, kv_fraction=0.2)
+        with Engine(cfg) as e:
+            t1 = e.generate(first, max_tokens=12)
+            turn2 = [p + o + f for p, o, f in zip(first, t1, follow)]
+            rids = [e.submit(p, max_tokens=8) for p in turn2]
+            t2, usage = [[] for _ in rids], [None] * len(rids)
+            pending = set(range(len(rids)))
+            while pending:
+                ran = e.run(16, 1000)
+                for i in list(pending):
+                    pr = e.poll(rids[i])
+                    t2[i] += pr.tokens
+                    if pr.finished is not None:
+                        usage[i] = pr.usage
+                        pending.discard(i)
+                assert ran or not pending
+            return t1, t2, usage
+
+    a1, a2, ua = run()
+    b1, b2, ub = run()
+    assert a1 == b1 and a2 == b2 and ua == ub
+    assert all(len(o) == 12 for o in a1) and all(len(o) == 8 for o in a2)
+    assert all(0 <= t < 128256 for o in a1 + a2 for t in o)
+    for p, o, (prompt_tokens, cached, completion) in zip(first, a1, ua):
+        # turn 1 computed len(p) + 11 tokens of KV (the 12th id was sampled, never fed back): every FULL 16-token block of
+        # it is in the prefix cache, and turn 2 starts with exactly those tokens
+        assert cached == ((len(p) + 11) // 16) * 16 and completion == 8 and prompt_tokens > cached
