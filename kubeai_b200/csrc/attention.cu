@@ -328,13 +328,8 @@ int kv_map_for(const void* kv_layer, CUtensorMap* out) {
 template <bool DECODE, int S>
 int launch_attn(const CUtensorMap& tm, dim3 grid, cudaStream_t st, const __nv_bfloat16* q, int ldq, __nv_bfloat16* out,
                 int ldo, const int* block_tables, int max_blocks, const AttnWork* work, int Hkv, float scale_log2) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(paged_attn_kernel<DECODE, S>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             attn_smem_bytes<S>()) != cudaSuccess)
-      return -3;
-    attr_set = true;
-  }
+  static std::atomic<unsigned long long> attr_done{0};
+  if (!ensure_dynamic_smem(paged_attn_kernel<DECODE, S>, attn_smem_bytes<S>(), &attr_done)) return -3;
   launch_pdl(paged_attn_kernel<DECODE, S>, grid, dim3(128), attn_smem_bytes<S>(), st, tm, q, ldq, out, ldo, block_tables,
              max_blocks, work, Hkv, scale_log2);
   return cudaGetLastError() == cudaSuccess ? 0 : -2;

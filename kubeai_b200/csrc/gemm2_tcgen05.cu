@@ -583,13 +583,8 @@ template <int BLOCK_N>
 int launch2(const GemmPlan& p, const CUtensorMap& tm_x, __nv_bfloat16* out, int ldo, int T, cudaStream_t st,
             int deferred = 0) {
   using C = Cfg2<BLOCK_N>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(gemm2_streamk_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes) !=
-        cudaSuccess)
-      return -3;
-    attr_set = true;
-  }
+  static std::atomic<unsigned long long> attr_done{0};
+  if (!ensure_dynamic_smem(gemm2_streamk_kernel<BLOCK_N>, C::kSmemBytes, &attr_done)) return -3;
   const int ntt = (T + BLOCK_N - 1) / BLOCK_N;
   const int units = units_for(p, ntt);
   int tma_store = 0;

@@ -413,13 +413,8 @@ int num_sms() {
 template <int BLOCK_N>
 int launch(const GemmPlan& p, const CUtensorMap& tm_x, __nv_bfloat16* out, int ldo, int T, cudaStream_t st) {
   using C = Cfg<BLOCK_N>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_streamk_kernel<BLOCK_N>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
-    if (e != cudaSuccess) return -3;
-    attr_set = true;
-  }
+  static std::atomic<unsigned long long> attr_done{0};
+  if (!ensure_dynamic_smem(gemm_streamk_kernel<BLOCK_N>, C::kSmemBytes, &attr_done)) return -3;
   const int slabs = (p.N + kSlab - 1) / kSlab;
   const int ntt = (T + BLOCK_N - 1) / BLOCK_N;
   const int KB = (p.K + kBlockK - 1) / kBlockK;

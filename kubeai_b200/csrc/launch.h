@@ -5,6 +5,8 @@
 #include <cuda_runtime.h>
 #include <stdlib.h>
 
+#include <atomic>
+
 namespace b200 {
 
 inline bool pdl_enabled() {
@@ -14,6 +16,19 @@ inline bool pdl_enabled() {
     v = (e && e[0] == '0') ? 0 : 1;
   }
   return v != 0;
+}
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device property of a kernel: one process may drive several GPUs
+// (one engine per device), so "already set" is tracked per device ordinal.
+template <typename Kernel>
+inline bool ensure_dynamic_smem(Kernel kernel, int bytes, std::atomic<unsigned long long>* done_mask) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return false;
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (done_mask->load(std::memory_order_acquire) & bit) return true;
+  if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) return false;
+  done_mask->fetch_or(bit, std::memory_order_release);
+  return true;
 }
 
 template <typename... KArgs, typename... Args>

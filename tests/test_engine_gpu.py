@@ -268,3 +268,24 @@ def test_full_size_llama3_8b_run_is_deterministic_and_accounts_prefix_reuse():
         # turn 1 computed len(p) + 11 tokens of KV (the 12th id was sampled, never fed back): every FULL 16-token block of
         # it is in the prefix cache, and turn 2 starts with exactly those tokens
         assert cached == ((len(p) + 11) // 16) * 16 and completion == 8 and prompt_tokens > cached
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs in one process")
+def test_engines_on_two_devices_in_one_process_agree():
+    """One process, one engine per GPU (how b200serve --gpus N runs the replicas): per-device kernel attributes, tensor
+    maps and workspaces must not leak between devices."""
+    from kubeai_b200.engine import Engine, mini_config
+    g = torch.Generator().manual_seed(9)
+    prompts = [torch.randint(0, 512, (n,), generator=g).tolist() for n in (7, 40, 130)]
+    outs = []
+    for dev_id in (0, 1, 0):
+        with Engine(mini_config(device=dev_id)) as e:
+            outs.append(e.generate(prompts, max_tokens=10))
+    assert outs[0] == outs[1] == outs[2]
+    with Engine(mini_config(device=0)) as e0, Engine(mini_config(device=1)) as e1:   # both alive at once
+        r0 = [e0.submit(p, max_tokens=10) for p in prompts]
+        r1 = [e1.submit(p, max_tokens=10) for p in prompts]
+        for _ in range(200):
+            e0.step(); e1.step()
+        assert [e0.poll(r).tokens for r in r0] == outs[0]
+        assert [e1.poll(r).tokens for r in r1] == outs[0]
