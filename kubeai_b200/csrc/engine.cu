@@ -321,6 +321,23 @@ Engine::~Engine() {
   stop = true;
   cv_work_.notify_all();
   if (worker.joinable()) worker.join();
+  publish();
+  {
+    // nobody will step this engine again: wake every thread still blocked in b200_wait on an unfinished request
+    std::vector<std::shared_ptr<Seq>> open;
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      for (auto& kv : requests) open.push_back(kv.second);
+      requests.clear();
+    }
+    for (auto& s : open) {
+      {
+        std::lock_guard<std::mutex> lk(s->m);
+        if (!s->finished) s->finished = B200_FINISH_ABORTED;
+      }
+      s->cv.notify_all();
+    }
+  }
   if (step_timing[0] > 0) {
     const double n = step_timing[0], us = 1e6 / n;
     fprintf(stderr,
