@@ -75,10 +75,13 @@ def main():
 
     steps, marks, out_tokens, prompt_tokens = 0, {}, 0, 0
     seen_len = {}
+    step_log = []          # (wall seconds of this step() call, new output tokens, requests that got their first token)
+    t_prev = time.perf_counter()
     while eng.has_unfinished_requests() and steps < args.warmup + args.steps:
         outs = eng.step()
         steps += 1
         now = time.perf_counter()
+        tok_before, first_before = out_tokens, len(first_seen)
         for o in outs:
             n = len(o.outputs[0].token_ids)
             out_tokens += n - seen_len.get(o.request_id, 0)
@@ -98,20 +101,30 @@ def main():
                 elif next_thread < len(threads):
                     submit(next_thread, 0, [])
                     next_thread += 1
+        if steps > args.warmup:
+            step_log.append((now - t_prev, out_tokens - tok_before, len(first_seen) - first_before))
+        t_prev = now
         if steps == args.warmup:
             marks["t0"], marks["tok0"] = time.perf_counter(), out_tokens
+            t_prev = marks["t0"]
     t1 = time.perf_counter()
     timed_steps = steps - args.warmup
     toks = out_tokens - marks.get("tok0", 0)
     dt = t1 - marks.get("t0", t1)
     ttft.sort()
+    dec = sorted(dt for dt, n, f in step_log if f == 0 and n > 0)          # steps that only decoded
+    pre = sorted(dt for dt, n, f in step_log if f > 0)                     # steps that finished at least one prefill
+    med = lambda v: round(v[len(v) // 2] * 1e3, 3) if v else None
     line = {
         "impl": "vllm-%s (image wheel; reference pins v0.10.2)" % __import__("vllm").__version__,
         "metric": "agg output tok/s, Llama-3-8B multi-turn", "value": round(toks / dt, 1) if dt > 0 else None,
         "unit": "tok/s", "steps": timed_steps, "warmup": args.warmup, "ms_per_step": round(dt / max(1, timed_steps) * 1e3, 3),
         "ttft_ms_p50": round(statistics.median(ttft) * 1e3, 2) if ttft else None,
         "ttft_ms_p99": round(ttft[int(0.99 * (len(ttft) - 1))] * 1e3, 2) if ttft else None,
-        "requests_first_token": len(ttft), "init_s": round(init_s, 1), "sessions": args.sessions,
+        "requests_first_token": len(ttft),
+        "decode_only_steps": {"n": len(dec), "median_ms": med(dec), "mean_ms": round(sum(dec) / len(dec) * 1e3, 3) if dec else None},
+        "steps_completing_prefills": {"n": len(pre), "median_ms": med(pre), "mean_ms": round(sum(pre) / len(pre) * 1e3, 3) if pre else None,
+                                      "requests_per_step_mean": round(sum(f for _, _, f in step_log if f > 0) / max(1, len(pre)), 1)}, "init_s": round(init_s, 1), "sessions": args.sessions,
         "enforce_eager": args.eager, "timing": "host wall clock around LLMEngine.step() (engine-core process included)",
         "data": "synthetic threads (seed 2), dummy weights",
     }
