@@ -1022,7 +1022,7 @@ void b200_config_default(b200_config* c) {
   c->rope_theta = 500000.0f;
   c->max_model_len = 2048;
   c->max_num_seqs = 128;
-  c->max_batched_tokens = 2048;
+  c->max_batched_tokens = 1536;  // three 512-token GEMM tiles; throughput is flat 1024..4096, TTFT grows with it (profiles/r01_token_budget_sweep.md)
   c->num_kv_blocks = 0;
   c->kv_fraction = 0.85f;
   c->enable_prefix_caching = 1;
