@@ -35,6 +35,7 @@ def main():
     ap.add_argument("--sessions", type=int, default=128)
     ap.add_argument("--threads-per-session", type=float, default=2.5)
     ap.add_argument("--eager", action="store_true")
+    ap.add_argument("--max-batched-tokens", type=int, default=1536)
     args = ap.parse_args()
 
     from kubeai_b200.server import harness_config, synth_threads, tokenize
@@ -52,7 +53,7 @@ def main():
     from vllm import LLM, SamplingParams
     t_init = time.perf_counter()
     llm = LLM(model=d, load_format="dummy", skip_tokenizer_init=True, dtype="bfloat16", max_model_len=2048,
-              max_num_seqs=args.sessions, max_num_batched_tokens=2048, enable_prefix_caching=True,
+              max_num_seqs=args.sessions, max_num_batched_tokens=args.max_batched_tokens, enable_prefix_caching=True,
               gpu_memory_utilization=0.80, enforce_eager=args.eager, seed=0)
     init_s = time.perf_counter() - t_init
     eng = llm.llm_engine
@@ -124,7 +125,7 @@ def main():
         "requests_first_token": len(ttft),
         "decode_only_steps": {"n": len(dec), "median_ms": med(dec), "mean_ms": round(sum(dec) / len(dec) * 1e3, 3) if dec else None},
         "steps_completing_prefills": {"n": len(pre), "median_ms": med(pre), "mean_ms": round(sum(pre) / len(pre) * 1e3, 3) if pre else None,
-                                      "requests_per_step_mean": round(sum(f for _, _, f in step_log if f > 0) / max(1, len(pre)), 1)}, "init_s": round(init_s, 1), "sessions": args.sessions,
+                                      "requests_per_step_mean": round(sum(f for _, _, f in step_log if f > 0) / max(1, len(pre)), 1)}, "init_s": round(init_s, 1), "sessions": args.sessions, "max_num_batched_tokens": args.max_batched_tokens,
         "enforce_eager": args.eager, "timing": "host wall clock around LLMEngine.step() (engine-core process included)",
         "data": "synthetic threads (seed 2), dummy weights",
     }
