@@ -1,6 +1,6 @@
 // Bandwidth-bound per-step ops of the Llama forward.
 // Rounding points follow the reference backend so greedy tokens match:
-//   RMSNorm / fused add:  vllm/ir/ops/layernorm.py:9-21,42-60
+//   RMSNorm:              vllm/ir/ops/layernorm.py:9-21;  fused add: vllm/_custom_ops.py:323-327 (_C op: bf16 sum, norm of it)
 //   RoPE (neox):          vllm/model_executor/layers/rotary_embedding/base.py:140-198 (bf16 cos/sin cache)
 //   SiLU*mul:             vllm/model_executor/layers/activation.py:138-148 (silu in fp32, rounded, then * up)
 //   greedy sampling:      vllm/v1/sample/sampler.py:91,235-236 (argmax, lowest index wins ties)
@@ -86,9 +86,10 @@ __global__ void rmsnorm_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat1
       Vec8 o;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        float f = xa[i][j] + __bfloat162float(rb[i].h[j]);
-        o.h[j] = __float2bfloat16_rn(f);  // residual stored in input dtype ...
-        v[i][j] = f;                      // ... variance from the fp32 sum (layernorm.py:51-56)
+        // residual += x in bf16; variance and normalisation use the ROUNDED sum (vLLM _C fused_add_rms_norm, HF
+        // modeling_llama.py:325 + :62-67) — the decode GEMM epilogues store exactly this bf16 sum (gemm3_tcgen05.cu)
+        o.h[j] = __float2bfloat16_rn(xa[i][j] + __bfloat162float(rb[i].h[j]));
+        v[i][j] = __bfloat162float(o.h[j]);
       }
       if (!row_index) res[idx] = o.u;
     } else {

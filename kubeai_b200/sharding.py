@@ -37,3 +37,13 @@ def aggregate(dist, tokens: float, seconds: float, device=None):
     dist.all_reduce(t, op=dist.ReduceOp.SUM)
     dist.all_reduce(s, op=dist.ReduceOp.MAX)
     return t.item(), s.item()
+
+
+def gather_ranks(dist, values, device=None):
+    """values: list of floats of this rank -> list over ranks of those lists (per-rank reporting: tokens add, the
+    job's time is the max over ranks, and every rank's own figures are printed next to the aggregate)."""
+    import torch
+    v = torch.tensor(list(values), dtype=torch.float64, device=device)
+    out = [torch.zeros_like(v) for _ in range(dist.get_world_size())]
+    dist.all_gather(out, v)
+    return [o.tolist() for o in out]

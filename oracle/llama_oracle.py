@@ -6,7 +6,8 @@ vLLM pod (`vllm/vllm-openai:v0.10.2`, /root/reference/charts/kubeai/values.yaml:
 vLLM Llama forward with its rounding points (paths inside the vllm 0.22.0 wheel of this image, the
 closest available version):
 
-  rms_norm / fused_add_rms_norm   vllm/ir/ops/layernorm.py:9-21,42-60
+  rms_norm                        vllm/ir/ops/layernorm.py:9-21
+  fused_add_rms_norm              vllm/_custom_ops.py:323-327 (_C CUDA op: bf16 sum, then norm of the rounded sum)
   neox RoPE, bf16 cos/sin cache   vllm/model_executor/layers/rotary_embedding/base.py:70-92,140-198
                                   vllm/model_executor/layers/rotary_embedding/common.py:144-183
   SiluAndMul                      vllm/model_executor/layers/activation.py:117-148
@@ -51,18 +52,24 @@ def rms_norm(x, w, eps):
 
 
 def fused_add_rms_norm(x, residual, w, eps):
-    s = x + residual              # fp32 sum of two bf16 values
-    new_res = r(s)                # residual stored in bf16 ...
-    var = s.pow(2).mean(dim=-1, keepdim=True)   # ... variance from the fp32 sum
-    y = s * torch.rsqrt(var + eps)
-    return r(r(y) * w), new_res
+    """residual += x in bf16, then RMSNorm of the ROUNDED sum — the semantics of vLLM's CUDA op
+    (vllm/_custom_ops.py:323-327 -> torch.ops._C.fused_add_rms_norm: `z = input + residual` in scalar_t,
+    variance and normalisation from z) and of HF transformers (modeling_llama.py:325,328-329 + :62-67).
+    vLLM's python IR op (vllm/ir/ops/layernorm.py:42-60) keeps the fp32 sum instead; the two differ by one
+    double rounding of the normalised value.  The engine follows the CUDA-op form because its decode GEMM epilogues
+    store the summed residual in bf16 and the next GEMM normalises it on load (gemm3_tcgen05.cu)."""
+    z = r(x + residual)
+    var = z.pow(2).mean(dim=-1, keepdim=True)
+    y = z * torch.rsqrt(var + eps)
+    return r(r(y) * w), z
 
 
 def rope_neox(x, positions, cs_bf16):
-    """x: [T, heads, 128]; cs_bf16: [max_pos, 128] (cos|sin) already rounded to bf16."""
+    """x: [T, heads, D]; cs_bf16: [max_pos, D] (cos|sin) already rounded to bf16 (D = 128 in the engine)."""
     cs = cs_bf16[positions]
-    cos, sin = cs[:, None, :64], cs[:, None, 64:]
-    x1, x2 = x[..., :64], x[..., 64:]
+    h = x.shape[-1] // 2
+    cos, sin = cs[:, None, :h], cs[:, None, h:]
+    x1, x2 = x[..., :h], x[..., h:]
     o1 = r(r(x1 * cos) - r(x2 * sin))
     o2 = r(r(x2 * cos) + r(x1 * sin))
     return torch.cat([o1, o2], dim=-1)

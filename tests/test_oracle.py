@@ -61,12 +61,13 @@ def test_op_restatements_follow_vllm_rounding_points():
     g = torch.Generator().manual_seed(0)
     x, res, w = (O.r(torch.randn(3, 64, generator=g)) for _ in range(3))
     y, nr = O.fused_add_rms_norm(x, res, w[0], 1e-5)
-    # same thing written the way vllm/ir/ops/layernorm.py:42-60 writes it, in real bf16 tensors
+    # same thing the way HF writes it in real bf16 tensors (modeling_llama.py:325 residual + hidden in bf16, then
+    # LlamaRMSNorm :62-67) == vLLM's _C fused_add_rms_norm (sum in scalar_t, norm of the rounded sum)
     xb, rb, wb = x.bfloat16(), res.bfloat16(), w[0].bfloat16()
-    xf = xb.float() + rb.float()
-    r2 = xf.to(torch.bfloat16)
+    r2 = rb + xb
+    xf = r2.float()
     var = xf.pow(2).mean(dim=-1, keepdim=True)
-    y2 = ((xf * torch.rsqrt(var + 1e-5)).to(torch.bfloat16) * wb).to(torch.bfloat16)
+    y2 = wb * (xf * torch.rsqrt(var + 1e-5)).to(torch.bfloat16)
     assert torch.equal(y, y2.float()) and torch.equal(nr, r2.float())
     gu = O.r(torch.randn(4, 32, generator=g) * 3)
     d = 16

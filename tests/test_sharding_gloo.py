@@ -18,7 +18,7 @@ def _worker(rank, world, port, out):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from kubeai_b200.server import harness_config, synth_threads
-    from kubeai_b200.sharding import aggregate, assign_threads, first_user_prefix
+    from kubeai_b200.sharding import aggregate, assign_threads, first_user_prefix, gather_ranks
     threads = synth_threads(harness_config(synth_threads=400, seed=2))
     mine = assign_threads(threads, world)[rank]
     keys = sorted(first_user_prefix(t) for t in mine)
@@ -27,8 +27,9 @@ def _worker(rank, world, port, out):
     gathered = [torch.zeros_like(n) for _ in range(world)]
     dist.all_gather(gathered, n)
     tok, sec = aggregate(dist, tokens=1000.0 * (rank + 1), seconds=2.0 + rank)
+    rows = gather_ranks(dist, [1000.0 * (rank + 1), 2.0 + rank, float(rank)])
     if rank == 0:
-        out.put(dict(total=len(threads), counts=[int(g[0]) for g in gathered], tok=tok, sec=sec,
+        out.put(dict(total=len(threads), counts=[int(g[0]) for g in gathered], tok=tok, sec=sec, rows=rows,
                      all_keys=sorted(first_user_prefix(t) for t in threads),
                      parts=[sorted(first_user_prefix(t) for t in p) for p in assign_threads(threads, world)]))
     dist.barrier()
@@ -49,6 +50,7 @@ def test_two_ranks_shard_sessions_with_the_ring_and_aggregate():
     assert res["counts"] == [len(res["parts"][0]), len(res["parts"][1])]
     assert min(res["counts"]) > 0.35 * res["total"]             # 256 vnodes per replica: roughly even
     assert res["tok"] == 3000.0 and res["sec"] == 3.0           # tokens add, time is the max over ranks
+    assert res["rows"] == [[1000.0, 2.0, 0.0], [2000.0, 3.0, 1.0]]   # bench.py prints every rank's own figures too
 
 
 def test_assignment_is_stable_when_a_replica_is_added():
