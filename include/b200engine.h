@@ -57,6 +57,12 @@ typedef struct {
   float init_scale;           /* multiplies the lm_head init so greedy logits are separated; default 4 */
   int32_t manual_step;        /* 1 = no background thread; caller drives b200_engine_step() */
   int32_t record_steps;       /* >0 = keep the device-side inputs of the last N steps for b200_engine_replay */
+  /* RoPE frequency scaling (HF config.json "rope_scaling" / "rope_parameters"; vLLM rotary_embedding/__init__.py get_rope):
+   * 0 = none, 1 = "linear" (positions / factor), 2 = "llama3" (Llama-3.1+: per-frequency factor between the low and high
+   * wavelength bounds).  b200_config_from_hf fills these; any other rope_type is refused there. */
+  int32_t rope_scaling_type;
+  float rope_factor, rope_low_freq_factor, rope_high_freq_factor;
+  int32_t rope_original_max_pos;
 } b200_config;
 
 typedef struct {
@@ -109,6 +115,9 @@ int b200_abort(b200_engine* e, uint64_t req_id);
 /* Forget a finished request (frees its host-side record). */
 int b200_release(b200_engine* e, uint64_t req_id);
 int b200_stats_get(b200_engine* e, b200_stats* out);
+/* 1 when a CUDA failure has poisoned this replica (every request fails with B200_FINISH_ERROR / B200_ERR_CUDA from then on):
+ * the serving shell drops such a replica from the router's endpoint set (internal/loadbalancer/group.go:119-131). */
+int b200_engine_is_failed(b200_engine* e);
 
 /* manual_step mode: run one scheduler iteration + forward; *info may be NULL. Returns 1 if a step ran, 0 if idle. */
 int b200_engine_step(b200_engine* e, b200_step_info* info);
@@ -225,7 +234,8 @@ int b200_server_parse_request(b200_server* s, const char* path, const char* cont
 int b200_server_listen(b200_server* s, const char* host, int32_t port, int32_t* bound_port);
 /* Prometheus text (kubeai_inference_requests_active + engine gauges); returns the full length. */
 int b200_server_metrics(b200_server* s, char* buf, size_t cap);
-/* Fault injection for the retry path: the next `count` submits on `replica` fail. */
+/* Fault injection for the retry path: the next `count` submits on `replica` fail; count < 0 = every submit fails, which
+ * stands for an engine in the failed state: the first failure drops the replica from the router's endpoint set. */
 int b200_server_inject_fault(b200_server* s, int32_t replica, int32_t count);
 /* Synthetic tokenizer (ids 0..255 = bytes; " wxyz" spellings round-trip every id). Return the full count/length. */
 int b200_tokenize(int32_t vocab, const char* text, size_t len, int32_t* out, int32_t cap);

@@ -26,6 +26,8 @@ class Config(C.Structure):
         ("enable_prefix_caching", C.c_int32), ("eos_token_id", C.c_int32),
         ("seed", C.c_uint64), ("init_scale", C.c_float),
         ("manual_step", C.c_int32), ("record_steps", C.c_int32),
+        ("rope_scaling_type", C.c_int32), ("rope_factor", C.c_float), ("rope_low_freq_factor", C.c_float),
+        ("rope_high_freq_factor", C.c_float), ("rope_original_max_pos", C.c_int32),
     ]
 
 
@@ -106,6 +108,7 @@ SYMBOLS = {
     "b200_abort": (C.c_int, [_vp, _u64]),
     "b200_release": (C.c_int, [_vp, _u64]),
     "b200_stats_get": (C.c_int, [_vp, C.POINTER(Stats)]),
+    "b200_engine_is_failed": (C.c_int, [_vp]),
     "b200_engine_step": (C.c_int, [_vp, C.POINTER(StepInfo)]),
     "b200_engine_run": (C.c_int, [_vp, _i32, _i64, C.POINTER(StepInfo), C.POINTER(_i32)]),
     "b200_engine_replay": (C.c_int, [_vp, _i32, _i32, C.POINTER(C.c_double), C.POINTER(_i64), C.POINTER(_i64),

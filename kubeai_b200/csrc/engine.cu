@@ -413,9 +413,25 @@ int Engine::alloc_all() {
     std::vector<float> inv(kD / 2);
     for (int i = 0; i < kD / 2; ++i)
       inv[i] = 1.0f / powf(cfg.rope_theta, static_cast<float>(2 * i) / static_cast<float>(kD));
+    float pos_div = 1.0f;
+    if (cfg.rope_scaling_type == 1) {
+      // LinearScalingRotaryEmbedding (rotary_embedding/linear_scaling_rope.py): t / factor
+      pos_div = cfg.rope_factor;
+    } else if (cfg.rope_scaling_type == 2) {
+      // Llama3RotaryEmbedding._compute_inv_freq (rotary_embedding/llama3_rope.py:37-54)
+      const float orig = static_cast<float>(cfg.rope_original_max_pos);
+      const float low_wl = orig / cfg.rope_low_freq_factor, high_wl = orig / cfg.rope_high_freq_factor;
+      for (int i = 0; i < kD / 2; ++i) {
+        const float wl = 2.0f * static_cast<float>(M_PI) / inv[i];
+        if (wl < high_wl) continue;
+        if (wl > low_wl || cfg.rope_low_freq_factor == cfg.rope_high_freq_factor) { inv[i] = inv[i] / cfg.rope_factor; continue; }
+        const float smooth = (orig / wl - cfg.rope_low_freq_factor) / (cfg.rope_high_freq_factor - cfg.rope_low_freq_factor);
+        inv[i] = (1.0f - smooth) * inv[i] / cfg.rope_factor + smooth * inv[i];
+      }
+    }
     for (int t = 0; t < cfg.max_model_len; ++t)
       for (int i = 0; i < kD / 2; ++i) {
-        const float f = static_cast<float>(t) * inv[i];
+        const float f = static_cast<float>(t) / pos_div * inv[i];
         h[static_cast<size_t>(t) * kD + i] = __float2bfloat16_rn(cosf(f));
         h[static_cast<size_t>(t) * kD + kD / 2 + i] = __float2bfloat16_rn(sinf(f));
       }
@@ -480,8 +496,12 @@ int Engine::alloc_all() {
     const float frac = cfg.kv_fraction > 0 ? cfg.kv_fraction : 0.85f;
     nblocks = static_cast<int64_t>(static_cast<double>(fr) * frac / (static_cast<double>(block_bytes_layer) * L));
   }
-  if (nblocks < 4) {
-    set_error("KV pool too small (%lld blocks)", static_cast<long long>(nblocks));
+  // vLLM refuses to start when the cache cannot hold one max_model_len sequence (v1/core/kv_cache_utils.py
+  // check_enough_kv_cache_memory): a request that needs more pages than the pool could never be admitted
+  const int64_t need_blocks = (static_cast<int64_t>(cfg.max_model_len) + kPage - 1) / kPage;
+  if (nblocks < 4 || nblocks < need_blocks) {
+    set_error("KV pool too small: %lld blocks, one max_model_len=%d sequence needs %lld (lower max_model_len or raise num_kv_blocks / kv_fraction)",
+              static_cast<long long>(nblocks), cfg.max_model_len, static_cast<long long>(need_blocks));
     return B200_ERR_OOM;
   }
   if (nblocks > (1 << 27)) nblocks = 1 << 27;
@@ -507,9 +527,19 @@ int Engine::init(const b200_config& c) {
   cfg = c;
   L = c.num_layers; H = c.hidden; Hq = c.q_heads; Hkv = c.kv_heads; I = c.intermediate; V = c.vocab;
   QKV = (Hq + 2 * Hkv) * kD;
-  if (L < 1 || H % 64 || Hq != 4 * Hkv || I % 64 || V < 8 || c.max_model_len < 16 || c.max_num_seqs < 1 ||
-      c.max_batched_tokens < 16) {
-    set_error("unsupported model/config (need q_heads == 4*kv_heads, hidden %% 64 == 0, intermediate %% 64 == 0)");
+  // the constraints of every kernel the forward launches, checked here so that a bad shape fails at create time with a
+  // message instead of poisoning the replica at its first step: RMSNorm rows are 256-element multiples up to 8192,
+  // argmax and the partial readers use 8-element vectors, GEMM K dims are 64-element TMA boxes
+  if (L < 1 || H % 256 || H > 8192 || Hq != 4 * Hkv || Hkv < 1 || I % 64 || V < 8 || V % 8 || c.max_model_len < 16 ||
+      c.max_num_seqs < 1 || c.max_batched_tokens < 16) {
+    set_error("unsupported model/config (need q_heads == 4*kv_heads, hidden %% 256 == 0 and <= 8192, intermediate %% 64 == 0, "
+              "vocab %% 8 == 0, max_model_len >= 16)");
+    return B200_ERR_INVALID;
+  }
+  if (c.rope_scaling_type < 0 || c.rope_scaling_type > 2 ||
+      (c.rope_scaling_type != 0 && !(c.rope_factor > 0.f)) ||
+      (c.rope_scaling_type == 2 && (!(c.rope_low_freq_factor > 0.f) || !(c.rope_high_freq_factor > 0.f) || c.rope_original_max_pos < 1))) {
+    set_error("bad rope scaling parameters (type %d)", c.rope_scaling_type);
     return B200_ERR_INVALID;
   }
   Tcap = (c.max_batched_tokens + 15) / 16 * 16;
@@ -722,7 +752,7 @@ int Engine::launch(InFlight* f, StepMeta* mp) {
   bool preempted = false;
   // 1. running requests first (decodes and in-progress prefills)
   for (size_t i = 0; i < running.size() && budget > 0;) {
-    auto& s = running[i];
+    auto s = running[i];  // a copy: the preemption loop below pops elements of `running`, possibly this one
     int n = std::min(static_cast<int>(s->toks.size()) - s->n_computed, budget);
     if (n <= 0) { ++i; continue; }
     bool ok = true;
@@ -745,6 +775,13 @@ int Engine::launch(InFlight* f, StepMeta* mp) {
     int n = std::min(static_cast<int>(s->toks.size()) - s->n_computed, budget);
     if (!ensure_blocks(*s, s->n_computed + n)) {
       release_blocks(*s);
+      if (running.empty() && sched.empty()) {
+        // nothing else holds pages and it still does not fit: it never will (cannot happen while the pool holds one
+        // max_model_len sequence, which init() enforces) — fail it instead of blocking the queue behind it forever
+        waiting.pop_front();
+        finish(s, B200_FINISH_ERROR);
+        continue;
+      }
       break;
     }
     s->admitted = true;
@@ -1031,6 +1068,11 @@ void b200_config_default(b200_config* c) {
   c->init_scale = 4.0f;
   c->manual_step = 0;
   c->record_steps = 0;
+  c->rope_scaling_type = 0;
+  c->rope_factor = 1.0f;
+  c->rope_low_freq_factor = 1.0f;
+  c->rope_high_freq_factor = 4.0f;
+  c->rope_original_max_pos = 8192;
 }
 
 int b200_engine_create(const b200_config* cfg, b200_engine** out) {
@@ -1152,6 +1194,12 @@ int b200_stats_get(b200_engine* e, b200_stats* out) {
   std::lock_guard<std::mutex> lk(e->impl.mu_);
   *out = e->impl.stats;
   return 0;
+}
+
+int b200_engine_is_failed(b200_engine* e) {
+  if (!e) return 0;
+  std::lock_guard<std::mutex> lk(e->impl.mu_);
+  return e->impl.fatal ? 1 : 0;
 }
 
 int b200_engine_step(b200_engine* e, b200_step_info* info) {

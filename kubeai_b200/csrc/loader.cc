@@ -11,6 +11,8 @@
 #include <sys/stat.h>
 #include <unistd.h>
 
+#include <math.h>
+
 #include <map>
 #include <memory>
 #include <string>
@@ -68,10 +70,25 @@ struct StFile {
         return false;
       }
       t.dtype = dt->str;
-      for (auto& d : sh->arr) t.shape.push_back(static_cast<int64_t>(d.num));
-      t.begin = static_cast<size_t>(off->arr[0].num);
-      t.end = static_cast<size_t>(off->arr[1].num);
-      if (t.end < t.begin || data_off + t.end > size) { *err = "data_offsets out of range for " + kv.first; return false; }
+      // checkpoints are untrusted input: every number must be a non-negative integer below 2^53, offsets must lie inside
+      // the data section (compared without forming data_off + end, which could wrap), shape products must not overflow
+      auto as_index = [](const JVal& v, uint64_t* out) {
+        if (v.type != JVal::Num || !(v.num >= 0.0) || v.num >= 9007199254740992.0 || v.num != floor(v.num)) return false;
+        *out = static_cast<uint64_t>(v.num);
+        return true;
+      };
+      uint64_t b = 0, e = 0, elems = 1;
+      bool ok = as_index(off->arr[0], &b) && as_index(off->arr[1], &e);
+      for (auto& d : sh->arr) {
+        uint64_t dim = 0;
+        if (!ok || !as_index(d, &dim) || (dim != 0 && elems > (1ull << 53) / dim)) { ok = false; break; }
+        elems *= dim;
+        t.shape.push_back(static_cast<int64_t>(dim));
+      }
+      const uint64_t data_len = static_cast<uint64_t>(size - data_off);
+      if (!ok || e < b || e > data_len) { *err = "shape or data_offsets out of range for " + kv.first; return false; }
+      t.begin = static_cast<size_t>(b);
+      t.end = static_cast<size_t>(e);
       tensors[kv.first] = t;
     }
     return true;
@@ -240,6 +257,49 @@ int b200_config_from_hf(const char* dir, b200_config* cfg) {
   double theta = num("rope_theta", cfg->rope_theta);
   if (const JVal* rp = root.get("rope_parameters")) if (const JVal* t = rp->get("rope_theta"); t && t->type == JVal::Num) theta = t->num;
   cfg->rope_theta = static_cast<float>(theta);
+  // RoPE frequency scaling: HF "rope_scaling" (transformers < 5) or "rope_parameters" (>= 5); Llama-3.1/3.2 ship
+  // rope_type "llama3" with factor 8 — loading those with an unscaled table would silently diverge from vLLM/HF
+  cfg->rope_scaling_type = 0;
+  const JVal* rs = root.get("rope_scaling");
+  if (!rs || rs->type != JVal::Obj) rs = root.get("rope_parameters");
+  if (rs && rs->type == JVal::Obj) {
+    std::string ty = "default";
+    if (const JVal* t = rs->get("rope_type"); t && t->type == JVal::Str) ty = t->str;
+    else if (const JVal* t2 = rs->get("type"); t2 && t2->type == JVal::Str) ty = t2->str;
+    auto rnum = [&](const char* k, double def) { const JVal* v = rs->get(k); return v && v->type == JVal::Num ? v->num : def; };
+    if (ty == "default") {
+    } else if (ty == "linear") {
+      cfg->rope_scaling_type = 1;
+      cfg->rope_factor = static_cast<float>(rnum("factor", 1.0));
+    } else if (ty == "llama3") {
+      cfg->rope_scaling_type = 2;
+      cfg->rope_factor = static_cast<float>(rnum("factor", 8.0));
+      cfg->rope_low_freq_factor = static_cast<float>(rnum("low_freq_factor", 1.0));
+      cfg->rope_high_freq_factor = static_cast<float>(rnum("high_freq_factor", 4.0));
+      cfg->rope_original_max_pos = static_cast<int>(rnum("original_max_position_embeddings", 8192));
+    } else {
+      set_error("rope scaling type \"%s\" is not supported (default, linear, llama3)", ty.c_str());
+      return B200_ERR_INVALID;
+    }
+  }
+  // architecture switches the kernels do not implement are refused, not ignored
+  if (const JVal* mt = root.get("model_type"); mt && mt->type == JVal::Str && mt->str != "llama") {
+    set_error("model_type \"%s\" is not supported (llama)", mt->str.c_str());
+    return B200_ERR_INVALID;
+  }
+  if (const JVal* ha = root.get("hidden_act"); ha && ha->type == JVal::Str && ha->str != "silu") {
+    set_error("hidden_act \"%s\" is not supported (silu)", ha->str.c_str());
+    return B200_ERR_INVALID;
+  }
+  for (const char* k : {"attention_bias", "mlp_bias"})
+    if (const JVal* bflag = root.get(k); bflag && bflag->type == JVal::Bool && bflag->b) {
+      set_error("%s = true is not supported", k);
+      return B200_ERR_INVALID;
+    }
+  if (cfg->hidden % 256 || cfg->hidden > 8192 || cfg->vocab % 8 || cfg->intermediate % 64) {
+    set_error("shape not supported by the kernels (hidden %% 256 == 0 and <= 8192, vocab %% 8 == 0, intermediate %% 64 == 0)");
+    return B200_ERR_INVALID;
+  }
   const int head_dim = static_cast<int>(num("head_dim", cfg->q_heads ? cfg->hidden / cfg->q_heads : 0));
   if (head_dim != 128) { set_error("head_dim %d is not supported (kernels are specialised for 128)", head_dim); return B200_ERR_INVALID; }
   if (cfg->q_heads != 4 * cfg->kv_heads) { set_error("GQA ratio %d:%d is not supported (kernels are specialised for 4:1)", cfg->q_heads, cfg->kv_heads); return B200_ERR_INVALID; }

@@ -56,6 +56,17 @@ struct Server {
   std::thread acceptor;
   std::atomic<bool> stopping{false};
   std::atomic<int> live_conns{0};
+  std::mutex conn_mu;
+  std::set<int> conn_fds;          // open client sockets: shut down by the destructor so no thread outlives the Server
+  static constexpr int kMaxConns = 4096;
+  static constexpr int kIdleTimeoutS = 60;  // keep-alive read timeout (SO_RCVTIMEO)
+
+  // replicas whose engine reported a fatal error are taken out of the endpoint set, as reconcileEndpoints drops
+  // endpoints that vanished (internal/loadbalancer/group.go:119-131)
+  std::mutex dead_mu;
+  std::vector<char> dead;
+  std::string adapters_csv;
+  void drop_replica(int i);
 
   ~Server() {
     stopping = true;
@@ -64,10 +75,35 @@ struct Server {
       close(listen_fd);
     }
     if (acceptor.joinable()) acceptor.join();
-    for (int i = 0; i < 500 && live_conns.load() > 0; ++i) usleep(10000);
+    {
+      // wake every connection thread blocked in recv()/send(); each closes its own fd and leaves
+      std::lock_guard<std::mutex> lk(conn_mu);
+      for (int fd : conn_fds) shutdown(fd, SHUT_RDWR);
+    }
+    while (live_conns.load() > 0) usleep(1000);
     if (router) b200_router_destroy(router);
   }
 };
+
+void Server::drop_replica(int i) {
+  std::lock_guard<std::mutex> lk(dead_mu);
+  if (i < 0 || i >= static_cast<int>(dead.size()) || dead[i]) return;
+  dead[i] = 1;
+  std::vector<std::string> names;
+  std::vector<const char*> np, ap, dp;
+  for (size_t k = 0; k < replicas.size(); ++k) {
+    if (dead[k]) continue;
+    names.push_back("gpu-" + std::to_string(k));
+  }
+  size_t j = 0;
+  for (size_t k = 0; k < replicas.size(); ++k) {
+    if (dead[k]) continue;
+    np.push_back(names[j++].c_str());
+    ap.push_back(addrs[k].c_str());
+    dp.push_back(adapters_csv.c_str());
+  }
+  b200_router_set_endpoints(router, np.data(), ap.data(), dp.data(), static_cast<int32_t>(np.size()));
+}
 
 namespace {
 
@@ -218,6 +254,37 @@ int parse_request(Server& sv, const std::string& path, const std::string& ctype,
   if (const JVal* v = root.get("stop_token_ids"); v && v->type == JVal::Arr)
     for (auto& e : v->arr)
       if (e.type == JVal::Num) pr->stop_ids.push_back(static_cast<int32_t>(e.num));
+  // Fields of the reference's request schema (api/openai/v1/chat_completions.go:361-470, completions.go:19-130) whose
+  // semantics this engine does not implement are refused, never silently dropped.
+  auto num_of = [&](const char* k, double def) { const JVal* v = root.get(k); return v && v->type == JVal::Num ? v->num : def; };
+  auto truthy = [&](const char* k) {
+    const JVal* v = root.get(k);
+    return v && ((v->type == JVal::Bool && v->b) || (v->type == JVal::Num && v->num > 0));
+  };
+  auto nonempty = [&](const char* k) {
+    const JVal* v = root.get(k);
+    return v && ((v->type == JVal::Str && !v->str.empty()) || (v->type == JVal::Arr && !v->arr.empty()) ||
+                 (v->type == JVal::Obj && !v->obj.empty()));
+  };
+  const char* bad = nullptr;
+  if (num_of("n", 1) > 1) bad = "n > 1";
+  else if (num_of("best_of", 1) > 1) bad = "best_of > 1";
+  else if (truthy("logprobs") || truthy("top_logprobs") || truthy("prompt_logprobs")) bad = "logprobs";
+  else if (nonempty("stop")) bad = "stop strings (use stop_token_ids)";
+  else if (truthy("echo")) bad = "echo";
+  else if (nonempty("suffix")) bad = "suffix";
+  else if (num_of("presence_penalty", 0) != 0 || num_of("frequency_penalty", 0) != 0 || num_of("repetition_penalty", 1) != 1) bad = "sampling penalties";
+  else if (nonempty("logit_bias")) bad = "logit_bias";
+  else if (nonempty("tools") || nonempty("functions")) bad = "tool calling";
+  else if (truthy("min_tokens")) bad = "min_tokens";
+  else if (const JVal* rf = root.get("response_format"); rf && rf->type == JVal::Obj) {
+    const JVal* ty = rf->get("type");
+    if (ty && ty->type == JVal::Str && ty->str != "text") bad = "response_format other than text";
+  }
+  if (bad) {
+    *err = std::string("bad request: ") + bad + " is not supported by this engine";
+    return 400;
+  }
   return 0;
 }
 
@@ -304,7 +371,8 @@ static int serve_inference(Server& sv, const std::string& path, const std::strin
     sp.stop_ids = pr.stop_ids.empty() ? nullptr : pr.stop_ids.data();
     uint64_t rid = 0;
     bool failed = false;
-    if (sv.faults[replica]->load() > 0 && sv.faults[replica]->fetch_sub(1) > 0) failed = true;
+    if (sv.faults[replica]->load() < 0) failed = true;  // permanent fault: stands for an engine in the failed state
+    else if (sv.faults[replica]->load() > 0 && sv.faults[replica]->fetch_sub(1) > 0) failed = true;
     if (!failed && b200_submit(eng, ids.data(), static_cast<int>(ids.size()), &sp, &rid)) failed = true;
 
     std::vector<int32_t> all;
@@ -345,6 +413,7 @@ static int serve_inference(Server& sv, const std::string& path, const std::strin
       b200_release(eng, rid);
     }
     if (failed) {
+      if (b200_engine_is_failed(eng) || sv.faults[replica]->load() < 0) sv.drop_replica(replica);
       if (attempt < sv.max_retries) {
         sv.retries_total.fetch_add(1);
         continue;
@@ -502,6 +571,9 @@ int conn_write(void* ud, const char* data, size_t len) {
 void serve_conn(Server* sv, int fd) {
   int one = 1;
   setsockopt(fd, IPPROTO_TCP, TCP_NODELAY, &one, sizeof(one));
+  timeval tv{Server::kIdleTimeoutS, 0};
+  setsockopt(fd, SOL_SOCKET, SO_RCVTIMEO, &tv, sizeof(tv));
+  setsockopt(fd, SOL_SOCKET, SO_SNDTIMEO, &tv, sizeof(tv));
   std::string buf;
   char tmp[16384];
   for (;;) {
@@ -555,8 +627,12 @@ void serve_conn(Server* sv, int fd) {
     }
   }
 done:
+  {
+    std::lock_guard<std::mutex> lk(sv->conn_mu);
+    sv->conn_fds.erase(fd);
+  }
   close(fd);
-  sv->live_conns.fetch_sub(1);
+  sv->live_conns.fetch_sub(1);  // last touch of *sv: the destructor waits for this count to reach zero
 }
 
 }  // namespace
@@ -598,6 +674,8 @@ int b200_server_create(const b200_server_config* cfg, b200_engine* const* replic
   if (b200_router_create(sv.replication, &sv.router)) { delete s; return B200_ERR_INVALID; }
   std::vector<std::string> names;
   std::string ad = cfg->adapters ? cfg->adapters : "";
+  sv.adapters_csv = ad;
+  sv.dead.assign(static_cast<size_t>(n), 0);
   for (int i = 0; i < n; ++i) {
     sv.replicas.push_back(replicas[i]);
     names.push_back("gpu-" + std::to_string(i));
@@ -668,6 +746,17 @@ int b200_server_listen(b200_server* s, const char* host, int32_t port, int32_t* 
         if (sv.stopping) break;
         if (errno == EINTR) continue;
         break;
+      }
+      if (sv.live_conns.load() >= Server::kMaxConns) {
+        static const char busy[] = "HTTP/1.1 503 Service Unavailable\r\nContent-Length: 0\r\nConnection: close\r\n\r\n";
+        (void)!::send(c, busy, sizeof(busy) - 1, MSG_NOSIGNAL);
+        close(c);
+        continue;
+      }
+      {
+        std::lock_guard<std::mutex> lk(sv.conn_mu);
+        if (sv.stopping) { close(c); break; }
+        sv.conn_fds.insert(c);
       }
       sv.live_conns.fetch_add(1);
       std::thread(serve_conn, &sv, c).detach();

@@ -19,6 +19,8 @@ import torch
 from .weights import ModelCfg, bf16_bits_to_f32, make_weights
 
 OUT = Path(__file__).resolve().parent.parent / "tests" / "golden" / "llama_mini.npz"
+OUT_ROPE3 = OUT.with_name("llama_mini_rope3.npz")      # same model with Llama-3.1 style rope scaling
+ROPE3 = dict(rope_scaling_type=2, rope_factor=8.0, rope_low_freq_factor=1.0, rope_high_freq_factor=4.0, rope_original_max_pos=64)
 
 
 def hf_model(cfg: ModelCfg, weights: dict, dtype):
@@ -28,8 +30,12 @@ def hf_model(cfg: ModelCfg, weights: dict, dtype):
         vocab_size=cfg.vocab, hidden_size=cfg.hidden, intermediate_size=cfg.intermediate,
         num_hidden_layers=cfg.num_layers, num_attention_heads=cfg.q_heads, num_key_value_heads=cfg.kv_heads,
         head_dim=cfg.head_dim, max_position_embeddings=cfg.max_model_len, rms_norm_eps=cfg.rms_eps,
-        rope_theta=cfg.rope_theta, tie_word_embeddings=False, attention_bias=False, mlp_bias=False,
+        tie_word_embeddings=False, attention_bias=False, mlp_bias=False,
         hidden_act="silu",
+        rope_parameters=(dict(rope_type="llama3", rope_theta=cfg.rope_theta, factor=cfg.rope_factor,
+                              low_freq_factor=cfg.rope_low_freq_factor, high_freq_factor=cfg.rope_high_freq_factor,
+                              original_max_position_embeddings=cfg.rope_original_max_pos)
+                         if cfg.rope_scaling_type == 2 else dict(rope_type="default", rope_theta=cfg.rope_theta)),
     )
     hc._attn_implementation = "eager"
     m = LlamaForCausalLM(hc).to(dtype)
@@ -56,7 +62,11 @@ def hf_model(cfg: ModelCfg, weights: dict, dtype):
 
 
 def main():
-    cfg = ModelCfg()
+    write(ModelCfg(), OUT)
+    write(ModelCfg(**ROPE3), OUT_ROPE3)
+
+
+def write(cfg, OUT):
     w = make_weights(cfg)
     rng = np.random.default_rng(7)
     ids = rng.integers(0, cfg.vocab, size=40).astype(np.int64)

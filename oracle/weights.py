@@ -119,6 +119,12 @@ class ModelCfg:
     seed: int = 0
     init_scale: float = 4.0
     head_dim: int = 128
+    # RoPE frequency scaling (b200_config.rope_scaling_type: 0 none, 1 linear, 2 llama3)
+    rope_scaling_type: int = 0
+    rope_factor: float = 1.0
+    rope_low_freq_factor: float = 1.0
+    rope_high_freq_factor: float = 4.0
+    rope_original_max_pos: int = 8192
 
     @property
     def qkv_rows(self):
@@ -164,5 +170,14 @@ def cos_sin_cache(cfg: ModelCfg) -> np.ndarray:
     inv = (np.float32(1.0) / np.power(np.float32(cfg.rope_theta),
                                        np.arange(0, D, 2, dtype=np.float32) / np.float32(D))).astype(np.float32)
     t = np.arange(cfg.max_model_len, dtype=np.float32)
+    if cfg.rope_scaling_type == 1:      # vllm rotary_embedding/linear_scaling_rope.py: t / factor
+        t = (t / np.float32(cfg.rope_factor)).astype(np.float32)
+    elif cfg.rope_scaling_type == 2:    # vllm rotary_embedding/llama3_rope.py:37-54
+        orig, lo, hi, fac = (np.float32(x) for x in (cfg.rope_original_max_pos, cfg.rope_low_freq_factor,
+                                                     cfg.rope_high_freq_factor, cfg.rope_factor))
+        wl = (np.float32(2.0 * math.pi) / inv).astype(np.float32)
+        smooth = ((orig / wl - lo) / (hi - lo)).astype(np.float32) if lo != hi else np.zeros_like(inv)
+        mid = ((np.float32(1.0) - smooth) * inv / fac + smooth * inv).astype(np.float32)
+        inv = np.where(wl < orig / hi, inv, np.where(wl > orig / lo, inv / fac, mid)).astype(np.float32)
     f = np.outer(t, inv).astype(np.float32)
     return np.concatenate([np.cos(f), np.sin(f)], axis=-1).astype(np.float32)

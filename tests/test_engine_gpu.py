@@ -289,3 +289,46 @@ def test_engines_on_two_devices_in_one_process_agree():
             e0.step(); e1.step()
         assert [e0.poll(r).tokens for r in r0] == outs[0]
         assert [e1.poll(r).tokens for r in r1] == outs[0]
+
+
+def test_llama3_rope_scaling_matches_hf_golden():
+    """Llama-3.1 style RoPE frequency scaling: cos/sin table vs the numpy replica, logits vs HF."""
+    from kubeai_b200.engine import Engine, mini_config
+    from oracle.gen_golden import ROPE3
+    gold = np.load(Path(__file__).parent / "golden" / "llama_mini_rope3.npz")
+    cfg = ModelCfg(**ROPE3)
+    with Engine(mini_config(**ROPE3)) as e:
+        cs = e.tensor("cos_sin").reshape(cfg.max_model_len, 128)
+        want = f32_to_bf16_bits(cos_sin_cache(cfg))
+        diff = np.abs(cs.astype(np.int32) - want.astype(np.int32))
+        assert diff.max() <= 2 and (diff > 0).mean() < 0.002, (diff.max(), (diff > 0).mean())
+        plain = f32_to_bf16_bits(cos_sin_cache(ModelCfg()))
+        assert (cs != plain).mean() > 0.3                              # the scaling is not a no-op
+        got = e.forward_logits(gold["ids"])
+        _logit_close(got, gold["logits_fp32"], "engine (llama3 rope) vs HF fp32 golden")
+        out = e.generate([gold["ids"].tolist()], max_tokens=12)[0]
+    o = LlamaOracle(cfg, make_weights(cfg))
+    want_t, rows = o.generate(gold["ids"].tolist(), 12)
+    for i, (a, b) in enumerate(zip(out, want_t)):
+        if float(torch.sort(rows[i])[0][-1] - torch.sort(rows[i])[0][-2]) < 0.25:
+            break
+        assert a == b, f"token {i}"
+
+
+def test_create_time_validation_of_pool_and_shapes():
+    """a pool that cannot hold one max_model_len sequence, and shapes the kernels reject, fail at create."""
+    from kubeai_b200 import B200Error
+    from kubeai_b200.engine import Engine, mini_config
+    with pytest.raises(B200Error, match="KV pool too small"):
+        Engine(mini_config(max_model_len=256, num_kv_blocks=8))        # needs 16 pages
+    with pytest.raises(B200Error, match="unsupported model/config"):
+        Engine(mini_config(hidden=576))                                # not a multiple of 256
+    with pytest.raises(B200Error, match="unsupported model/config"):
+        Engine(mini_config(vocab=509))
+    with pytest.raises(B200Error, match="rope scaling"):
+        Engine(mini_config(rope_scaling_type=2, rope_factor=0.0))
+    with Engine(mini_config(max_model_len=256, num_kv_blocks=16)) as e:   # exactly one sequence fits
+        rng = np.random.default_rng(3)
+        outs = e.generate([rng.integers(0, 512, size=200).tolist(), rng.integers(0, 512, size=120).tolist()], max_tokens=50)
+        assert [len(o) for o in outs] == [50, 50]                      # served one after the other through preemption
+        assert e.stats().preemptions >= 0

@@ -63,6 +63,44 @@ def test_corrupt_safetensors_is_rejected(tmp_path):
     p.write_bytes(struct.pack("<Q", len(hdr)) + hdr + b"\0" * 8)
     with pytest.raises(B200Error, match="data_offsets out of range"):
         safetensors_list(p)
+    # untrusted header numbers: negative, fractional, wrapping (2^64 - 2048) and overflowing shapes are all refused
+    for entry in ({"dtype": "BF16", "shape": [4], "data_offsets": [-8, 0]},
+                  {"dtype": "BF16", "shape": [4], "data_offsets": [0, 7.5]},
+                  {"dtype": "BF16", "shape": [4], "data_offsets": [18446744073709549568, 18446744073709549576]},
+                  {"dtype": "BF16", "shape": [-4], "data_offsets": [0, 8]},
+                  {"dtype": "BF16", "shape": [4294967296, 4294967296, 16], "data_offsets": [0, 8]},
+                  {"dtype": "BF16", "shape": ["4"], "data_offsets": [0, 8]}):
+        hdr = json.dumps({"w": entry}).encode()
+        p.write_bytes(struct.pack("<Q", len(hdr)) + hdr + b"\0" * 8)
+        with pytest.raises(B200Error, match="out of range"):
+            safetensors_list(p)
+
+
+def test_config_json_rope_scaling_and_unsupported_switches(tmp_path):
+    base = dict(model_type="llama", hidden_size=512, num_attention_heads=4, num_key_value_heads=1, intermediate_size=1024,
+                num_hidden_layers=2, vocab_size=512, head_dim=128, rms_norm_eps=1e-5, rope_theta=500000.0, hidden_act="silu")
+
+    def cfg_of(**kw):
+        d = dict(base)
+        d.update(kw)
+        (tmp_path / "config.json").write_text(json.dumps(d))
+        return config_from_hf(tmp_path)
+    c = cfg_of()
+    assert c.rope_scaling_type == 0
+    # Llama-3.1 style (transformers < 5 key "rope_scaling", >= 5 key "rope_parameters")
+    l3 = dict(rope_type="llama3", factor=8.0, low_freq_factor=1.0, high_freq_factor=4.0, original_max_position_embeddings=8192)
+    for key in ("rope_scaling", "rope_parameters"):
+        c = cfg_of(**{key: dict(l3, rope_theta=500000.0)})
+        assert (c.rope_scaling_type, c.rope_factor, c.rope_low_freq_factor, c.rope_high_freq_factor, c.rope_original_max_pos) == \
+               (2, 8.0, 1.0, 4.0, 8192)
+    c = cfg_of(rope_scaling=dict(type="linear", factor=2.0))
+    assert (c.rope_scaling_type, c.rope_factor) == (1, 2.0)
+    for kw, msg in ((dict(rope_scaling=dict(rope_type="yarn", factor=4.0)), "yarn"), (dict(model_type="qwen2"), "model_type"),
+                    (dict(hidden_act="gelu"), "hidden_act"), (dict(attention_bias=True), "attention_bias"),
+                    (dict(mlp_bias=True), "mlp_bias"), (dict(hidden_size=576, num_attention_heads=4, head_dim=128), "hidden"),
+                    (dict(vocab_size=509), "vocab")):
+        with pytest.raises(B200Error, match=msg):
+            cfg_of(**kw)
 
 
 @pytest.mark.gpu

@@ -33,6 +33,22 @@ def test_oracle_logits_match_hf():
     assert (l.argmax(-1)[solid] == GOLD["logits_fp32"].argmax(-1)[solid]).all()
 
 
+def test_oracle_with_llama3_rope_scaling_matches_hf():
+    """Llama-3.1 style frequency scaling (b200_config.rope_scaling_type 2): pinned on HF's own implementation."""
+    from oracle.gen_golden import ROPE3
+    gold = np.load(Path(__file__).parent / "golden" / "llama_mini_rope3.npz")
+    cfg = ModelCfg(**ROPE3)
+    o = O.LlamaOracle(cfg, make_weights(cfg))
+    l = o.forward(gold["ids"])[0].numpy()
+    err = np.abs(l - gold["logits_fp32"])
+    assert (err <= 0.15 + 1.6e-2 * np.abs(gold["logits_fp32"])).all() and err.mean() < 0.04, err.max()
+    toks, rows = o.generate(gold["ids"].tolist(), 12)
+    assert toks == gold["greedy"].tolist()
+    # and the scaling is not a no-op: the unscaled model gives different logits
+    l0 = O.LlamaOracle(ModelCfg(), make_weights(ModelCfg())).forward(gold["ids"])[0].numpy()
+    assert np.abs(l0 - l).max() > 1.0
+
+
 def test_oracle_greedy_matches_hf_and_kv_cache_path_is_consistent():
     cfg = ModelCfg()
     o = O.LlamaOracle(cfg, make_weights(cfg))

@@ -179,3 +179,24 @@ def test_parse_request_and_split_model_adapter_tables(psrv):
     st, r = psrv.parse_request("/v1/chat/completions", '{"model":"test-model","top_k":5,"nested":{"a":[1,2,{"b":null}]},'
                                '"messages":[{"role":"user","content":"\\u4e16\\ud83d\\ude00x"}]}', prefix_chars=2)
     assert st == 0 and r["prefix"] == "世😀"
+
+
+def test_unsupported_request_fields_are_refused_not_dropped(psrv):
+    """Fields of the reference's schema (api/openai/v1/chat_completions.go:361-470) whose semantics the engine does not
+    implement get a 400 at parse time; harmless ones (seed with greedy decoding, user, stream_options) pass."""
+    base = {"model": "test-model", "messages": [{"role": "user", "content": "hi"}]}
+    ok = [{}, {"seed": 7}, {"user": "u"}, {"n": 1}, {"logprobs": False}, {"stop": []}, {"stop": None}, {"top_logprobs": 0},
+          {"presence_penalty": 0}, {"response_format": {"type": "text"}}, {"stop_token_ids": [5]}, {"tools": []}]
+    for extra in ok:
+        st, out = psrv.parse_request("/openai/v1/chat/completions", json.dumps({**base, **extra}))
+        assert st == 0, (extra, out)
+    bad = [({"n": 2}, "n > 1"), ({"best_of": 4}, "best_of"), ({"logprobs": True}, "logprobs"), ({"top_logprobs": 5}, "logprobs"),
+           ({"stop": "\n\n"}, "stop strings"), ({"stop": ["a", "b"]}, "stop strings"), ({"echo": True}, "echo"),
+           ({"frequency_penalty": 0.5}, "penalties"), ({"repetition_penalty": 1.1}, "penalties"),
+           ({"logit_bias": {"5": 1}}, "logit_bias"), ({"tools": [{"type": "function"}]}, "tool calling"),
+           ({"response_format": {"type": "json_object"}}, "response_format"), ({"min_tokens": 4}, "min_tokens")]
+    for extra, msg in bad:
+        st, out = psrv.parse_request("/openai/v1/chat/completions", json.dumps({**base, **extra}))
+        assert st == 400 and msg in out["error"] and "not supported" in out["error"], (extra, st, out)
+    st, out = psrv.parse_request("/openai/v1/completions", json.dumps({"model": "test-model", "prompt": "x", "suffix": "y"}))
+    assert st == 400 and "suffix" in out["error"]

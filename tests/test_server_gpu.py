@@ -140,3 +140,45 @@ def test_client_disconnect_aborts_the_sequence(stack):
     st = [e.stats() for e in engines]
     assert all(s.running == 0 and s.kv_blocks_free == s.kv_blocks_total for s in st)
     assert sum(s.generated_tokens for s in st) < 200
+
+
+def test_failed_replica_leaves_the_endpoint_set(stack):
+    """A replica whose engine is in the failed state is dropped from the router like an endpoint that vanished
+    (internal/loadbalancer/group.go:119-131): one request pays the retry, later ones never see the dead replica."""
+    from kubeai_b200.server import LEAST_LOAD, Server
+    _, engines = stack
+    with Server(engines, model="mini", strategy=LEAST_LOAD, vocab=V, max_model_len=1024) as srv:
+        assert not any(srv._l.b200_engine_is_failed(e._h) for e in engines)
+        srv.inject_fault(0, -1)                                    # replica 0 fails every submit from now on
+        retried = lambda: int(re.search(r"b200_request_retries_total (\d+)", srv.metrics()).group(1))
+        # LeastLoad picks an idle replica; ties go to the first endpoint, so the dead one is tried first
+        for i in range(6):
+            assert chat(srv, [{"role": "user", "content": f"after the failure {i}"}]).status == 200
+        assert retried() == 1, "only the request that found the replica dead retried"
+        m = srv.metrics()
+        assert 'endpoint="gpu-0"' not in m.split("b200_requests_total")[0] or "gpu-1" in m
+        st0, st1 = engines[0].stats(), engines[1].stats()
+        assert st0.generated_tokens == 0 and st1.generated_tokens == 6 * 6
+
+
+def test_destroy_with_idle_keepalive_client_returns_promptly(stack):
+    """The destructor shuts client sockets down and waits for every connection thread: no 5 s stall, nothing touches
+    the freed server afterwards."""
+    import socket
+    import time
+    from kubeai_b200.server import LEAST_LOAD, Server
+    _, engines = stack
+    srv = Server(engines, model="mini", strategy=LEAST_LOAD, vocab=V, max_model_len=1024)
+    port = srv.listen()
+    socks = []
+    for _ in range(3):
+        c = socket.create_connection(("127.0.0.1", port))
+        c.sendall(b"GET /healthz HTTP/1.1\r\nHost: x\r\n\r\n")
+        assert b"200 OK" in c.recv(4096)
+        socks.append(c)                                           # kept open: the server thread sits in recv()
+    t0 = time.perf_counter()
+    srv.close()
+    assert time.perf_counter() - t0 < 1.0
+    for c in socks:
+        assert c.recv(16) == b""                                  # peer closed
+        c.close()
