@@ -157,6 +157,11 @@ int b200_engine_tensor_write(b200_engine* e, const char* name, const void* host_
 /* Debug/parity: run a plain forward over `n` tokens of ONE sequence (positions 0..n-1, fresh KV pages taken from
  * the pool and returned afterwards) and copy the bf16 logits of every position to host_logits [n, vocab]. */
 int b200_engine_forward_logits(b200_engine* e, const int32_t* ids, int32_t n, void* host_logits_bf16);
+/* Parity hook for decode steps (manual_step mode): with keep != 0 the lm_head of every later step leaves the complete
+ * bf16 logits of its sampled rows in HBM (the serving path only keeps what the argmax needs); read_logits copies the
+ * first `rows` rows [rows, vocab] of the last step, in the order the step sampled them (scheduling order). */
+int b200_engine_set_keep_logits(b200_engine* e, int32_t keep);
+int b200_engine_read_logits(b200_engine* e, void* host_logits_bf16, int32_t rows);
 
 /* ------------------------------------------------------------------ checkpoints
  * HF-layout Llama checkpoints: <dir>/config.json + model.safetensors[.index.json] (BF16/F16/F32 tensors).

@@ -123,6 +123,8 @@ SYMBOLS = {
     "b200_engine_tensor_read": (C.c_int, [_vp, C.c_char_p, _vp, _u64]),
     "b200_engine_tensor_write": (C.c_int, [_vp, C.c_char_p, _vp, _u64]),
     "b200_engine_forward_logits": (C.c_int, [_vp, _pi32, _i32, _vp]),
+    "b200_engine_set_keep_logits": (C.c_int, [_vp, _i32]),
+    "b200_engine_read_logits": (C.c_int, [_vp, _vp, _i32]),
     "b200_config_from_hf": (C.c_int, [C.c_char_p, C.POINTER(Config)]),
     "b200_engine_load_safetensors": (C.c_int, [_vp, C.c_char_p]),
     "b200_safetensors_list": (C.c_int64, [C.c_char_p, C.c_char_p, C.c_size_t]),

@@ -279,6 +279,8 @@ struct Engine {
   double step_timing_last_end = 0;
   uint32_t skip_mask = 0;  // debug/timing: kernel classes (1 << B200_K_*) NOT launched by forward() (results are garbage)
   bool profiling = false;
+  bool keep_logits = false;  // parity hook: lm_head leaves complete bf16 logits (b200_engine_set_keep_logits)
+  int last_S = 0;
   std::vector<std::pair<int, cudaEvent_t>> prof_events;  // (class, event) in launch order: start, stop pairs
   size_t prof_used = 0;
 
@@ -637,8 +639,9 @@ int Engine::forward(const StepMeta& m, int32_t* dbuf, bool all_logits, bf16* log
     P(B200_K_NORM); rc |= rmsnorm(x, res, final_norm, last_hidden, rows, m.S, H, cfg.rms_eps, stream, pv_x); Q();
     PartialView pv = no_partials();
     P(B200_K_GEMM_LM);
-    if (dfr) rc |= gemm_def(p_lm, xm_last, logits, V, m.S, &pv); else rc |= gemm(p_lm, xm_last, logits, V, m.S);
+    if (dfr && !keep_logits) rc |= gemm_def(p_lm, xm_last, logits, V, m.S, &pv); else rc |= gemm(p_lm, xm_last, logits, V, m.S);
     Q();
+    last_S = m.S;
     P(B200_K_ARGMAX); rc |= argmax_rows(logits, sampled, m.S, V, V, stream, pv); Q();
     launched(2);
   }
@@ -1336,6 +1339,24 @@ int b200_engine_tensor_write(b200_engine* e, const char* name, const void* host_
   cudaSetDevice(e->impl.cfg.device);
   CK(cudaStreamSynchronize(e->impl.stream));
   CK(cudaMemcpy(p, host_src, nb, cudaMemcpyHostToDevice));
+  return 0;
+}
+
+int b200_engine_set_keep_logits(b200_engine* e, int32_t keep) {
+  if (!e) { set_error("null engine"); return B200_ERR_INVALID; }
+  if (!e->impl.cfg.manual_step) { set_error("keep_logits needs manual_step"); return B200_ERR_INVALID; }
+  e->impl.keep_logits = keep != 0;
+  return 0;
+}
+
+int b200_engine_read_logits(b200_engine* e, void* host_logits_bf16, int32_t rows) {
+  if (!e || !host_logits_bf16 || rows <= 0) { set_error("bad arguments"); return B200_ERR_INVALID; }
+  Engine& g = e->impl;
+  if (!g.keep_logits) { set_error("logits are only kept after b200_engine_set_keep_logits(e, 1)"); return B200_ERR_INVALID; }
+  if (rows > g.last_S) { set_error("the last step sampled %d rows", g.last_S); return B200_ERR_INVALID; }
+  cudaSetDevice(g.cfg.device);
+  CK(cudaStreamSynchronize(g.stream));
+  CK(cudaMemcpy(host_logits_bf16, g.logits, static_cast<size_t>(rows) * g.V * 2, cudaMemcpyDeviceToHost));
   return 0;
 }
 

@@ -186,6 +186,15 @@ class Engine:
                                                  out.ctypes.data_as(C.c_void_p)))
         return (out.astype(np.uint32) << 16).view(np.float32)
 
+    def set_keep_logits(self, on: bool):
+        check(self._l.b200_engine_set_keep_logits(self._h, 1 if on else 0))
+
+    def read_logits(self, rows: int) -> np.ndarray:
+        """fp32 array [rows, vocab] of the bf16 logits the last step sampled from (after set_keep_logits(True))."""
+        out = np.empty((rows, self.cfg.vocab), dtype=np.uint16)
+        check(self._l.b200_engine_read_logits(self._h, out.ctypes.data_as(C.c_void_p), rows))
+        return (out.astype(np.uint32) << 16).view(np.float32)
+
     def generate(self, prompts, max_tokens=16, max_steps=100000):
         """Manual-step helper: run all prompts to completion, return the list of token lists."""
         rids = [self.submit(p, max_tokens=max_tokens) for p in prompts]

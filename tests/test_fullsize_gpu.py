@@ -1,0 +1,208 @@
+"""Parity at BASELINE config 2's model size (Llama-3-8B shapes: hidden 4096, 32 query / 8 KV heads of 128, intermediate 14336,
+vocab 128256), default-on in the GPU suite:
+
+  * one full-size decoder layer + lm_head through the engine against the oracle's ops on the same weights, for a
+    T=128 prefill, a T=1536 prefill and a 128-sequence decode step over contexts 16..2047 (the production decode batch);
+  * paged attention at Hq/Hkv = 32/8 with 128 sequences, contexts {16, 1023, 2048} and ragged ones, shuffled block
+    tables, for decode and for chunked prefill on top of a cached prefix.
+
+Tolerances.  Ops: vLLM's bf16 kernel tolerance (vllm/ir/tolerances.py:13-24: atol 1e-3, rtol 1.6e-2).  Logits: stated in
+bf16 ulps of the logit — |got - want| <= LOGIT_ULPS * ulp_bf16(|want|) + 1e-3, ulp_bf16(x) = 2^(floor(log2 x) - 7) — a
+logit is one bf16 rounding of a 4096-term fp32 dot product of values that themselves carry up to one ulp of upstream
+difference, so 2 ulps is the floor for two correct bf16 pipelines; the measured maxima are printed.
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import llama_oracle as O
+from oracle.weights import ModelCfg, bf16_bits_to_f32, cos_sin_cache
+
+pytestmark = pytest.mark.gpu
+LOGIT_ULPS = 3.0
+SHAPE = dict(num_layers=1, hidden=4096, q_heads=32, kv_heads=8, intermediate=14336, vocab=128256, max_model_len=2048)
+
+
+def ulp_bf16(x: np.ndarray) -> np.ndarray:
+    a = np.maximum(np.abs(x), 2.0 ** -20)
+    return np.exp2(np.floor(np.log2(a)) - 7)
+
+
+def logits_close(got, want, what):
+    err = np.abs(got - want)
+    tol = LOGIT_ULPS * ulp_bf16(want) + 1e-3
+    worst = float((err / ulp_bf16(want)).max())
+    print(f"{what}: max |dlogit| {err.max():.4f}, max error {worst:.2f} bf16 ulps of the logit, mean |dlogit| {err.mean():.5f}")
+    assert (err <= tol).all(), f"{what}: {int((err > tol).sum())} of {err.size} logits outside {LOGIT_ULPS} ulps (worst {worst:.2f})"
+    return worst
+
+
+@pytest.fixture(scope="module")
+def layer():
+    """A one-layer engine at the full shapes and its weights as oracle tensors (read back through the C ABI; the seeded
+    init itself is pinned bit-exactly on the numpy replica by test_engine_gpu.py)."""
+    from kubeai_b200.engine import Engine, default_config
+    e = Engine(default_config(manual_step=1, max_num_seqs=128, max_batched_tokens=1536, num_kv_blocks=128 * 129 + 64, **SHAPE))
+    cfg = ModelCfg(**SHAPE)
+    names = ["embed", "final_norm", "lm_head"] + ["layers.0." + n for n in ("wqkv", "wo", "wgu", "wdown", "norm1", "norm2")]
+    w = {}
+    for n in names:
+        w[n] = torch.from_numpy(bf16_bits_to_f32(e.tensor(n)).copy())
+    H, I, V = cfg.hidden, cfg.intermediate, cfg.vocab
+    for n, shp in (("embed", (V, H)), ("lm_head", (V, H)), ("layers.0.wqkv", (cfg.qkv_rows, H)), ("layers.0.wo", (H, H)),
+                   ("layers.0.wgu", (2 * I, H)), ("layers.0.wdown", (H, I))):
+        w[n] = w[n].reshape(shp)
+    cs = O.r(torch.from_numpy(cos_sin_cache(cfg)))
+    yield e, cfg, w, cs
+    e.close()
+
+
+def oracle_layer(cfg, w, cs, ids, rows):
+    """Logits of the positions `rows` of one sequence `ids` through the one-layer model (oracle ops, full prefill)."""
+    D, Hq, Hkv = cfg.head_dim, cfg.q_heads, cfg.kv_heads
+    n = len(ids)
+    pos = torch.arange(n)
+    hidden = w["embed"][torch.as_tensor(ids, dtype=torch.long)]
+    h = O.rms_norm(hidden, w["layers.0.norm1"], cfg.rms_eps)
+    qkv = O.gemm(h, w["layers.0.wqkv"])
+    q = O.rope_neox(qkv[:, :Hq * D].reshape(n, Hq, D), pos, cs)
+    k = O.rope_neox(qkv[:, Hq * D:(Hq + Hkv) * D].reshape(n, Hkv, D), pos, cs)
+    v = qkv[:, (Hq + Hkv) * D:].reshape(n, Hkv, D)
+    rows = torch.as_tensor(rows, dtype=torch.long)
+    a = O.attention(q[rows], k, v, pos[rows], 1.0 / math.sqrt(D)).reshape(len(rows), Hq * D)
+    o = O.gemm(a, w["layers.0.wo"])
+    h2, res = O.fused_add_rms_norm(o, hidden[rows], w["layers.0.norm2"], cfg.rms_eps)
+    down = O.gemm(O.silu_and_mul(O.gemm(h2, w["layers.0.wgu"])), w["layers.0.wdown"])
+    hf, _ = O.fused_add_rms_norm(down, res, w["final_norm"], cfg.rms_eps)
+    return O.gemm(hf, w["lm_head"]).numpy()
+
+
+@pytest.mark.parametrize("T", [128, 1536])
+def test_full_size_layer_prefill_logits_match_oracle(layer, T):
+    e, cfg, w, cs = layer
+    rng = np.random.default_rng(T)
+    ids = rng.integers(0, cfg.vocab, size=T).tolist()
+    got = e.forward_logits(ids)
+    rows = sorted(set(range(0, T, max(1, T // 96))) | {T - 1, T - 2, 15, 16, 17})
+    want = oracle_layer(cfg, w, cs, ids, rows)
+    logits_close(got[rows], want, f"prefill T={T} ({len(rows)} rows x {cfg.vocab})")
+    margin = np.sort(want, axis=-1)[:, -2:]
+    solid = (margin[:, 1] - margin[:, 0]) > 4 * ulp_bf16(margin[:, 1])
+    assert (got[rows].argmax(-1)[solid] == want.argmax(-1)[solid]).all()
+
+
+def test_full_size_decode_step_of_128_sequences_matches_oracle(layer):
+    """The production decode batch: 128 sequences with contexts from 17 to 2047 tokens (ragged last pages), prefilled in
+    chunks by the scheduler while the earlier ones already decode; the first step in which ALL 128 decode (T = 128, the
+    shape of ~80% of the bench's steps) is compared row by row with the oracle's last-position logits."""
+    e, cfg, w, cs = layer
+    rng = np.random.default_rng(5)
+    lens = [16, 17, 31, 1023, 1024, 1025, 500, 33] + rng.integers(16, 1900, size=117).tolist() + [2040, 2045, 2046]
+    prompts = [rng.integers(0, cfg.vocab, size=n).tolist() for n in lens]
+    e.set_keep_logits(True)
+    rids = [e.submit(p, max_tokens=400) for p in prompts]
+    gen = [[] for _ in rids]
+    lg = None
+    try:
+        for _ in range(600):
+            ran, info = e.step()
+            assert ran
+            for i, r in enumerate(rids):
+                gen[i] += e.poll(r).tokens
+            if info.prefill_seqs == 0 and info.decode_seqs == len(rids):
+                assert info.tokens == len(rids) and info.sampled == len(rids)
+                lg = e.read_logits(len(rids))       # rows in scheduling order = submission order
+                break
+    finally:
+        for r in rids:
+            e.release(r)
+        e.set_keep_logits(False)
+        while e.step()[0]:                            # released while running: the engine drops them at its next step
+            pass
+    assert lg is not None, "no step with all 128 sequences decoding"
+    ctx = [lens[i] + len(gen[i]) - 1 for i in range(len(rids))]      # tokens each row attended over (incl. itself)
+    assert max(ctx) == 2047 and min(ctx) < 150
+    assert all(int(lg[i].argmax()) == gen[i][-1] for i in range(len(rids))), "the sampled id is the argmax of the kept logits"
+    sel = sorted(range(len(rids)), key=lambda i: ctx[i])
+    sel = sel[:4] + sel[-4:] + sel[4:-4:6]            # the extremes and every 6th in between (CPU time of the oracle)
+    G = lg[sel]
+    Wn = np.stack([oracle_layer(cfg, w, cs, prompts[i] + gen[i][:-1], [ctx[i] - 1])[0] for i in sel])
+    logits_close(G, Wn, f"decode step T=128, {len(sel)} of 128 sequences (contexts {min(ctx)}..{max(ctx)})")
+    m = np.sort(Wn, axis=-1)[:, -2:]
+    solid = (m[:, 1] - m[:, 0]) > 4 * ulp_bf16(m[:, 1])
+    assert (G.argmax(-1)[solid] == Wn.argmax(-1)[solid]).all()
+
+
+# --------------------------------------------------------------------------------------------- attention, production shape
+def _pool(seq_lens, Hkv, seed, extra=7):
+    """Random bf16 K/V for every sequence scattered into a shuffled page pool [blocks][K|V][head][16][128]."""
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    nb_total = sum((l + 15) // 16 for l in seq_lens) + extra
+    perm = torch.randperm(nb_total, generator=torch.Generator().manual_seed(seed)).tolist()
+    kv = torch.zeros(nb_total, 2, Hkv, 16, 128, dtype=torch.bfloat16, device="cuda")
+    max_blocks = (max(seq_lens) + 15) // 16
+    btab = torch.zeros(len(seq_lens), max_blocks, dtype=torch.int32)
+    ks, vs = [], []
+    for s, L in enumerate(seq_lens):
+        nb = (L + 15) // 16
+        blocks = torch.tensor([perm.pop() for _ in range(nb)])
+        btab[s, :nb] = blocks.int()
+        k = torch.randn(nb * 16, Hkv, 128, generator=g, device="cuda").bfloat16()
+        v = torch.randn(nb * 16, Hkv, 128, generator=g, device="cuda").bfloat16()
+        kv[blocks.cuda(), 0] = k.reshape(nb, 16, Hkv, 128).permute(0, 2, 1, 3)
+        kv[blocks.cuda(), 1] = v.reshape(nb, 16, Hkv, 128).permute(0, 2, 1, 3)
+        ks.append(k[:L].float())
+        vs.append(v[:L].float())     # rows past L stay in the page as (finite) garbage the kernel must mask
+    return kv, btab.cuda(), ks, vs
+
+
+def _attn_close(got, want, what):
+    err = (got - want).abs()
+    tol = 4e-3 + 1.6e-2 * want.abs()          # vLLM bf16 tolerance (rtol 1.6e-2) + bf16 rounding of P and of the output
+    assert bool((err <= tol).all()), f"{what}: max err {float(err.max()):.4g}, {int((err > tol).sum())} outside tolerance"
+
+
+def test_decode_attention_at_production_shape():
+    """Hq/Hkv = 32/8, 128 sequences, contexts {16, 1023, 2048} plus ragged lengths, shuffled block tables."""
+    from kubeai_b200 import ops
+    Hq, Hkv = 32, 8
+    rng = np.random.default_rng(9)
+    lens = [16, 1023, 2048, 1, 15, 17, 2047, 1024] + rng.integers(1, 2049, size=120).tolist()
+    kv, btab, ks, vs = _pool(lens, Hkv, seed=21)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    q = torch.randn(len(lens), (Hq + 2 * Hkv) * 128, generator=g, device="cuda").bfloat16()
+    # work items in a shuffled order (the engine sorts them longest-first; any order must work)
+    order = rng.permutation(len(lens)).tolist()
+    work = torch.tensor([[i, 1, lens[i] - 1, i] for i in order], dtype=torch.int32).cuda()
+    got = ops.paged_attn(q, kv, btab, work, Hq, Hkv, decode=True).float()
+    torch.cuda.synchronize()
+    for i, L in enumerate(lens):
+        qi = q[i, :Hq * 128].float().reshape(1, Hq, 128)
+        want = O.attention(qi, ks[i], vs[i], torch.tensor([L - 1], device="cuda"), 128 ** -0.5).reshape(1, Hq * 128)
+        _attn_close(got[i:i + 1], want, f"decode seq {i} ctx {L}")
+
+
+def test_chunked_prefill_attention_at_production_shape_with_cached_prefix():
+    from kubeai_b200 import ops
+    Hq, Hkv = 32, 8
+    case = [(2048, 512), (1023, 1023), (16, 16), (1500, 37), (2047, 1), (777, 300), (64, 64), (1025, 1000)]   # (context, new tokens)
+    lens = [c[0] for c in case]
+    kv, btab, ks, vs = _pool(lens, Hkv, seed=22)
+    T = sum(n for _, n in case)
+    g = torch.Generator(device="cuda").manual_seed(4)
+    q = torch.randn(T, (Hq + 2 * Hkv) * 128, generator=g, device="cuda").bfloat16()
+    work, spans, tok = [], [], 0
+    for i, (L, n) in enumerate(case):
+        for j in range(0, n, 16):
+            work.append([tok + j, min(16, n - j), L - n + j, i])
+        spans.append(tok)
+        tok += n
+    got = ops.paged_attn(q, kv, btab, torch.tensor(work, dtype=torch.int32).cuda(), Hq, Hkv, decode=False).float()
+    torch.cuda.synchronize()
+    for i, (L, n) in enumerate(case):
+        t0 = spans[i]
+        qi = q[t0:t0 + n, :Hq * 128].float().reshape(n, Hq, 128)
+        want = O.attention(qi, ks[i], vs[i], torch.arange(L - n, L, device="cuda"), 128 ** -0.5).reshape(n, Hq * 128)
+        _attn_close(got[t0:t0 + n], want, f"prefill seq {i} ctx {L} new {n}")
