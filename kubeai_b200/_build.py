@@ -20,6 +20,7 @@ OBJ = ROOT / "lib" / "obj"
 SOURCES = [
     "gemm_tcgen05.cu",
     "gemm2_tcgen05.cu",
+    "gemm3_tcgen05.cu",
     "attention.cu",
     "elementwise.cu",
     "abi_ops.cu",

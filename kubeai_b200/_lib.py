@@ -31,6 +31,16 @@ class Config(C.Structure):
     ]
 
 
+class Gemm3Args(C.Structure):
+    _fields_ = [("N", C.c_int32), ("T", C.c_int32), ("K", C.c_int32), ("x_rows", C.c_int32),
+                ("pro", C.c_int32), ("epi", C.c_int32), ("force", C.c_int32),
+                ("w", C.c_void_p), ("x", C.c_void_p), ("ssq_in", C.c_void_p), ("ssq_slabs", C.c_int32),
+                ("norm_w", C.c_void_p), ("eps", C.c_float), ("out", C.c_void_p), ("ldo", C.c_int32),
+                ("ssq_out", C.c_void_p), ("positions", C.c_void_p), ("slots", C.c_void_p), ("cos_sin", C.c_void_p),
+                ("kv_layer", C.c_void_p), ("q_heads", C.c_int32), ("kv_heads", C.c_int32), ("max_pos", C.c_int32),
+                ("argmax_out", C.c_void_p), ("n_valid", C.c_int32)]
+
+
 class Sampling(C.Structure):
     _fields_ = [("max_tokens", C.c_int32), ("temperature", C.c_float), ("ignore_eos", C.c_int32),
                 ("num_stop_ids", C.c_int32), ("stop_ids", C.POINTER(C.c_int32))]
@@ -158,6 +168,7 @@ SYMBOLS = {
     "b200_op_gemm_trace": (C.c_int, [_vp]),
     "b200_op_gemm_deferred": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp]),
     "b200_op_gemm": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp]),
+    "b200_op_gemm3": (C.c_int, [C.POINTER(Gemm3Args), _vp, _pi32]),
     "b200_op_embed": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp]),
     "b200_op_rmsnorm": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _f, _vp]),
     "b200_op_rope_kvwrite": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),

@@ -10,6 +10,7 @@
 #include "../../include/b200engine.h"
 #include "errors.h"
 #include "gemm.h"
+#include "gemm3.h"
 #include "kernels.h"
 
 namespace b200 {
@@ -121,6 +122,54 @@ int b200_op_gemm_deferred(const void* w, const void* x, void* out, int32_t N, in
   cudaStreamSynchronize(st);  // the segment table is freed below
   gemm_plan_destroy(&plan);
   return rc ? cuda_fail("gemm_deferred", rc) : 0;
+}
+
+int b200_op_gemm3(const b200_gemm3_args* a, void* stream, int32_t* schedule_out) {
+  if (int rc = require_device()) return rc;
+  if (!a || !a->w || !a->x || a->N <= 0 || a->T <= 0 || a->K <= 0 || a->x_rows < a->T) {
+    set_error("b200_op_gemm3: bad arguments");
+    return B200_ERR_INVALID;
+  }
+  if (ensure_scratch()) { set_error("workspace allocation failed"); return B200_ERR_OOM; }
+  static float2* cand = nullptr;          // [128 tokens][slabs]
+  static int* flags = nullptr;
+  static int epoch = 0;
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lk(mu);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!flags) {
+    if (cudaMalloc(&flags, 4096 * sizeof(int)) != cudaSuccess || cudaMemset(flags, 0, 4096 * sizeof(int)) != cudaSuccess) return B200_ERR_OOM;
+    if (cudaMalloc(&cand, sizeof(float2) * 128 * 4096) != cudaSuccess) return B200_ERR_OOM;
+  }
+  if (a->epi == GEMM3_EPI_ARGMAX && (a->N / 128 > 4096 || !a->argmax_out)) { set_error("b200_op_gemm3: argmax needs argmax_out and N <= 524288"); return B200_ERR_INVALID; }
+  Gemm3Schedule sch;
+  int rc = gemm3_schedule(a->N, a->K, a->T, a->pro, a->force, &sch);
+  if (rc) { set_error("b200_op_gemm3: shape / schedule not served (rc=%d, N=%d K=%d T=%d force=%d)", rc, a->N, a->K, a->T, a->force); return B200_ERR_INVALID; }
+  if (gemm3_ws_bytes(sch.grid) > g_ws_bytes) { set_error("b200_op_gemm3: workspace too small"); return B200_ERR_INVALID; }
+  GemmPlan plan;
+  rc = gemm_plan_init(&plan, a->w, a->N, a->K, a->K, g_ws, g_counters, 0);
+  if (rc) return cuda_fail("gemm_plan_init", rc);
+  Gemm3Params p;
+  memset(&p, 0, sizeof(p));
+  p.tm_w = plan.tm_w;
+  rc = gemm_make_x_map(&p.tm_x, a->x, a->x_rows, a->K, a->K, 128);
+  if (rc) return cuda_fail("gemm_make_x_map", rc);
+  p.N = a->N; p.T = a->T; p.K = a->K; p.pro = a->pro; p.epi = a->epi;
+  p.ssq_in = a->ssq_in; p.ssq_slabs = a->ssq_slabs; p.norm_w = static_cast<const __nv_bfloat16*>(a->norm_w); p.eps = a->eps;
+  p.out = static_cast<__nv_bfloat16*>(a->out); p.ldo = a->ldo; p.ssq_out = a->ssq_out;
+  p.positions = a->positions; p.slots = a->slots; p.cos_sin = static_cast<const __nv_bfloat16*>(a->cos_sin);
+  p.kv_layer = static_cast<__nv_bfloat16*>(a->kv_layer); p.Hq = a->q_heads; p.Hkv = a->kv_heads; p.max_pos = a->max_pos;
+  p.cand = cand; p.n_valid = a->n_valid > 0 ? a->n_valid : a->N;
+  p.ws = g_ws; p.flags = flags; p.epoch = ++epoch;
+  if (schedule_out) { schedule_out[0] = sch.S; schedule_out[1] = sch.streamk; schedule_out[2] = sch.grid; }
+  rc = gemm3_launch(p, sch, st);
+  if (rc) return cuda_fail("gemm3_launch", rc);
+  if (a->epi == GEMM3_EPI_ARGMAX) {
+    rc = argmax_candidates(cand, a->argmax_out, a->T, a->N / 128, st);
+    if (rc) return cuda_fail("argmax_candidates", rc);
+    cudaStreamSynchronize(st);   // the shared candidate buffer is reused by the next call
+  }
+  return 0;
 }
 
 int b200_set_gemm_variant(int32_t v) {

@@ -30,15 +30,38 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 // ------------------------------------------------------------------ embedding gather
+// ssq (optional): [T, ssq_slabs] per-slab sums of squares of the row, the form the fused GEMM's RMSNorm prologue reads
+// (gemm3_tcgen05.cu PRO_NORM); the whole row's sum goes to slab 0, the other slabs are zeroed.
 __global__ void embed_kernel(const __nv_bfloat16* __restrict__ table, const int* __restrict__ ids,
-                             __nv_bfloat16* __restrict__ out, int H, int vocab) {
+                             __nv_bfloat16* __restrict__ out, int H, int vocab, float* __restrict__ ssq, int ssq_slabs) {
   griddep_enter();
   const int t = blockIdx.x;
   int id = ids[t];
   if (id < 0 || id >= vocab) id = 0;
   const uint4* src = reinterpret_cast<const uint4*>(table + static_cast<size_t>(id) * H);
   uint4* dst = reinterpret_cast<uint4*>(out + static_cast<size_t>(t) * H);
-  for (int i = threadIdx.x; i < H / 8; i += blockDim.x) dst[i] = __ldg(src + i);
+  float ss = 0.f;
+  for (int i = threadIdx.x; i < H / 8; i += blockDim.x) {
+    Vec8 v;
+    v.u = __ldg(src + i);
+    dst[i] = v.u;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float f = __bfloat162float(v.h[j]);
+      ss += f * f;
+    }
+  }
+  if (!ssq) return;
+  __shared__ float red[32];
+  ss = warp_sum(ss);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) ssq[static_cast<size_t>(t) * ssq_slabs] = v;
+  }
+  for (int i = 1 + threadIdx.x; i < ssq_slabs; i += blockDim.x) ssq[static_cast<size_t>(t) * ssq_slabs + i] = 0.f;
 }
 
 // ------------------------------------------------------------------ (fused add) RMSNorm
@@ -245,11 +268,12 @@ __global__ void rope_kv_kernel(__nv_bfloat16* __restrict__ qkv, const int* __res
 
 // ------------------------------------------------------------------ SiLU(gate) * up
 template <int VPT>  // uint4 output vectors per thread
+// interleaved != 0: gate and up columns alternate in 64-column blocks (the engine's gate_up weight rows are laid out
+// that way so that the decode GEMM's epilogue finds a gate row and its up row in one 128-row slab)
 __global__ void silu_mul_kernel(const __nv_bfloat16* __restrict__ gu, __nv_bfloat16* __restrict__ out, int I,
-                                int ldi, PartialView pv) {
+                                int ldi, PartialView pv, int interleaved) {
   const int t = blockIdx.y;
   const uint4* g = reinterpret_cast<const uint4*>(gu + static_cast<size_t>(t) * ldi);
-  const uint4* u = reinterpret_cast<const uint4*>(gu + static_cast<size_t>(t) * ldi + I);
   uint4* o = reinterpret_cast<uint4*>(out + static_cast<size_t>(t) * I);
   const int nvec = I / 8;
   const int i0 = blockIdx.x * blockDim.x * VPT + threadIdx.x;
@@ -259,8 +283,9 @@ __global__ void silu_mul_kernel(const __nv_bfloat16* __restrict__ gu, __nv_bfloa
 #pragma unroll
   for (int k = 0; k < VPT; ++k) {
     const int i = min(i0 + k * static_cast<int>(blockDim.x), nvec - 1);
-    n0[k] = i * 8;
-    n0[VPT + k] = I + i * 8;
+    const int c = i * 8;
+    n0[k] = interleaved ? ((c >> 6) << 7) + (c & 63) : c;
+    n0[VPT + k] = interleaved ? n0[k] + 64 : I + c;
   }
   if (pv.ws) partial_entries<2 * VPT>(pv, t, n0, ent);  // static table: looked up before the dependency wait
   griddep_enter();
@@ -271,7 +296,7 @@ __global__ void silu_mul_kernel(const __nv_bfloat16* __restrict__ gu, __nv_bfloa
 #pragma unroll
     for (int k = 0; k < VPT; ++k) {
       raw[k] = g[n0[k] >> 3];
-      raw[VPT + k] = u[n0[k] >> 3];
+      raw[VPT + k] = g[n0[VPT + k] >> 3];
     }
 #pragma unroll
     for (int k = 0; k < 2 * VPT; ++k) unpack8_bf16(raw[k], x[k]);
@@ -361,6 +386,18 @@ __global__ void argmax_kernel(const __nv_bfloat16* __restrict__ logits, int* __r
   }
 }
 
+// ------------------------------------------------------------------ gate_up row layout
+// logical [gate rows 0..I) | up rows 0..I)]  <->  physical 64 gate rows, the 64 matching up rows, next 64 gate rows, ...
+__global__ void permute_gu_kernel(__nv_bfloat16* __restrict__ dst, const __nv_bfloat16* __restrict__ src, int I, int H,
+                                  int to_physical) {
+  const int r = blockIdx.x;  // logical row
+  const int i = r < I ? r : r - I;
+  const int pr = ((i >> 6) << 7) + (r < I ? 0 : 64) + (i & 63);
+  const uint4* s = reinterpret_cast<const uint4*>(src + static_cast<size_t>(to_physical ? r : pr) * H);
+  uint4* d = reinterpret_cast<uint4*>(dst + static_cast<size_t>(to_physical ? pr : r) * H);
+  for (int k = threadIdx.x; k < H / 8; k += blockDim.x) d[k] = s[k];
+}
+
 // ------------------------------------------------------------------ seeded weight init (device side)
 __device__ __forceinline__ uint32_t mix32(uint32_t x) {
   x ^= x >> 16;
@@ -385,11 +422,12 @@ __global__ void init_uniform_kernel(__nv_bfloat16* __restrict__ p, size_t n, uin
 
 }  // namespace
 
-int embed_gather(const void* table, const int* ids, void* out, int T, int H, int vocab, cudaStream_t st) {
+int embed_gather(const void* table, const int* ids, void* out, int T, int H, int vocab, cudaStream_t st, float* ssq,
+                 int ssq_slabs) {
   if (T <= 0) return 0;
   if (H % 8) return -1;
   launch_pdl(embed_kernel, dim3(T), dim3(256), 0, st, static_cast<const __nv_bfloat16*>(table), ids,
-             static_cast<__nv_bfloat16*>(out), H, vocab);
+             static_cast<__nv_bfloat16*>(out), H, vocab, ssq, ssq_slabs);
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 
@@ -432,16 +470,16 @@ int rope_kv_write(void* qkv, const int* positions, const int* slots, const void*
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 
-int silu_mul(const void* gate_up, void* out, int T, int I, cudaStream_t st, PartialView pv) {
+int silu_mul(const void* gate_up, void* out, int T, int I, cudaStream_t st, PartialView pv, int interleaved) {
   if (T <= 0) return 0;
   if (I % 8) return -1;
   const __nv_bfloat16* gu = static_cast<const __nv_bfloat16*>(gate_up);
   __nv_bfloat16* o = static_cast<__nv_bfloat16*>(out);
   // decode: one output vector per thread (2 loads in flight); prefill bursts: two (4 batched loads in flight)
   if (T >= 512)
-    launch_pdl(silu_mul_kernel<2>, dim3((I / 8 + 511) / 512, T), dim3(256), 0, st, gu, o, I, 2 * I, pv);
+    launch_pdl(silu_mul_kernel<2>, dim3((I / 8 + 511) / 512, T), dim3(256), 0, st, gu, o, I, 2 * I, pv, interleaved);
   else
-    launch_pdl(silu_mul_kernel<1>, dim3((I / 8 + 255) / 256, T), dim3(256), 0, st, gu, o, I, 2 * I, pv);
+    launch_pdl(silu_mul_kernel<1>, dim3((I / 8 + 255) / 256, T), dim3(256), 0, st, gu, o, I, 2 * I, pv, interleaved);
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 
@@ -449,6 +487,12 @@ int argmax_rows(const void* logits, int* out, int S, int V, int ld, cudaStream_t
   if (S <= 0) return 0;
   if (ld % 8 || (pv.ws && V % 8)) return -1;
   launch_pdl(argmax_kernel, dim3(S), dim3(1024), 0, st, static_cast<const __nv_bfloat16*>(logits), out, V, ld, pv);
+  return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+int permute_gate_up(void* dst, const void* src, int I, int H, int to_physical, cudaStream_t st) {
+  if (I % 64 || H % 8) return -1;
+  permute_gu_kernel<<<2 * I, 128, 0, st>>>(static_cast<__nv_bfloat16*>(dst), static_cast<const __nv_bfloat16*>(src), I, H, to_physical);
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 

@@ -30,6 +30,7 @@
 #include "../../include/b200engine.h"
 #include "errors.h"
 #include "gemm.h"
+#include "gemm3.h"
 #include "kernels.h"
 #include "hostutil.h"
 #include "xxh64.h"
@@ -240,6 +241,14 @@ struct Engine {
        *last_hidden = nullptr, *logits = nullptr;
   int* sampled = nullptr;
   int32_t* sampled_host = nullptr;  // pinned
+  // decode-shape fused path (gemm3_tcgen05.cu): per-slab sums of squares of the residual, argmax candidates, stream-K flags
+  float* ssq = nullptr;
+  float2* cand = nullptr;
+  int* g3_flags = nullptr;
+  int g3_epoch = 0;
+  bool fused_ok = false;
+  Gemm3Schedule sch_qkv, sch_o, sch_gu, sch_down, sch_lm;
+  XMaps xm_res;
   XMaps xm_normed, xm_attn, xm_act, xm_last;
   float* gemm_ws = nullptr;
   size_t gemm_ws_bytes = 0;
@@ -288,6 +297,7 @@ struct Engine {
   int init(const b200_config& c);
   int alloc_all();
   int forward(const StepMeta& m, int32_t* dbuf, bool all_logits, bf16* logits_out);
+  int forward_fused(const StepMeta& m, int32_t* dbuf);
   // one scheduler iteration = launch (schedule, pack, H2D, kernels, D2H enqueue) + complete (sync, apply) + publish
   int launch(InFlight* f, StepMeta* m);
   int complete(InFlight& f, const StepMeta& m, b200_step_info* info);
@@ -351,7 +361,7 @@ Engine::~Engine() {
   cudaSetDevice(cfg.device);
   if (stream) cudaStreamSynchronize(stream);
   void* frees[] = {weights_blob, res, x, normed, qkv, attn, gu, act, last_hidden, logits, sampled, gemm_ws,
-                   gemm_counters, kv};
+                   gemm_counters, kv, ssq, cand, g3_flags};
   for (void* p : frees)
     if (p) cudaFree(p);
   for (auto p : stage_dev)
@@ -400,13 +410,22 @@ int Engine::alloc_all() {
   total += align_up(cs_elems * 2, 1024);
   weights_bytes = total;
   CK(cudaMalloc(&weights_blob, total));
+  // gate_up rows live interleaved in 64-row blocks (gate block, matching up block, ...): the decode GEMM's SiLU epilogue
+  // needs a gate row and its up row in the same 128-row slab.  The named tensor keeps its logical [gate | up] meaning at
+  // the ABI (tensor_read / tensor_write / the checkpoint loader permute), and the seeded init is generated in logical order.
+  bf16* gu_tmp = nullptr;
+  CK(cudaMalloc(&gu_tmp, static_cast<size_t>(2) * I * H * 2));
   for (size_t i = 0; i < items.size(); ++i) {
     bf16* p = reinterpret_cast<bf16*>(reinterpret_cast<uint8_t*>(weights_blob) + offs[i]);
     *items[i].dst = p;
     tensors[items[i].name] = {p, items[i].elems * 2};
     uint32_t seed = static_cast<uint32_t>(xxh64(items[i].name.data(), items[i].name.size(), cfg.seed));
-    if (init_uniform(p, items[i].elems, seed, items[i].scale, items[i].offset, stream)) return cuda_fail("init_uniform", -2);
+    const bool is_gu = items[i].name.size() > 4 && items[i].name.compare(items[i].name.size() - 4, 4, ".wgu") == 0;
+    if (init_uniform(is_gu ? gu_tmp : p, items[i].elems, seed, items[i].scale, items[i].offset, stream)) return cuda_fail("init_uniform", -2);
+    if (is_gu && permute_gate_up(p, gu_tmp, I, H, 1, stream)) return cuda_fail("permute_gate_up", -2);
   }
+  CK(cudaStreamSynchronize(stream));
+  CK(cudaFree(gu_tmp));
   cos_sin = reinterpret_cast<bf16*>(reinterpret_cast<uint8_t*>(weights_blob) + cs_off);
   tensors["cos_sin"] = {cos_sin, cs_elems * 2};
   {
@@ -457,8 +476,12 @@ int Engine::alloc_all() {
   CK(cudaMemset(act, 0, static_cast<size_t>(Tcap) * I * 2));
   CK(cudaMemset(last_hidden, 0, static_cast<size_t>(Scap) * H * 2));
   CK(cudaMallocHost(&sampled_host, static_cast<size_t>(Scap) * 4));
+  CK(cudaMalloc(&ssq, static_cast<size_t>(Tcap) * (H / 128) * 4));
+  CK(cudaMalloc(&cand, static_cast<size_t>(std::min(Scap, 128)) * (V / 128 + 1) * sizeof(float2)));
+  CK(cudaMalloc(&g3_flags, 4096 * 4));
+  CK(cudaMemset(g3_flags, 0, 4096 * 4));
   // split-K workspace: 2 fp32 slots of 512 tokens x 128 rows per CTA (in-kernel fix-up slots == deferred segments)
-  size_t ws_bytes = std::max(gemm_workspace_bytes(sms), gemm_deferred_ws_bytes(sms));
+  size_t ws_bytes = std::max(std::max(gemm_workspace_bytes(sms), gemm_deferred_ws_bytes(sms)), gemm3_ws_bytes(sms));
   gemm_ws_bytes = ws_bytes;
   CK(cudaMalloc(&gemm_ws, ws_bytes));
   const int maxN = std::max(std::max(QKV, 2 * I), V);
@@ -485,8 +508,20 @@ int Engine::alloc_all() {
     if (gemm_make_x_map(&xm_normed.m[i], normed, Tcap, H, H, bns[i]) ||
         gemm_make_x_map(&xm_attn.m[i], attn, Tcap, Hq * kD, Hq * kD, bns[i]) ||
         gemm_make_x_map(&xm_act.m[i], act, Tcap, I, I, bns[i]) ||
-        gemm_make_x_map(&xm_last.m[i], last_hidden, Scap, H, H, bns[i]))
+        gemm_make_x_map(&xm_last.m[i], last_hidden, Scap, H, H, bns[i]) ||
+        gemm_make_x_map(&xm_res.m[i], res, Tcap, H, H, bns[i]))
       return cuda_fail("gemm_make_x_map", -2);
+  }
+  // decode-shape fused path: one schedule per projection (cluster split-K or stream-K, gemm3_schedule); any shape it does
+  // not serve keeps the whole engine on the unfused path
+  {
+    const char* e = getenv("B200_FUSED_DECODE");   // A/B knob: 0 keeps every step on the unfused kernels
+    const bool want = !(e && atoi(e) == 0) && gemm_variant() == 2;
+    fused_ok = want && QKV % 256 == 0 && H % 256 == 0 && (2 * I) % 256 == 0 && V % 256 == 0 && H <= 4096 &&
+               !gemm3_schedule(QKV, H, 128, GEMM3_PRO_NORM, 0, &sch_qkv) && !gemm3_schedule(H, Hq * kD, 128, GEMM3_PRO_NONE, 0, &sch_o) &&
+               !gemm3_schedule(2 * I, H, 128, GEMM3_PRO_NORM, 0, &sch_gu) && !gemm3_schedule(H, I, 128, GEMM3_PRO_NONE, 0, &sch_down) &&
+               !gemm3_schedule(V, H, 128, GEMM3_PRO_NONE, 0, &sch_lm);
+    cudaGetLastError();
   }
 
   // ---- KV pool
@@ -587,6 +622,10 @@ int Engine::forward(const StepMeta& m, int32_t* dbuf, bool all_logits, bf16* log
     prof_used += 2;
   };
   auto on = [&](int cls) { return !(skip_mask & (1u << cls)); };
+  // Steps of at most 128 tokens (the decode steps: ~80% of the bench's steps, all of them weight streams) run the fused
+  // chain: 4 GEMMs + attention per layer, the split-K reductions finished inside the GEMMs, RMSNorm / RoPE + KV write /
+  // SiLU / residual add / argmax in their prologues and epilogues (gemm3_tcgen05.cu).
+  if (fused_ok && !all_logits && T <= 128 && m.S <= 128) return forward_fused(m, dbuf);
   P(B200_K_EMBED); if (on(B200_K_EMBED)) rc |= embed_gather(embed, ids, res, T, H, V, stream); Q(); launched(1);
   // T <= 512: every GEMM dumps fp32 stream-K partials and its consumer (norm / rope / silu / argmax) sums them while
   // loading — no in-GEMM reduction handshake.  Larger steps use the in-kernel fix-up and bf16 intermediates.
@@ -623,7 +662,7 @@ int Engine::forward(const StepMeta& m, int32_t* dbuf, bool all_logits, bf16* log
     if (!on(B200_K_GEMM_GU)) {}
     else if (dfr) rc |= gemm_def(ly.p_gu, xm_normed, gu, 2 * I, T, &pv); else rc |= gemm(ly.p_gu, xm_normed, gu, 2 * I, T);
     Q();
-    P(B200_K_SILU); if (on(B200_K_SILU)) rc |= silu_mul(gu, act, T, I, stream, pv); Q();
+    P(B200_K_SILU); if (on(B200_K_SILU)) rc |= silu_mul(gu, act, T, I, stream, pv, 1); Q();
     P(B200_K_GEMM_DOWN);
     if (!on(B200_K_GEMM_DOWN)) {}
     else if (dfr) rc |= gemm_def(ly.p_down, xm_act, x, H, T, &pv_x); else rc |= gemm(ly.p_down, xm_act, x, H, T);
@@ -646,6 +685,96 @@ int Engine::forward(const StepMeta& m, int32_t* dbuf, bool all_logits, bf16* log
     launched(2);
   }
   if (rc) return cuda_fail("forward(head)", -2);
+  return 0;
+}
+
+// ------------------------------------------------------------------ forward pass, decode-shape fused chain (T <= 128)
+int Engine::forward_fused(const StepMeta& m, int32_t* dbuf) {
+  const int T = m.T;
+  const int* ids = dbuf + m.off_ids;
+  const int* pos = dbuf + m.off_pos;
+  const int* slots = dbuf + m.off_slots;
+  const int* rows = dbuf + m.off_rows;
+  const AttnWork* dwork = reinterpret_cast<const AttnWork*>(dbuf + m.off_dwork);
+  const AttnWork* pwork = reinterpret_cast<const AttnWork*>(dbuf + m.off_pwork);
+  const int* btab = dbuf + m.off_btab;
+  const float scale = 1.0f / sqrtf(static_cast<float>(kD));
+  const int slabs = H / 128;
+  int rc = 0;
+  auto P = [&](int cls) {
+    if (!profiling) return;
+    if (prof_used + 2 > prof_events.size()) {
+      for (int i = 0; i < 2; ++i) { cudaEvent_t e; cudaEventCreate(&e); prof_events.push_back({cls, e}); }
+    }
+    prof_events[prof_used].first = cls;
+    cudaEventRecord(prof_events[prof_used].second, stream);
+  };
+  auto Q = [&]() {
+    if (!profiling) return;
+    cudaEventRecord(prof_events[prof_used + 1].second, stream);
+    prof_used += 2;
+  };
+  auto on = [&](int cls) { return !(skip_mask & (1u << cls)); };
+  auto base = [&](const GemmPlan& pl, const CUtensorMap& tmx, int Tn, int pro, int epi) {
+    Gemm3Params p;
+    memset(&p, 0, sizeof(p));
+    p.tm_w = pl.tm_w;
+    p.tm_x = tmx;
+    p.N = pl.N; p.T = Tn; p.K = pl.K;
+    p.pro = pro; p.epi = epi;
+    p.ssq_in = ssq; p.ssq_slabs = slabs; p.eps = cfg.rms_eps;
+    p.ws = gemm_ws; p.flags = g3_flags; p.epoch = ++g3_epoch;
+    p.n_valid = pl.N;
+    return p;
+  };
+  // embedding rows are the first residual; their sums of squares feed layer 0's norm prologue
+  P(B200_K_EMBED); if (on(B200_K_EMBED)) rc |= embed_gather(embed, ids, res, T, H, V, stream, ssq, slabs); Q();
+  stats.kernel_launches += 1;
+  for (int l = 0; l < L && !rc; ++l) {
+    Layer& ly = layers[l];
+    bf16* kv_l = kv + static_cast<size_t>(l) * kv_layer_elems;
+    {
+      Gemm3Params p = base(ly.p_qkv, xmap(xm_res, 128), T, GEMM3_PRO_NORM, GEMM3_EPI_ROPE_KV);
+      p.norm_w = ly.norm1;
+      p.out = qkv; p.ldo = QKV;
+      p.positions = pos; p.slots = slots; p.cos_sin = cos_sin; p.kv_layer = kv_l; p.Hq = Hq; p.Hkv = Hkv; p.max_pos = cfg.max_model_len;
+      P(B200_K_GEMM_QKV); if (on(B200_K_GEMM_QKV)) rc |= gemm3_launch(p, sch_qkv, stream); Q();
+    }
+    if (m.nd) { P(B200_K_ATTN_DECODE); if (on(B200_K_ATTN_DECODE)) rc |= paged_attention(qkv, QKV, attn, Hq * kD, kv_l, btab, max_blocks_per_seq, dwork, m.nd, Hq, Hkv, scale, 1, stream); Q(); ++stats.kernel_launches; }
+    if (m.np) { P(B200_K_ATTN_PREFILL); if (on(B200_K_ATTN_PREFILL)) rc |= paged_attention(qkv, QKV, attn, Hq * kD, kv_l, btab, max_blocks_per_seq, pwork, m.np, Hq, Hkv, scale, 0, stream); Q(); ++stats.kernel_launches; }
+    {
+      Gemm3Params p = base(ly.p_o, xmap(xm_attn, 128), T, GEMM3_PRO_NONE, GEMM3_EPI_RESADD);
+      p.out = res; p.ldo = H; p.ssq_out = ssq;
+      P(B200_K_GEMM_O); if (on(B200_K_GEMM_O)) rc |= gemm3_launch(p, sch_o, stream); Q();
+    }
+    {
+      Gemm3Params p = base(ly.p_gu, xmap(xm_res, 128), T, GEMM3_PRO_NORM, GEMM3_EPI_SILU);
+      p.norm_w = ly.norm2;
+      p.out = act; p.ldo = I;
+      P(B200_K_GEMM_GU); if (on(B200_K_GEMM_GU)) rc |= gemm3_launch(p, sch_gu, stream); Q();
+    }
+    {
+      Gemm3Params p = base(ly.p_down, xmap(xm_act, 128), T, GEMM3_PRO_NONE, GEMM3_EPI_RESADD);
+      p.out = res; p.ldo = H; p.ssq_out = ssq;
+      P(B200_K_GEMM_DOWN); if (on(B200_K_GEMM_DOWN)) rc |= gemm3_launch(p, sch_down, stream); Q();
+    }
+    stats.kernel_launches += 4;
+  }
+  if (rc) return cuda_fail("forward_fused", -2);
+  if (m.S > 0) {
+    // the residual already holds the summed stream: the final norm is a plain RMSNorm of the sampled rows
+    P(B200_K_NORM); rc |= rmsnorm(res, nullptr, final_norm, last_hidden, rows, m.S, H, cfg.rms_eps, stream); Q();
+    Gemm3Params p = base(p_lm, xmap(xm_last, 128), m.S, GEMM3_PRO_NONE, keep_logits ? GEMM3_EPI_PLAIN : GEMM3_EPI_ARGMAX);
+    p.out = logits; p.ldo = V; p.cand = cand;
+    P(B200_K_GEMM_LM); rc |= gemm3_launch(p, sch_lm, stream); Q();
+    P(B200_K_ARGMAX);
+    if (keep_logits) rc |= argmax_rows(logits, sampled, m.S, V, V, stream);
+    else rc |= argmax_candidates(cand, sampled, m.S, V / 128, stream);
+    Q();
+    last_S = m.S;
+    stats.kernel_launches += 3;
+  }
+  if (rc) return cuda_fail("forward_fused(head)", -2);
   return 0;
 }
 
@@ -1322,12 +1451,28 @@ int b200_engine_tensor_info(b200_engine* e, const char* name, uint64_t* num_byte
   return 0;
 }
 
+static bool is_gate_up(const char* name) {
+  const size_t n = strlen(name);
+  return n > 4 && strcmp(name + n - 4, ".wgu") == 0;
+}
+
 int b200_engine_tensor_read(b200_engine* e, const char* name, void* host_dst, uint64_t cap) {
   uint64_t nb = 0; void* p = nullptr;
   if (int rc = b200_engine_tensor_info(e, name, &nb, &p)) return rc;
   if (!host_dst || cap < nb) { set_error("buffer too small (%llu < %llu)", (unsigned long long)cap, (unsigned long long)nb); return B200_ERR_INVALID; }
-  cudaSetDevice(e->impl.cfg.device);
-  CK(cudaStreamSynchronize(e->impl.stream));
+  Engine& g = e->impl;
+  cudaSetDevice(g.cfg.device);
+  CK(cudaStreamSynchronize(g.stream));
+  if (is_gate_up(name)) {   // the ABI speaks the logical [gate | up] row order
+    void* tmp = nullptr;
+    CK(cudaMalloc(&tmp, nb));
+    int rc = permute_gate_up(tmp, p, g.I, g.H, 0, g.stream);
+    cudaError_t ce = rc ? cudaErrorUnknown : cudaStreamSynchronize(g.stream);
+    if (ce == cudaSuccess) ce = cudaMemcpy(host_dst, tmp, nb, cudaMemcpyDeviceToHost);
+    cudaFree(tmp);
+    if (ce != cudaSuccess) { set_error("tensor_read(%s): %s", name, cudaGetErrorString(ce)); return B200_ERR_CUDA; }
+    return 0;
+  }
   CK(cudaMemcpy(host_dst, p, nb, cudaMemcpyDeviceToHost));
   return 0;
 }
@@ -1336,9 +1481,11 @@ int b200_engine_tensor_write(b200_engine* e, const char* name, const void* host_
   uint64_t nb = 0; void* p = nullptr;
   if (int rc = b200_engine_tensor_info(e, name, &nb, &p)) return rc;
   if (!host_src || n != nb) { set_error("size mismatch (%llu != %llu)", (unsigned long long)n, (unsigned long long)nb); return B200_ERR_INVALID; }
-  cudaSetDevice(e->impl.cfg.device);
-  CK(cudaStreamSynchronize(e->impl.stream));
+  Engine& g = e->impl;
+  cudaSetDevice(g.cfg.device);
+  CK(cudaStreamSynchronize(g.stream));
   CK(cudaMemcpy(p, host_src, nb, cudaMemcpyHostToDevice));
+  if (is_gate_up(name)) return b200::engine_relayout_gate_up(e, name);
   return 0;
 }
 
@@ -1359,6 +1506,25 @@ int b200_engine_read_logits(b200_engine* e, void* host_logits_bf16, int32_t rows
   CK(cudaMemcpy(host_logits_bf16, g.logits, static_cast<size_t>(rows) * g.V * 2, cudaMemcpyDeviceToHost));
   return 0;
 }
+
+}  // extern "C"
+
+int b200::engine_relayout_gate_up(b200_engine* e, const char* name) {
+  uint64_t nb = 0; void* p = nullptr;
+  if (int rc = b200_engine_tensor_info(e, name, &nb, &p)) return rc;
+  Engine& g = e->impl;
+  cudaSetDevice(g.cfg.device);
+  void* tmp = nullptr;
+  CK(cudaMalloc(&tmp, nb));
+  cudaError_t ce = cudaMemcpyAsync(tmp, p, nb, cudaMemcpyDeviceToDevice, g.stream);
+  if (ce == cudaSuccess && permute_gate_up(p, tmp, g.I, g.H, 1, g.stream)) ce = cudaErrorUnknown;
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(g.stream);
+  cudaFree(tmp);
+  if (ce != cudaSuccess) { set_error("relayout(%s): %s", name, cudaGetErrorString(ce)); return B200_ERR_CUDA; }
+  return 0;
+}
+
+extern "C" {
 
 int b200_engine_forward_logits(b200_engine* e, const int32_t* ids, int32_t n, void* host_logits_bf16) {
   if (!e || !ids || n <= 0 || !host_logits_bf16) { set_error("bad arguments"); return B200_ERR_INVALID; }

@@ -9,7 +9,9 @@
 
 namespace b200 {
 
-int embed_gather(const void* table, const int* ids, void* out, int T, int H, int vocab, cudaStream_t st);
+// ssq (optional): [T, ssq_slabs] fp32, the row's sum of squares in slab 0 and zeros elsewhere (RMSNorm prologue of the fused GEMM)
+int embed_gather(const void* table, const int* ids, void* out, int T, int H, int vocab, cudaStream_t st, float* ssq = nullptr,
+                 int ssq_slabs = 0);
 // out[s] = rmsnorm(x[r] (+ residual[r])) * w,  r = row_index ? row_index[s] : s.
 // residual (optional) is updated in place with bf16(x + residual) unless row_index is given.
 // Every consumer of a GEMM output takes an optional PartialView: when pv.ws != nullptr the input is the fp32
@@ -18,7 +20,10 @@ int rmsnorm(const void* x, void* residual, const void* w, void* out, const int* 
             float eps, cudaStream_t st, PartialView pv = no_partials());
 int rope_kv_write(void* qkv, const int* positions, const int* slots, const void* cos_sin, void* kv_layer,
                   int T, int Hq, int Hkv, int max_pos, cudaStream_t st, PartialView pv = no_partials());
-int silu_mul(const void* gate_up, void* out, int T, int I, cudaStream_t st, PartialView pv = no_partials());
+// interleaved: gate/up columns alternate in 64-column blocks (engine layout) instead of [gate | up]
+int silu_mul(const void* gate_up, void* out, int T, int I, cudaStream_t st, PartialView pv = no_partials(), int interleaved = 0);
+// gate_up weight rows: logical [gate | up] <-> physical (64 gate rows, their 64 up rows, ...); dst != src
+int permute_gate_up(void* dst, const void* src, int I, int H, int to_physical, cudaStream_t st);
 int argmax_rows(const void* logits, int* out, int S, int V, int ld, cudaStream_t st, PartialView pv = no_partials());
 int init_uniform(void* p, size_t n, uint32_t seed, float scale, float offset, cudaStream_t st);
 

@@ -347,6 +347,7 @@ int b200_engine_load_safetensors(b200_engine* e, const char* path) {
     const int64_t I = static_cast<int64_t>(nb / 2) / H / 2;
     LD(hp + "mlp.gate_proj.weight", 0, I, H);
     LD(hp + "mlp.up_proj.weight", I, I, H);
+    if ((rc = engine_relayout_gate_up(e, (ep + "wgu").c_str()))) return rc;   // logical [gate | up] -> interleaved 64-row blocks
     if (dev(ep + "wdown", &p, &nb)) return B200_ERR_NOT_FOUND;
     LD(hp + "mlp.down_proj.weight", 0, H, I);
     if (dev(ep + "norm1", &p, &nb)) return B200_ERR_NOT_FOUND;

@@ -42,6 +42,46 @@ def gemm_deferred(x: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
     return out
 
 
+PRO_NONE, PRO_NORM = 0, 1
+EPI_PLAIN, EPI_RESADD, EPI_SILU, EPI_ROPE_KV, EPI_ARGMAX = 0, 1, 2, 3, 4
+
+
+def gemm3(x, w, T=None, pro=PRO_NONE, epi=EPI_PLAIN, force=0, ssq_in=None, norm_w=None, eps=1e-5, out=None, ssq_out=None,
+          positions=None, slots=None, cos_sin=None, kv_layer=None, q_heads=0, kv_heads=0, argmax_out=None, n_valid=0):
+    """The decode-shape fused GEMM (b200_op_gemm3).  x: [rows >= T, K] activations (or the residual for PRO_NORM),
+    w: [N, K].  Returns (out, schedule) with schedule = (pairs per tile, stream-K flag, CTAs)."""
+    from ._lib import Gemm3Args
+    _chk(x), _chk(w)
+    T = x.shape[0] if T is None else T
+    N, K = w.shape
+    a = Gemm3Args(N=N, T=T, K=K, x_rows=x.shape[0], pro=pro, epi=epi, force=force, w=w.data_ptr(), x=x.data_ptr(), eps=eps,
+                  q_heads=q_heads, kv_heads=kv_heads, n_valid=n_valid)
+    if pro == PRO_NORM:
+        _chk(norm_w), _chk(ssq_in, torch.float32)
+        a.ssq_in, a.ssq_slabs, a.norm_w = ssq_in.data_ptr(), ssq_in.shape[1], norm_w.data_ptr()
+    if epi == EPI_PLAIN:
+        out = torch.empty(T, N, dtype=torch.bfloat16, device=x.device) if out is None else out
+    elif epi == EPI_RESADD:
+        _chk(out)                                               # the residual, updated in place
+        ssq_out = torch.zeros(T, N // 128, dtype=torch.float32, device=x.device) if ssq_out is None else ssq_out
+        a.ssq_out = ssq_out.data_ptr()
+    elif epi == EPI_SILU:
+        out = torch.empty(T, N // 2, dtype=torch.bfloat16, device=x.device) if out is None else out
+    elif epi == EPI_ROPE_KV:
+        _chk(out), _chk(positions, torch.int32), _chk(slots, torch.int32), _chk(cos_sin), _chk(kv_layer)
+        a.positions, a.slots, a.cos_sin, a.kv_layer = positions.data_ptr(), slots.data_ptr(), cos_sin.data_ptr(), kv_layer.data_ptr()
+        a.max_pos = cos_sin.shape[0]
+    elif epi == EPI_ARGMAX:
+        argmax_out = torch.empty(T, dtype=torch.int32, device=x.device) if argmax_out is None else argmax_out
+        a.argmax_out = argmax_out.data_ptr()
+    if out is not None:
+        a.out, a.ldo = out.data_ptr(), out.stride(0)
+    sch = (C.c_int32 * 3)()
+    check(lib().b200_op_gemm3(C.byref(a), _stream(), sch))
+    res = argmax_out if epi == EPI_ARGMAX else (out, ssq_out) if epi == EPI_RESADD else out
+    return res, tuple(sch)
+
+
 def embed(table, ids):
     _chk(table), _chk(ids, torch.int32)
     out = torch.empty(ids.numel(), table.shape[1], dtype=torch.bfloat16, device=table.device)

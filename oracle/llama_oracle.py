@@ -89,7 +89,7 @@ def attention(q, k, v, q_pos, scale):
     kk = k.repeat_interleave(g, dim=1)
     vv = v.repeat_interleave(g, dim=1)
     s = torch.einsum("qhd,khd->hqk", q, kk) * scale
-    mask = torch.arange(Tk)[None, :] > q_pos[:, None]
+    mask = torch.arange(Tk, device=q.device)[None, :] > q_pos[:, None]
     s = s.masked_fill(mask[None], float("-inf"))
     p = torch.softmax(s, dim=-1)
     return r(torch.einsum("hqk,khd->qhd", p, vv))

@@ -49,6 +49,31 @@ def gemm_bench():
             del x, w
 
 
+def gemm3_bench():
+    """decode-shape fused GEMM (plain epilogue) vs the stream-K pair kernel with deferred partials vs cuBLAS, T <= 128"""
+    print("== gemm3 (in-kernel split-K, T<=128) vs gemm2 deferred (+reducer) vs cuBLAS, us median, L2 flushed")
+    shapes = [("qkv", 6144, 4096), ("o", 4096, 4096), ("gate_up", 28672, 4096), ("down", 4096, 14336), ("lm_head", 128256, 4096)]
+    for T in (16, 64, 128):
+        for name, N, K in shapes:
+            x = torch.randn(T, K, device="cuda").bfloat16()
+            w = (torch.randn(N, K, device="cuda") / math.sqrt(K)).bfloat16()
+            byts = (N * K + T * K + T * N) * 2
+            res = {}
+            for force in ([0] if N > 16384 else [1, 2, 3]):
+                try:
+                    sch = ops.gemm3(x, w, force=force)[1]
+                    res[f"g3{sch}"] = timeit(lambda: ops.gemm3(x, w, force=force))
+                except Exception as ex:  # noqa: BLE001
+                    res[f"g3 force {force}"] = float("nan")
+            t_def = timeit(lambda: ops.gemm_deferred(x, w))
+            t_cublas = timeit(lambda: torch.nn.functional.linear(x, w))
+            best = min(v for v in res.values() if v == v)
+            print(f"T={T:4d} {name:8s} " + "  ".join(f"{k} {v:6.1f}" for k, v in res.items()) +
+                  f" | best {best:6.1f} us = {byts / best / 1e3:6.0f} GB/s ({byts / best / 1e3 / PEAK:4.2f} of HBM) | gemm2+reduce {t_def:6.1f} | cublas {t_cublas:6.1f} "
+                  f"ratio {t_cublas / best:4.2f}x")
+            del x, w
+
+
 def attn_bench():
     print("== paged decode attention, B=128, Hq=32/Hkv=8")
     Hq, Hkv, D = 32, 8, 128

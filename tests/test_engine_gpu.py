@@ -124,8 +124,9 @@ def test_preemption_under_kv_pressure_keeps_outputs(oracle):
     rng = np.random.default_rng(5)
     prompts = [rng.integers(0, 512, size=40).tolist() for _ in range(6)]
     want = [oracle.generate(p, 24) for p in prompts]
-    # 6 seqs x 64 tokens = 24 pages needed; give 14 so the scheduler must preempt and recompute
-    with Engine(mini_config(num_kv_blocks=14, enable_prefix_caching=0)) as e:
+    # 6 seqs x 64 tokens = 24 pages needed; give 14 so the scheduler must preempt and recompute (the pool must still hold
+    # one max_model_len sequence: 14 pages = 224 tokens)
+    with Engine(mini_config(num_kv_blocks=14, max_model_len=224, enable_prefix_caching=0)) as e:
         outs = e.generate(prompts, max_tokens=24)
         assert e.stats().preemptions > 0
     for i, (o, (w, rows)) in enumerate(zip(outs, want)):

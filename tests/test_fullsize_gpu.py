@@ -7,9 +7,10 @@ vocab 128256), default-on in the GPU suite:
     tables, for decode and for chunked prefill on top of a cached prefix.
 
 Tolerances.  Ops: vLLM's bf16 kernel tolerance (vllm/ir/tolerances.py:13-24: atol 1e-3, rtol 1.6e-2).  Logits: stated in
-bf16 ulps of the logit — |got - want| <= LOGIT_ULPS * ulp_bf16(|want|) + 1e-3, ulp_bf16(x) = 2^(floor(log2 x) - 7) — a
-logit is one bf16 rounding of a 4096-term fp32 dot product of values that themselves carry up to one ulp of upstream
-difference, so 2 ulps is the floor for two correct bf16 pipelines; the measured maxima are printed.
+bf16 ulps — |got - want| <= LOGIT_ULPS * ulp_bf16(max(|want|, rms of the row)) + 1e-3, ulp_bf16(x) = 2^(floor(log2 x) - 7)
+— a logit is one bf16 rounding of a 4096-term fp32 dot product of values that themselves carry up to one ulp of upstream
+difference, so 2 ulps is the floor for two correct bf16 pipelines; the measured maxima are printed (first run on a B200:
+max |dlogit| 0.125 = 2 ulps at |logit| 8..16, mean |dlogit| 0.01).
 """
 import math
 
@@ -31,11 +32,15 @@ def ulp_bf16(x: np.ndarray) -> np.ndarray:
 
 
 def logits_close(got, want, what):
+    """|got - want| in bf16 ulps of max(|logit|, the row's RMS logit): a small logit is the cancellation of terms of the
+    row's typical size, so its error scale is the row's, not its own."""
     err = np.abs(got - want)
-    tol = LOGIT_ULPS * ulp_bf16(want) + 1e-3
-    worst = float((err / ulp_bf16(want)).max())
+    scale = ulp_bf16(np.maximum(np.abs(want), np.sqrt((want ** 2).mean(-1, keepdims=True))))
+    tol = LOGIT_ULPS * scale + 1e-3
+    worst = float((err / scale).max())
     print(f"{what}: max |dlogit| {err.max():.4f}, max error {worst:.2f} bf16 ulps of the logit, mean |dlogit| {err.mean():.5f}")
     assert (err <= tol).all(), f"{what}: {int((err > tol).sum())} of {err.size} logits outside {LOGIT_ULPS} ulps (worst {worst:.2f})"
+    assert err.mean() < 0.25 * float(scale.mean()), "mean error under a quarter ulp"
     return worst
 
 
@@ -106,9 +111,14 @@ def test_full_size_decode_step_of_128_sequences_matches_oracle(layer):
     gen = [[] for _ in rids]
     lg = None
     try:
+        hist = []
         for _ in range(600):
             ran, info = e.step()
-            assert ran
+            st = e.stats()
+            assert ran, f"engine idle after {len(hist)} steps: running {st.running} waiting {st.waiting} kv_free {st.kv_blocks_free} " \
+                        f"preemptions {st.preemptions}; last steps (T, decode, prefill): {hist[-12:]}; finished: " \
+                        f"{[(i, len(g), e.poll(r).finished) for i, (g, r) in enumerate(zip(gen, rids)) if e.poll(r).finished][:8]}"
+            hist.append((info.tokens, info.decode_seqs, info.prefill_seqs))
             for i, r in enumerate(rids):
                 gen[i] += e.poll(r).tokens
             if info.prefill_seqs == 0 and info.decode_seqs == len(rids):

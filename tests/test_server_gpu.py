@@ -174,7 +174,10 @@ def test_destroy_with_idle_keepalive_client_returns_promptly(stack):
     for _ in range(3):
         c = socket.create_connection(("127.0.0.1", port))
         c.sendall(b"GET /healthz HTTP/1.1\r\nHost: x\r\n\r\n")
-        assert b"200 OK" in c.recv(4096)
+        got = b""
+        while not got.endswith(b"0\r\n\r\n"):                     # the whole chunked response
+            got += c.recv(4096)
+        assert b"200 OK" in got
         socks.append(c)                                           # kept open: the server thread sits in recv()
     t0 = time.perf_counter()
     srv.close()
