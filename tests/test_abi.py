@@ -74,3 +74,22 @@ def test_product_package_never_imports_the_oracle():
         assert not re.search(r"^\s*(from|import)\s+oracle\b", p.read_text(), flags=re.M), p
     for p in (ROOT / "kubeai_b200" / "csrc").glob("*"):
         assert "oracle/" not in p.read_text(errors="ignore"), p
+
+
+def test_go_shim_calls_only_declared_and_exported_functions():
+    """shim/engine.go (the cgo binding a KubeAI maintainer adds; no Go toolchain here) must bind real entry points."""
+    go = (ROOT / "shim" / "engine.go").read_text()
+    used = set(re.findall(r"C\.(b200_[a-z0-9_]+)\(", go))
+    assert {"b200_engine_create", "b200_submit", "b200_poll", "b200_wait", "b200_abort", "b200_server_create",
+            "b200_server_handle", "b200_engine_is_failed"} <= used
+    header = (ROOT / "include" / "b200engine.h").read_text()
+    from kubeai_b200 import _lib
+    l = _lib.lib()
+    for fn in used:
+        assert re.search(r"\b%s\s*\(" % fn, header), f"{fn} is not declared in include/b200engine.h"
+        assert hasattr(l, fn), f"{fn} is not exported by libb200engine.so"
+    for imp in ("errors", "io", "net/http", "runtime/cgo", "unsafe"):
+        assert f'"{imp}"' in go, f"import {imp} missing"
+    # struct fields the shim sets exist in the header
+    for field in ("max_tokens", "ignore_eos", "mean_load_pct", "prefix_char_length", "default_max_tokens"):
+        assert field in header
