@@ -10,6 +10,7 @@
 // sequence on one CUDA stream, greedy sampling, thread-safe submit/poll/wait/abort.
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -997,9 +998,15 @@ int Engine::launch(InFlight* f, StepMeta* mp) {
   ring_meta[slot] = m;
   int32_t* dbuf = stage_dev[slot];
   f->t_packed = timing ? now_s() : 0.0;
+  // NVTX range per step: visible in nsys / ncu --nvtx timelines as "step T=<tokens> dec=<n> pre=<n>"
+  char nv[64];
+  snprintf(nv, sizeof(nv), "step T=%d dec=%d pre=%d", m.T, f->ndec_seq, f->npre_seq);
+  nvtxRangePushA(nv);
   CK(cudaMemcpyAsync(dbuf, h, static_cast<size_t>(w) * 4, cudaMemcpyHostToDevice, stream));
   CK(cudaEventRecord(ev0, stream));
-  if (int rc = forward(m, dbuf, false, nullptr)) return rc;
+  const int frc = forward(m, dbuf, false, nullptr);
+  nvtxRangePop();
+  if (frc) return frc;
   CK(cudaEventRecord(ev1, stream));
   if (m.S) CK(cudaMemcpyAsync(sampled_host, sampled, static_cast<size_t>(m.S) * 4, cudaMemcpyDeviceToHost, stream));
   f->t_launched = timing ? now_s() : 0.0;
