@@ -22,6 +22,7 @@ SOURCES = [
     "gemm2_tcgen05.cu",
     "gemm3_tcgen05.cu",
     "attention.cu",
+    "attention_tc.cu",
     "elementwise.cu",
     "abi_ops.cu",
     "engine.cu",

@@ -228,6 +228,16 @@ int b200_op_paged_attn(const void* q, int32_t ldq, void* out, int32_t ldo, const
   return rc ? cuda_fail("paged_attention", rc) : 0;
 }
 
+int b200_op_paged_attn_prefill_tc(const void* qkv, int32_t q_rows, int32_t ldq, void* out, int32_t ldo, const void* kv_layer,
+                                  const int32_t* block_tables, int32_t max_blocks, const int32_t* work, int32_t num_work,
+                                  int32_t q_heads, int32_t kv_heads, float scale, void* stream) {
+  if (int rc = require_device()) return rc;
+  int rc = paged_attention_prefill_tc(qkv, q_rows, ldq, out, ldo, kv_layer, block_tables, max_blocks,
+                                      reinterpret_cast<const AttnWork*>(work), num_work, q_heads, kv_heads, scale,
+                                      static_cast<cudaStream_t>(stream));
+  return rc ? cuda_fail("paged_attention_prefill_tc", rc) : 0;
+}
+
 int b200_op_init_uniform(void* p, uint64_t n, uint32_t seed, float scale, float offset, void* stream) {
   if (int rc = require_device()) return rc;
   int rc = init_uniform(p, n, seed, scale, offset, static_cast<cudaStream_t>(stream));

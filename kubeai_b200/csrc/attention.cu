@@ -309,6 +309,8 @@ int decode_stages() {  // B200_ATTN_STAGES=2|3|4 (tiles in flight per decode CTA
 // One tensor map per KV-layer base pointer: the layer is viewed as [rows][128] bf16 with 256-byte rows, gathered in
 // boxes of 16 rows x 64 columns (one page-head half).  The row count is an upper bound, not the allocation size: the
 // kernel only ever addresses pages named by the block table.
+}  // namespace
+
 int kv_map_for(const void* kv_layer, CUtensorMap* out) {
   static std::unordered_map<const void*, CUtensorMap> cache;
   static std::mutex mu;
@@ -325,6 +327,8 @@ int kv_map_for(const void* kv_layer, CUtensorMap* out) {
   return 0;
 }
 
+namespace {
+
 template <bool DECODE, int S>
 int launch_attn(const CUtensorMap& tm, dim3 grid, cudaStream_t st, const __nv_bfloat16* q, int ldq, __nv_bfloat16* out,
                 int ldo, const int* block_tables, int max_blocks, const AttnWork* work, int Hkv, float scale_log2) {
@@ -336,6 +340,14 @@ int launch_attn(const CUtensorMap& tm, dim3 grid, cudaStream_t st, const __nv_bf
 }
 
 }  // namespace
+
+int prefill_attn_query_block() {
+  static const int v = [] {
+    const char* e = getenv("B200_ATTN_TC");
+    return (e && atoi(e) == 0) ? 16 : 64;
+  }();
+  return v;
+}
 
 int paged_attention(const void* q, int ldq, void* out, int ldo, const void* kv_layer, const int* block_tables,
                     int max_blocks, const AttnWork* work, int num_work, int Hq, int Hkv, float scale,

@@ -299,6 +299,11 @@ struct Engine {
   int alloc_all();
   int forward(const StepMeta& m, int32_t* dbuf, bool all_logits, bf16* logits_out);
   int forward_fused(const StepMeta& m, int32_t* dbuf);
+  int prefill_attention(bf16* kv_l, const int* btab, const AttnWork* pwork, int np, float scale) {
+    if (prefill_attn_query_block() == 64)
+      return paged_attention_prefill_tc(qkv, Tcap, QKV, attn, Hq * kD, kv_l, btab, max_blocks_per_seq, pwork, np, Hq, Hkv, scale, stream);
+    return paged_attention(qkv, QKV, attn, Hq * kD, kv_l, btab, max_blocks_per_seq, pwork, np, Hq, Hkv, scale, 0, stream);
+  }
   // one scheduler iteration = launch (schedule, pack, H2D, kernels, D2H enqueue) + complete (sync, apply) + publish
   int launch(InFlight* f, StepMeta* m);
   int complete(InFlight& f, const StepMeta& m, b200_step_info* info);
@@ -652,7 +657,7 @@ int Engine::forward(const StepMeta& m, int32_t* dbuf, bool all_logits, bf16* log
     P(B200_K_ROPE); if (on(B200_K_ROPE)) rc |= rope_kv_write(qkv, pos, slots, cos_sin, kv_l, T, Hq, Hkv, cfg.max_model_len, stream, pv); Q();
     launched(2);
     if (m.nd) { P(B200_K_ATTN_DECODE); if (on(B200_K_ATTN_DECODE)) rc |= paged_attention(qkv, QKV, attn, Hq * kD, kv_l, btab, max_blocks_per_seq, dwork, m.nd, Hq, Hkv, scale, 1, stream); Q(); launched(1); }
-    if (m.np) { P(B200_K_ATTN_PREFILL); if (on(B200_K_ATTN_PREFILL)) rc |= paged_attention(qkv, QKV, attn, Hq * kD, kv_l, btab, max_blocks_per_seq, pwork, m.np, Hq, Hkv, scale, 0, stream); Q(); launched(1); }
+    if (m.np) { P(B200_K_ATTN_PREFILL); if (on(B200_K_ATTN_PREFILL)) rc |= prefill_attention(kv_l, btab, pwork, m.np, scale); Q(); launched(1); }
     P(B200_K_GEMM_O);
     if (!on(B200_K_GEMM_O)) {}
     else if (dfr) rc |= gemm_def(ly.p_o, xm_attn, x, H, T, &pv_x); else rc |= gemm(ly.p_o, xm_attn, x, H, T);
@@ -742,7 +747,7 @@ int Engine::forward_fused(const StepMeta& m, int32_t* dbuf) {
       P(B200_K_GEMM_QKV); if (on(B200_K_GEMM_QKV)) rc |= gemm3_launch(p, sch_qkv, stream); Q();
     }
     if (m.nd) { P(B200_K_ATTN_DECODE); if (on(B200_K_ATTN_DECODE)) rc |= paged_attention(qkv, QKV, attn, Hq * kD, kv_l, btab, max_blocks_per_seq, dwork, m.nd, Hq, Hkv, scale, 1, stream); Q(); ++stats.kernel_launches; }
-    if (m.np) { P(B200_K_ATTN_PREFILL); if (on(B200_K_ATTN_PREFILL)) rc |= paged_attention(qkv, QKV, attn, Hq * kD, kv_l, btab, max_blocks_per_seq, pwork, m.np, Hq, Hkv, scale, 0, stream); Q(); ++stats.kernel_launches; }
+    if (m.np) { P(B200_K_ATTN_PREFILL); if (on(B200_K_ATTN_PREFILL)) rc |= prefill_attention(kv_l, btab, pwork, m.np, scale); Q(); ++stats.kernel_launches; }
     {
       Gemm3Params p = base(ly.p_o, xmap(xm_attn, 128), T, GEMM3_PRO_NONE, GEMM3_EPI_RESADD);
       p.out = res; p.ldo = H; p.ssq_out = ssq;
@@ -956,7 +961,8 @@ int Engine::launch(InFlight* f, StepMeta* mp) {
       m.kv_tokens += p0 + 1;
       ++f->ndec_seq;
     } else {
-      for (int j = 0; j < n; j += 16) pwork_.push_back({tok + j, std::min(16, n - j), p0 + j, si});
+      const int qb = prefill_attn_query_block();   // 64 query tokens per work item on the tensor-core kernel
+      for (int j = 0; j < n; j += qb) pwork_.push_back({tok + j, std::min(qb, n - j), p0 + j, si});
       m.kv_tokens += p0 + n;  // unique K/V tokens this sequence streams from HBM (query tiles re-read them from L2)
       ++f->npre_seq;
     }
@@ -1558,7 +1564,8 @@ int b200_engine_forward_logits(b200_engine* e, const int32_t* ids, int32_t n, vo
   if (n == 1) { m.nd = 1; h[w] = 0; h[w + 1] = 1; h[w + 2] = 0; h[w + 3] = 0; w += 4; m.off_pwork = w; }
   else {
     m.off_pwork = w;
-    for (int j = 0; j < n; j += 16) { h[w] = j; h[w + 1] = std::min(16, n - j); h[w + 2] = j; h[w + 3] = 0; w += 4; ++m.np; }
+    const int qb = prefill_attn_query_block();
+    for (int j = 0; j < n; j += qb) { h[w] = j; h[w + 1] = std::min(qb, n - j); h[w + 2] = j; h[w + 3] = 0; w += 4; ++m.np; }
   }
   m.off_btab = w;
   memcpy(h + w, s.blocks.data(), s.blocks.size() * 4);

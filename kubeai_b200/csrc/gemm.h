@@ -39,6 +39,10 @@ int gemm_make_x_map(CUtensorMap* tm, const void* X, int rows, int K, int ldx, in
 // Generic 2-D bf16 tensor map (used by the attention kernel for the paged KV cache).
 int tmap_encode_bf16_2d(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, int box_rows,
                         int box_cols, int swizzle128);
+// 3-D bf16 map (innermost d0 contiguous; strides in elements), box b2 x b1 x b0 with b0 = 64 (128-byte swizzle): the
+// tensor-core prefill attention reads its (token, head) query rows from the fused qkv buffer through it.
+int tmap_encode_bf16_3d(CUtensorMap* tm, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1, uint64_t stride2,
+                        int b0, int b1, int b2);
 // Output map (TMA-store epilogue of the pair kernel): out row-major [rows, N], rows = the T of the launch.
 int gemm_make_out_map(CUtensorMap* tm, const void* out, int rows, int N, int ldo);
 // variant-2 internals (gemm2_tcgen05.cu)

@@ -476,6 +476,21 @@ int tmap_encode_bf16_2d(CUtensorMap* tm, const void* base, uint64_t rows, uint64
   return r == CUDA_SUCCESS ? 0 : -2;
 }
 
+// 3-D bf16 map [d2][d1][d0] (d0 innermost, contiguous): strides in elements, box b2 x b1 x b0, 128-byte swizzle (b0 * 2 == 128).
+int tmap_encode_bf16_3d(CUtensorMap* tm, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1, uint64_t stride2,
+                        int b0, int b1, int b2) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return -1;
+  cuuint64_t dims[3] = {d0, d1, d2};
+  cuuint64_t strides[2] = {stride1 * 2, stride2 * 2};
+  cuuint32_t box[3] = {static_cast<cuuint32_t>(b0), static_cast<cuuint32_t>(b1), static_cast<cuuint32_t>(b2)};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -2;
+}
+
 // Output map for the TMA-store epilogue of the pair kernel: out row-major [rows, N] bf16, box = 32 rows x 128 cols,
 // no swizzle (the staging tile in smem is plain row-major); rows/cols outside the tensor are clipped by the hardware.
 int gemm_make_out_map(CUtensorMap* tm, const void* out, int rows, int N, int ldo) {

@@ -44,4 +44,10 @@ int paged_attention(const void* q, int ldq, void* out, int ldo, const void* kv_l
                     int max_blocks, const AttnWork* work, int num_work, int Hq, int Hkv, float scale,
                     int decode, cudaStream_t st);
 
+// Chunked-prefill attention on tcgen05 (attention_tc.cu): work items of up to 64 query tokens; q rows are read from the
+// fused qkv buffer [qkv_rows, ldq] through a 3-D TMA map.
+int paged_attention_prefill_tc(const void* qkv, int qkv_rows, int ldq, void* out, int ldo, const void* kv_layer, const int* block_tables,
+                               int max_blocks, const AttnWork* work, int num_work, int Hq, int Hkv, float scale, cudaStream_t st);
+int prefill_attn_query_block();   // query tokens per prefill work item: 64 (tensor-core kernel) or 16 (B200_ATTN_TC=0)
+
 }  // namespace b200

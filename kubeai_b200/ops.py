@@ -131,6 +131,17 @@ def paged_attn(qkv, kv_layer, block_tables, work, q_heads, kv_heads, decode: boo
     return out
 
 
+def paged_attn_prefill_tc(qkv, kv_layer, block_tables, work, q_heads, kv_heads, out=None):
+    """Tensor-core chunked-prefill attention; work: int32 [n, 4] = (q_tok0, q_count <= 64, q_pos0, seq)."""
+    _chk(qkv), _chk(kv_layer), _chk(block_tables, torch.int32), _chk(work, torch.int32)
+    T = qkv.shape[0]
+    if out is None:
+        out = torch.zeros(T, q_heads * 128, dtype=torch.bfloat16, device=qkv.device)
+    check(lib().b200_op_paged_attn_prefill_tc(_p(qkv), T, qkv.shape[1], _p(out), out.shape[1], _p(kv_layer), _p(block_tables),
+                                              block_tables.shape[1], _p(work), work.shape[0], q_heads, kv_heads, 128 ** -0.5, _stream()))
+    return out
+
+
 def init_uniform(n, seed, scale, offset, device="cuda"):
     out = torch.empty(n, dtype=torch.bfloat16, device=device)
     check(lib().b200_op_init_uniform(_p(out), n, seed & 0xFFFFFFFF, scale, offset, _stream()))

@@ -194,9 +194,11 @@ def test_decode_attention_at_production_shape():
         _attn_close(got[i:i + 1], want, f"decode seq {i} ctx {L}")
 
 
-def test_chunked_prefill_attention_at_production_shape_with_cached_prefix():
+@pytest.mark.parametrize("kernel", ["tensor_core", "mma_sync"])
+def test_chunked_prefill_attention_at_production_shape_with_cached_prefix(kernel):
     from kubeai_b200 import ops
     Hq, Hkv = 32, 8
+    qb = 64 if kernel == "tensor_core" else 16
     case = [(2048, 512), (1023, 1023), (16, 16), (1500, 37), (2047, 1), (777, 300), (64, 64), (1025, 1000)]   # (context, new tokens)
     lens = [c[0] for c in case]
     kv, btab, ks, vs = _pool(lens, Hkv, seed=22)
@@ -205,11 +207,13 @@ def test_chunked_prefill_attention_at_production_shape_with_cached_prefix():
     q = torch.randn(T, (Hq + 2 * Hkv) * 128, generator=g, device="cuda").bfloat16()
     work, spans, tok = [], [], 0
     for i, (L, n) in enumerate(case):
-        for j in range(0, n, 16):
-            work.append([tok + j, min(16, n - j), L - n + j, i])
+        for j in range(0, n, qb):
+            work.append([tok + j, min(qb, n - j), L - n + j, i])
         spans.append(tok)
         tok += n
-    got = ops.paged_attn(q, kv, btab, torch.tensor(work, dtype=torch.int32).cuda(), Hq, Hkv, decode=False).float()
+    wt = torch.tensor(work, dtype=torch.int32).cuda()
+    got = (ops.paged_attn_prefill_tc(q, kv, btab, wt, Hq, Hkv) if kernel == "tensor_core"
+           else ops.paged_attn(q, kv, btab, wt, Hq, Hkv, decode=False)).float()
     torch.cuda.synchronize()
     for i, (L, n) in enumerate(case):
         t0 = spans[i]

@@ -257,3 +257,35 @@ def test_paged_attention_prefill(case):
         want = O.attention(q[L - n:], k, v, torch.arange(L - n, L), 128 ** -0.5).reshape(n, Hq * 128)
         t0 = spans[i][0]
         close(got[t0:t0 + n], want, atol=4e-3, what=f"prefill attn seq {i}")
+
+
+@pytest.mark.parametrize("case", [
+    [(40, 40)],                                 # one partial block, no cached prefix
+    [(64, 64)],                                 # exactly one block, one kv tile
+    [(100, 37), (16, 16)],                      # 37 new tokens on 63 cached; a 16-token prompt
+    [(300, 130), (65, 1), (33, 33)],            # three blocks (64 + 64 + 2) on 170 cached; a 1-token chunk
+    [(513, 200), (129, 129)],
+])
+@pytest.mark.parametrize("Hkv", [1, 2])
+def test_paged_attention_prefill_tensor_core(case, Hkv):
+    """attention_tc.cu: 64-query blocks, S and P V on tcgen05 (V as an MN-major operand), against the oracle."""
+    from kubeai_b200 import ops
+    Hq = 4 * Hkv
+    seq_lens = [c[0] for c in case]
+    kv, btab, seqs = _paged_setup(seq_lens, None, Hq, Hkv, seed=13, nblocks=sum((l + 15) // 16 for l in seq_lens) + 3)
+    rows, work, spans = [], [], []
+    tok = 0
+    for i, (L, n) in enumerate(case):
+        rows.append(seqs[i][0][L - n:])
+        for j in range(0, n, 64):
+            work.append([tok + j, min(64, n - j), L - n + j, i])
+        spans.append((tok, n))
+        tok += n
+    rows = torch.cat(rows, dim=0).contiguous()
+    got = ops.paged_attn_prefill_tc(rows, kv, btab, torch.tensor(work, dtype=torch.int32).cuda(), Hq, Hkv)
+    torch.cuda.synchronize()
+    for i, (L, n) in enumerate(case):
+        _, q, k, v, _ = seqs[i]
+        want = O.attention(q[L - n:], k, v, torch.arange(L - n, L), 128 ** -0.5).reshape(n, Hq * 128)
+        t0 = spans[i][0]
+        close(got[t0:t0 + n], want, atol=4e-3, what=f"tensor-core prefill attn seq {i} (ctx {L}, new {n})")
