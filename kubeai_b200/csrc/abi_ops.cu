@@ -124,6 +124,8 @@ int b200_op_gemm_deferred(const void* w, const void* x, void* out, int32_t N, in
   return rc ? cuda_fail("gemm_deferred", rc) : 0;
 }
 
+static long long* g_gemm3_trace = nullptr;
+
 int b200_op_gemm3(const b200_gemm3_args* a, void* stream, int32_t* schedule_out) {
   if (int rc = require_device()) return rc;
   if (!a || !a->w || !a->x || a->N <= 0 || a->T <= 0 || a->K <= 0 || a->x_rows < a->T) {
@@ -161,6 +163,7 @@ int b200_op_gemm3(const b200_gemm3_args* a, void* stream, int32_t* schedule_out)
   p.kv_layer = static_cast<__nv_bfloat16*>(a->kv_layer); p.Hq = a->q_heads; p.Hkv = a->kv_heads; p.max_pos = a->max_pos;
   p.cand = cand; p.n_valid = a->n_valid > 0 ? a->n_valid : a->N;
   p.ws = g_ws; p.flags = flags; p.epoch = ++epoch;
+  p.trace = g_gemm3_trace;
   if (schedule_out) { schedule_out[0] = sch.S; schedule_out[1] = sch.streamk; schedule_out[2] = sch.grid; }
   rc = gemm3_launch(p, sch, st);
   if (rc) return cuda_fail("gemm3_launch", rc);
@@ -179,6 +182,7 @@ int b200_set_gemm_variant(int32_t v) {
 
 int b200_op_gemm_trace(void* trace_dev) {
   gemm2_set_trace(static_cast<long long*>(trace_dev));
+  g_gemm3_trace = static_cast<long long*>(trace_dev);   // b200_op_gemm3 launches stamp 8 values per CTA while this is set
   return 0;
 }
 

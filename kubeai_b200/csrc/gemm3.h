@@ -39,6 +39,8 @@ struct Gemm3Params {
   float* ws;
   int* flags;
   int epoch;
+  long long* trace;   // debug: 8 %globaltimer stamps per CTA (start, after cluster sync, first MMA, last MMA issued, epilogue
+                      // start, before / after the wait for the peers' partials, epilogue done), or nullptr
 };
 
 struct Gemm3Schedule {

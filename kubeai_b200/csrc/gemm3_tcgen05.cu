@@ -174,7 +174,16 @@ __global__ void __launch_bounds__(kThreads, 1) gemm3_kernel(const __grid_constan
   float* inv_s = reinterpret_cast<float*>(smem + (misc - smem_base) + 512);   // [64] 1/rms of this CTA's token half
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + (tmem_slot - smem_base));
 
+  // optional phase trace (debug): 8 %globaltimer stamps (ns, one clock for the whole GPU) per CTA
+  auto mark = [&](int i) {
+    if (P.trace) {
+      long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      P.trace[static_cast<size_t>(blockIdx.x) * 8 + i] = t;
+    }
+  };
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 64) mark(0);
   const uint32_t crank = cluster_ctarank();       // rank in the cluster (2S CTAs)
   const uint32_t rank = crank & 1u;               // rank in the pair
   const uint32_t pair = crank >> 1;               // pair index inside the cluster
@@ -241,6 +250,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm3_kernel(const __grid_constan
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
   griddep_launch();
+  if (threadIdx.x == 64) mark(1);
 
   const bool pro_norm = P.pro == GEMM3_PRO_NORM;
   const int row_half0 = static_cast<int>(rank) * (nc >> 1);   // first token of this CTA's half of the tile
@@ -294,6 +304,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm3_kernel(const __grid_constan
           mbar_wait(full_bar(stage), phase);
           if (pro_norm) mbar_wait(xf_bar(stage), phase);
           tc_fence_after();
+          if (it == it_begin && kb == sg.kb0) mark(2);
           const uint32_t sa = smem_base + stage * kStageBytes;
           const uint64_t a_desc = umma_desc_kmajor_sw128(sa);
           const uint64_t b_desc = umma_desc_kmajor_sw128(sa + kABytes);
@@ -314,6 +325,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm3_kernel(const __grid_constan
         }
         it += sg.kb1 - sg.kb0;
       }
+      mark(3);
     }
   } else if (warp >= 6) {
     // ------------------------------------------------------------ transform warps: RMSNorm of the token tile in smem
@@ -323,16 +335,25 @@ __global__ void __launch_bounds__(kThreads, 1) gemm3_kernel(const __grid_constan
       for (int i = xt; i < K / 8; i += 128)
         reinterpret_cast<uint4*>(smem + (wnorm - smem_base))[i] = __ldg(reinterpret_cast<const uint4*>(P.norm_w) + i);
       griddep_wait();
-      if (xt < kBN / 2) {
-        const int t = row_half0 + xt;
-        float inv = 0.f;
-        if (xt < (nc >> 1) && t < T) {
-          float ss = 0.f;
+      {
+        // 1/rms of this CTA's 64 token rows from the per-slab sums of squares: two threads per token, loads issued eight
+        // at a time (a dependent chain of L2 loads per slab measured ~10 us per launch)
+        const int tr = xt >> 1, part = xt & 1;
+        const int t = row_half0 + tr;
+        float ss = 0.f;
+        if (tr < (nc >> 1) && t < T) {
           const float* p = P.ssq_in + static_cast<size_t>(t) * P.ssq_slabs;
-          for (int s = 0; s < P.ssq_slabs; ++s) ss += __ldcg(p + s);
-          inv = rsqrtf(ss / static_cast<float>(K) + P.eps);
+          const int half = (P.ssq_slabs + 1) >> 1, s0 = part * half, s1 = min(P.ssq_slabs, s0 + half);
+          for (int s = s0; s < s1; s += 8) {
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = (s + u < s1) ? __ldcg(p + s + u) : 0.f;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) ss += v[u];
+          }
         }
-        inv_s[xt] = inv;
+        ss += __shfl_xor_sync(0xffffffffu, ss, 1);
+        if (part == 0) inv_s[tr] = (tr < (nc >> 1) && t < T) ? rsqrtf(ss / static_cast<float>(K) + P.eps) : 0.f;
       }
       xf_bar_sync();
       int stage = 0;
@@ -345,16 +366,22 @@ __global__ void __launch_bounds__(kThreads, 1) gemm3_kernel(const __grid_constan
         // 64 rows x 8 sixteen-byte chunks; 128B swizzle: physical chunk p of row r holds logical chunk p ^ (r & 7)
         for (int c = xt; c < nrows * 8; c += 128) {
           const int r = c >> 3, pch = c & 7, lch = pch ^ (r & 7);
-          V8 x, w, o;
-          x.u = *reinterpret_cast<const uint4*>(b + r * 128 + pch * 16);
-          w.u = *reinterpret_cast<const uint4*>(smem + (wnorm - smem_base) + (kb * kBlockK + lch * 8) * 2);
+          // packed math: the conversion units are the scarce resource here (scalar cvt per element measured ~1 us per
+          // stage, three times the stage's HBM time).  x * inv in fp32 -> one packed rounding; the product with the norm
+          // weight is a bf16 x bf16 multiply, exact in fp32, so __hmul2's single rounding equals bf16(float(nb) * float(w)).
+          const uint4 xv = *reinterpret_cast<const uint4*>(b + r * 128 + pch * 16);
+          const uint4 wv = *reinterpret_cast<const uint4*>(smem + (wnorm - smem_base) + (kb * kBlockK + lch * 8) * 2);
           const float inv = inv_s[r];
+          const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w}, ww[4] = {wv.x, wv.y, wv.z, wv.w};
+          uint32_t ow[4];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const __nv_bfloat16 nb = __float2bfloat16_rn(__bfloat162float(x.h[j]) * inv);
-            o.h[j] = __float2bfloat16_rn(__bfloat162float(nb) * __bfloat162float(w.h[j]));
+          for (int j = 0; j < 4; ++j) {
+            const float lo = __uint_as_float(xw[j] << 16) * inv, hi = __uint_as_float(xw[j] & 0xffff0000u) * inv;
+            const __nv_bfloat162 nb = __floats2bfloat162_rn(lo, hi);
+            const __nv_bfloat162 prod = __hmul2(nb, *reinterpret_cast<const __nv_bfloat162*>(&ww[j]));
+            ow[j] = *reinterpret_cast<const uint32_t*>(&prod);
           }
-          *reinterpret_cast<uint4*>(b + r * 128 + pch * 16) = o.u;
+          *reinterpret_cast<uint4*>(b + r * 128 + pch * 16) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
         }
         fence_proxy_async();
         __syncwarp();
@@ -374,6 +401,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm3_kernel(const __grid_constan
     const int row = q * 32 + lane;                    // TMEM lane = weight row inside the slab
     const int et = threadIdx.x - 64;                  // 0..127
     griddep_wait();
+    if (et == 0) mark(4);
     int acc = 0;
     uint32_t acc_phase = 0, recv_phase = 0;
     float* xb = reinterpret_cast<float*>(smem + (xbuf - smem_base));
@@ -473,9 +501,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm3_kernel(const __grid_constan
           tmem_ld_32x32(taddr + c * kChunkTok, v);
           tmem_ld_wait();
           if (need_recv && !recv_waited) {
+            if (et == 0 && it + (sg.kb1 - sg.kb0) >= it_end) mark(5);
             mbar_wait(recv_bar, recv_phase);
             recv_phase ^= 1u;
             recv_waited = true;
+            if (et == 0 && it + (sg.kb1 - sg.kb0) >= it_end) mark(6);
           }
           float f[32];
 #pragma unroll
@@ -644,6 +674,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm3_kernel(const __grid_constan
     }
   }
 
+  if (threadIdx.x == 64) mark(7);
   tc_fence_before();
   cluster_sync_all();  // no CTA may exit (or free TMEM) while a peer can still signal its barriers or read / write its smem
   if (warp == 1) {
