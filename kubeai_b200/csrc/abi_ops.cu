@@ -164,6 +164,7 @@ int b200_op_gemm3(const b200_gemm3_args* a, void* stream, int32_t* schedule_out)
   p.cand = cand; p.n_valid = a->n_valid > 0 ? a->n_valid : a->N;
   p.ws = g_ws; p.flags = flags; p.epoch = ++epoch;
   p.trace = g_gemm3_trace;
+  { const char* e = getenv("B200_GEMM3_DBG"); p.dbg = e ? atoi(e) : 0; }
   if (schedule_out) { schedule_out[0] = sch.S; schedule_out[1] = sch.streamk; schedule_out[2] = sch.grid; }
   rc = gemm3_launch(p, sch, st);
   if (rc) return cuda_fail("gemm3_launch", rc);

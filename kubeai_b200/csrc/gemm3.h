@@ -39,6 +39,7 @@ struct Gemm3Params {
   float* ws;
   int* flags;
   int epoch;
+  int dbg;            // debug switches of the norm prologue (timing experiments only): 1 skip the math, 2 no proxy fence, 4 plain remote arrive
   long long* trace;   // debug: 8 %globaltimer stamps per CTA (start, after cluster sync, first MMA, last MMA issued, epilogue
                       // start, before / after the wait for the peers' partials, epilogue done), or nullptr
 };

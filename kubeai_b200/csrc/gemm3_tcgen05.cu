@@ -128,6 +128,16 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t cta) 
       "r"(cta)
       : "memory");
 }
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t bar, uint32_t cta) {
+  asm volatile(
+      "{\n"
+      ".reg .b32 ra;\n"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n"
+      "}\n" ::"r"(bar),
+      "r"(cta)
+      : "memory");
+}
 // smem -> peer CTA's smem, completion (bytes) on the PEER's mbarrier
 __device__ __forceinline__ void dsmem_copy(uint32_t dst_cluster, uint32_t src_cta, uint32_t bytes, uint32_t bar_cluster) {
   asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -364,7 +374,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm3_kernel(const __grid_constan
         mbar_wait(bfull_bar(stage), phase);
         uint8_t* b = smem + (stage * kStageBytes + kABytes);
         // 64 rows x 8 sixteen-byte chunks; 128B swizzle: physical chunk p of row r holds logical chunk p ^ (r & 7)
-        for (int c = xt; c < nrows * 8; c += 128) {
+        for (int c = xt; c < ((P.dbg & 1) ? 0 : nrows * 8); c += 128) {
           const int r = c >> 3, pch = c & 7, lch = pch ^ (r & 7);
           // packed math: the conversion units are the scarce resource here (scalar cvt per element measured ~1 us per
           // stage, three times the stage's HBM time).  x * inv in fp32 -> one packed rounding; the product with the norm
@@ -383,10 +393,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm3_kernel(const __grid_constan
           }
           *reinterpret_cast<uint4*>(b + r * 128 + pch * 16) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
         }
-        fence_proxy_async();
+        if (!(P.dbg & 2)) fence_proxy_async();
         __syncwarp();
         if (lane == 0) {
           if (leader) mbar_arrive(xf_bar(stage));
+          else if (P.dbg & 4) mbar_arrive_cluster_relaxed(xf_bar(stage), leader_cta);
           else mbar_arrive_cluster(xf_bar(stage), leader_cta);
         }
         if (++stage == kStages) {

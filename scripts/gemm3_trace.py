@@ -46,6 +46,14 @@ def trace(name, T, N, K, force=0, pro=0, epi=0):
 
 
 if __name__ == "__main__":
+    import os
+    if len(sys.argv) > 1 and sys.argv[1] == "norm":
+        for dbg in (0, 1, 2, 4, 6, 7):
+            os.environ["B200_GEMM3_DBG"] = str(dbg)
+            print("dbg", dbg)
+            trace("qkv S=2 norm", 128, 6144, 4096, 2, pro=1)
+            trace("gate_up streamK norm", 128, 28672, 4096, 0, pro=1)
+        sys.exit(0)
     for T in (128,):
         trace("o S=1", T, 4096, 4096, 1)
         trace("o S=2", T, 4096, 4096, 2)
