@@ -181,6 +181,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm3_kernel(const __grid_constan
   auto tempty_bar = [&](int a) { return misc + 8u * (4 * kStages + 2 + a); };  // leader: 8 epilogue-warp arrivals
   const uint32_t recv_bar = misc + 8u * (4 * kStages + 4);                 // DSMEM partials / partner partial landed
   const uint32_t tmem_slot = misc + 8u * (4 * kStages + 5);
+  auto xf_local = [&](int s) { return misc + 8u * (4 * kStages + 6 + s); };    // non-leader: its 4 transform warps are done with stage s
   float* inv_s = reinterpret_cast<float*>(smem + (misc - smem_base) + 512);   // [64] 1/rms of this CTA's token half
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + (tmem_slot - smem_base));
 
@@ -242,7 +243,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm3_kernel(const __grid_constan
         mbar_init(full_bar(s), 1);
         mbar_init(empty_bar(s), 1);
         mbar_init(bfull_bar(s), 1);
-        mbar_init(xf_bar(s), 8);
+        mbar_init(xf_bar(s), 5);       // 4 transform warps of the leader + the peer CTA's relay thread
+        mbar_init(xf_local(s), 4);
       }
       for (int a = 0; a < 2; ++a) {
         mbar_init(tfull_bar(a), 1);
@@ -312,7 +314,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm3_kernel(const __grid_constan
         tc_fence_after();
         for (int kb = sg.kb0; kb < sg.kb1; ++kb) {
           mbar_wait(full_bar(stage), phase);
-          if (pro_norm) mbar_wait(xf_bar(stage), phase);
+          if (pro_norm) mbar_wait_cluster(xf_bar(stage), phase);
           tc_fence_after();
           if (it == it_begin && kb == sg.kb0) mark(2);
           const uint32_t sa = smem_base + stage * kStageBytes;
@@ -336,6 +338,21 @@ __global__ void __launch_bounds__(kThreads, 1) gemm3_kernel(const __grid_constan
         it += sg.kb1 - sg.kb0;
       }
       mark(3);
+    } else if (lane == 0 && pro_norm) {
+      // Non-leader CTA: relay "my half of stage s is normalised" to the leader's MMA thread.  The transform warps signal a
+      // LOCAL barrier (cheap); this otherwise idle thread forwards it with cluster-scope release semantics — when the
+      // transform warps did that themselves (one mbarrier.arrive.release.cluster per warp per stage) each of them stalled
+      // ~0.6 us per stage and the GEMM ran 3x slower (profiles/r02_gemm3_trace.md).
+      int stage = 0;
+      uint32_t phase = 0;
+      for (long long it = it_begin; it < it_end; ++it) {
+        mbar_wait(xf_local(stage), phase);
+        mbar_arrive_cluster(xf_bar(stage), leader_cta);
+        if (++stage == kStages) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
     }
   } else if (warp >= 6) {
     // ------------------------------------------------------------ transform warps: RMSNorm of the token tile in smem
@@ -373,33 +390,43 @@ __global__ void __launch_bounds__(kThreads, 1) gemm3_kernel(const __grid_constan
         const int kb = static_cast<int>(it % KB);
         mbar_wait(bfull_bar(stage), phase);
         uint8_t* b = smem + (stage * kStageBytes + kABytes);
-        // 64 rows x 8 sixteen-byte chunks; 128B swizzle: physical chunk p of row r holds logical chunk p ^ (r & 7)
-        for (int c = xt; c < ((P.dbg & 1) ? 0 : nrows * 8); c += 128) {
-          const int r = c >> 3, pch = c & 7, lch = pch ^ (r & 7);
-          // packed math: the conversion units are the scarce resource here (scalar cvt per element measured ~1 us per
-          // stage, three times the stage's HBM time).  x * inv in fp32 -> one packed rounding; the product with the norm
-          // weight is a bf16 x bf16 multiply, exact in fp32, so __hmul2's single rounding equals bf16(float(nb) * float(w)).
-          const uint4 xv = *reinterpret_cast<const uint4*>(b + r * 128 + pch * 16);
-          const uint4 wv = *reinterpret_cast<const uint4*>(smem + (wnorm - smem_base) + (kb * kBlockK + lch * 8) * 2);
-          const float inv = inv_s[r];
-          const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w}, ww[4] = {wv.x, wv.y, wv.z, wv.w};
-          uint32_t ow[4];
+        const uint8_t* wsm = smem + (wnorm - smem_base) + kb * kBlockK * 2;
+        // 64 rows x 8 sixteen-byte chunks, four per thread; 128B swizzle: physical chunk p of row r holds logical chunk
+        // p ^ (r & 7).  All loads first, then the math: the four chunks' shared-memory latencies overlap.
+        uint4 xv[4], wv[4];
+        float inv[4];
+        const int nchunks = (P.dbg & 1) ? 0 : nrows * 8;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float lo = __uint_as_float(xw[j] << 16) * inv, hi = __uint_as_float(xw[j] & 0xffff0000u) * inv;
-            const __nv_bfloat162 nb = __floats2bfloat162_rn(lo, hi);
-            const __nv_bfloat162 prod = __hmul2(nb, *reinterpret_cast<const __nv_bfloat162*>(&ww[j]));
-            ow[j] = *reinterpret_cast<const uint32_t*>(&prod);
+        for (int i = 0; i < 4; ++i) {
+          const int c = xt + i * 128;
+          if (c < nchunks) {
+            const int r = c >> 3, pch = c & 7;
+            xv[i] = *reinterpret_cast<const uint4*>(b + r * 128 + pch * 16);
+            wv[i] = *reinterpret_cast<const uint4*>(wsm + ((pch ^ (r & 7)) << 4));
+            inv[i] = inv_s[r];
           }
-          *reinterpret_cast<uint4*>(b + r * 128 + pch * 16) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
         }
-        if (!(P.dbg & 2)) fence_proxy_async();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int c = xt + i * 128;
+          if (c < nchunks) {
+            // packed math: x * inv in fp32 -> one packed rounding; the product with the norm weight is a bf16 x bf16
+            // multiply, exact in fp32, so __hmul2's single rounding equals bf16(float(nb) * float(w))
+            const uint32_t xw[4] = {xv[i].x, xv[i].y, xv[i].z, xv[i].w}, ww[4] = {wv[i].x, wv[i].y, wv[i].z, wv[i].w};
+            uint32_t ow[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float lo = __uint_as_float(xw[j] << 16) * inv[i], hi = __uint_as_float(xw[j] & 0xffff0000u) * inv[i];
+              const __nv_bfloat162 nb = __floats2bfloat162_rn(lo, hi);
+              const __nv_bfloat162 prod = __hmul2(nb, *reinterpret_cast<const __nv_bfloat162*>(&ww[j]));
+              ow[j] = *reinterpret_cast<const uint32_t*>(&prod);
+            }
+            *reinterpret_cast<uint4*>(b + (c >> 3) * 128 + (c & 7) * 16) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+          }
+        }
+        fence_proxy_async();
         __syncwarp();
-        if (lane == 0) {
-          if (leader) mbar_arrive(xf_bar(stage));
-          else if (P.dbg & 4) mbar_arrive_cluster_relaxed(xf_bar(stage), leader_cta);
-          else mbar_arrive_cluster(xf_bar(stage), leader_cta);
-        }
+        if (lane == 0) mbar_arrive(leader ? xf_bar(stage) : xf_local(stage));
         if (++stage == kStages) {
           stage = 0;
           phase ^= 1u;
