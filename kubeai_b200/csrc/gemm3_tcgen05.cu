@@ -59,14 +59,14 @@ constexpr int kThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue, wa
 constexpr int kABytes = kSlab * kBlockK * 2;            // 16 KB
 constexpr int kBBytes = (kBN / 2) * kBlockK * 2;        // 8 KB: this CTA's half of the token tile
 constexpr int kStageBytes = kABytes + kBBytes;          // 24 KB
-constexpr int kStages = 6;
-constexpr int kRing = kStages * kStageBytes;            // 144 KB
+constexpr int kStagesDefault = 6;                       // 144 KB ring
+constexpr int kMaxStages = 8;
 constexpr int kChunkF32 = kChunkTok * kSlab * 4;        // 16 KB: one chunk of fp32 partials [32 tokens][128 rows]
-constexpr int kXbuf = 4 * kChunkF32;                    // 64 KB: DSMEM receive slots / stream-K partner partial
+constexpr int kXbufDefault = 4 * kChunkF32;             // 64 KB: DSMEM receive slots / stream-K partner partial
 constexpr int kOpStage = kChunkTok * kSlab * 2;         // 8 KB: bf16 [32 tokens][128 rows] for the fused epilogue pass
 constexpr int kWnormMax = 8192 * 2;                     // norm weight (K <= 8192 for PRO_NORM)
 constexpr int kMisc = 1024;                             // barriers, tmem slot, inv table (64 floats)
-constexpr int kSmemBytes = 1024 + kRing + kXbuf + kOpStage + kMisc;   // + K*2 for PRO_NORM (<= 227 KB at K = 4096)
+constexpr int smem_bytes_for(int stages, int xbuf) { return 1024 + stages * kStageBytes + xbuf + kOpStage + kMisc; }   // + K*2 for PRO_NORM
 constexpr uint32_t kPeerMask = 0xFEFFFFFFu;  // clears bit 0 of the CTA rank in a shared::cluster address -> the pair's leader
 
 __device__ __forceinline__ long long range_begin(int unit, long long total, int units) {
@@ -165,7 +165,10 @@ struct Seg {
   int tile, kb0, kb1;
 };
 
+// kStages x 24 KB ring; kXbuf = 64 KB in production, 0 in the ring-depth experiment (plain S = 1 launches only)
+template <int kStages, int kXbuf>
 __global__ void __launch_bounds__(kThreads, 1) gemm3_kernel(const __grid_constant__ Gemm3Params P) {
+  constexpr int kRing = kStages * kStageBytes;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -181,7 +184,6 @@ __global__ void __launch_bounds__(kThreads, 1) gemm3_kernel(const __grid_constan
   auto tempty_bar = [&](int a) { return misc + 8u * (4 * kStages + 2 + a); };  // leader: 8 epilogue-warp arrivals
   const uint32_t recv_bar = misc + 8u * (4 * kStages + 4);                 // DSMEM partials / partner partial landed
   const uint32_t tmem_slot = misc + 8u * (4 * kStages + 5);
-  auto xf_local = [&](int s) { return misc + 8u * (4 * kStages + 6 + s); };    // non-leader: its 4 transform warps are done with stage s
   float* inv_s = reinterpret_cast<float*>(smem + (misc - smem_base) + 512);   // [64] 1/rms of this CTA's token half
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + (tmem_slot - smem_base));
 
@@ -243,8 +245,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm3_kernel(const __grid_constan
         mbar_init(full_bar(s), 1);
         mbar_init(empty_bar(s), 1);
         mbar_init(bfull_bar(s), 1);
-        mbar_init(xf_bar(s), 5);       // 4 transform warps of the leader + the peer CTA's relay thread
-        mbar_init(xf_local(s), 4);
+        mbar_init(xf_bar(s), 8);       // 4 transform warps of each CTA of the pair
       }
       for (int a = 0; a < 2; ++a) {
         mbar_init(tfull_bar(a), 1);
@@ -338,21 +339,6 @@ __global__ void __launch_bounds__(kThreads, 1) gemm3_kernel(const __grid_constan
         it += sg.kb1 - sg.kb0;
       }
       mark(3);
-    } else if (lane == 0 && pro_norm) {
-      // Non-leader CTA: relay "my half of stage s is normalised" to the leader's MMA thread.  The transform warps signal a
-      // LOCAL barrier (cheap); this otherwise idle thread forwards it with cluster-scope release semantics — when the
-      // transform warps did that themselves (one mbarrier.arrive.release.cluster per warp per stage) each of them stalled
-      // ~0.6 us per stage and the GEMM ran 3x slower (profiles/r02_gemm3_trace.md).
-      int stage = 0;
-      uint32_t phase = 0;
-      for (long long it = it_begin; it < it_end; ++it) {
-        mbar_wait(xf_local(stage), phase);
-        mbar_arrive_cluster(xf_bar(stage), leader_cta);
-        if (++stage == kStages) {
-          stage = 0;
-          phase ^= 1u;
-        }
-      }
     }
   } else if (warp >= 6) {
     // ------------------------------------------------------------ transform warps: RMSNorm of the token tile in smem
@@ -426,7 +412,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemm3_kernel(const __grid_constan
         }
         fence_proxy_async();
         __syncwarp();
-        if (lane == 0) mbar_arrive(leader ? xf_bar(stage) : xf_local(stage));
+        // the peer's warps signal the leader's barrier directly with a plain remote arrive (the form CUTLASS's ClusterBarrier
+        // uses between CTAs): the writes above were made visible to the async proxy by fence.proxy.async in this thread
+        // before the arrive is sent.  A cluster-scope release here cost ~1 us per stage — per warp, or in a relay thread —
+        // and tripled the GEMM's time (profiles/r02_gemm3_trace.md).
+        if (lane == 0) {
+          if (leader) mbar_arrive(xf_bar(stage));
+          else mbar_arrive_cluster_relaxed(xf_bar(stage), leader_cta);
+        }
         if (++stage == kStages) {
           stage = 0;
           phase ^= 1u;
@@ -786,7 +779,7 @@ bool query_occupancy(int smem_bytes, Occupancy* o) {
     cfg.attrs = at;
     cfg.numAttrs = 1;
     int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, gemm3_kernel, &cfg) != cudaSuccess) {
+    if (cudaOccupancyMaxActiveClusters(&n, gemm3_kernel<kStagesDefault, kXbufDefault>, &cfg) != cudaSuccess) {
       cudaGetLastError();
       n = 0;
     }
@@ -797,7 +790,18 @@ bool query_occupancy(int smem_bytes, Occupancy* o) {
 
 }  // namespace
 
-int gemm3_smem_bytes(int K, int pro) { return kSmemBytes + (pro == GEMM3_PRO_NORM ? K * 2 : 0); }
+int gemm3_stages() {   // B200_GEMM3_STAGES=4|8: ring-depth experiment (8: no exchange buffer, plain S=1 cluster launches only)
+  static const int v = [] {
+    const char* e = getenv("B200_GEMM3_STAGES");
+    const int n = e ? atoi(e) : kStagesDefault;
+    return n == 4 || n == 8 ? n : kStagesDefault;
+  }();
+  return v;
+}
+int gemm3_smem_bytes(int K, int pro) {
+  const int st = gemm3_stages();
+  return smem_bytes_for(st, st == 8 ? 0 : kXbufDefault) + (pro == GEMM3_PRO_NORM ? K * 2 : 0);
+}
 
 int gemm3_schedule(int N, int K, int T, int pro, int force, Gemm3Schedule* out) {
   if (T < 1 || T > kBN || N % (2 * kSlab) != 0 || K % kBlockK != 0) return -1;
@@ -807,9 +811,12 @@ int gemm3_schedule(int N, int K, int T, int pro, int force, Gemm3Schedule* out) 
   if (cudaGetDevice(&dev) != cudaSuccess) return -2;
   dev &= 63;
   const int smem = gemm3_smem_bytes(4096, GEMM3_PRO_NORM);   // the largest footprint the engine launches (K = 4096)
-  static std::atomic<unsigned long long> attr_done{0};
+  static std::atomic<unsigned long long> attr_done{0}, attr_done4{0}, attr_done8{0};
   constexpr int kMaxDynSmem = 232448;   // 227 KB: the per-CTA limit of sm_100
-  if (!ensure_dynamic_smem(gemm3_kernel, kMaxDynSmem, &attr_done)) return -3;
+  if (!ensure_dynamic_smem(gemm3_kernel<kStagesDefault, kXbufDefault>, kMaxDynSmem, &attr_done) ||
+      !ensure_dynamic_smem(gemm3_kernel<4, kXbufDefault>, kMaxDynSmem, &attr_done4) ||
+      !ensure_dynamic_smem(gemm3_kernel<8, 0>, kMaxDynSmem, &attr_done8))
+    return -3;
   if (!have[dev]) {
     if (!query_occupancy(smem, &occ[dev])) return -3;
     have[dev] = true;
@@ -863,7 +870,12 @@ int gemm3_launch(const Gemm3Params& p, const Gemm3Schedule& sch, cudaStream_t st
   Gemm3Params q = p;
   q.S = sch.S;
   q.streamk = sch.streamk;
-  return cudaLaunchKernelEx(&cfg, gemm3_kernel, q) == cudaSuccess ? 0 : -4;
+  const int st_n = gemm3_stages();
+  if (st_n == 8 && (q.streamk || q.S > 1)) return -6;   // the 8-stage variant has no exchange buffer
+  cudaError_t e = st_n == 4 ? cudaLaunchKernelEx(&cfg, gemm3_kernel<4, kXbufDefault>, q)
+                : st_n == 8 ? cudaLaunchKernelEx(&cfg, gemm3_kernel<8, 0>, q)
+                            : cudaLaunchKernelEx(&cfg, gemm3_kernel<kStagesDefault, kXbufDefault>, q);
+  return e == cudaSuccess ? 0 : -4;
 }
 
 int argmax_candidates(const void* cand, int* out, int S, int slabs, cudaStream_t st) {

@@ -54,6 +54,16 @@ if __name__ == "__main__":
             trace("qkv S=2 norm", 128, 6144, 4096, 2, pro=1)
             trace("gate_up streamK norm", 128, 28672, 4096, 0, pro=1)
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "stages":
+        print("B200_GEMM3_STAGES =", os.environ.get("B200_GEMM3_STAGES", "6 (default)"))
+        trace("o S=1", 128, 4096, 4096, 1)
+        trace("down S=1", 128, 4096, 14336, 1)
+        trace("qkv S=1", 128, 6144, 4096, 1)
+        trace("gate_up S=1 (2 waves)", 128, 28672, 4096, 1) if False else None
+        if os.environ.get("B200_GEMM3_STAGES") != "8":
+            trace("o S=3", 128, 4096, 4096, 3)
+            trace("gate_up streamK", 128, 28672, 4096, 0)
+        sys.exit(0)
     for T in (128,):
         trace("o S=1", T, 4096, 4096, 1)
         trace("o S=2", T, 4096, 4096, 2)
