@@ -298,7 +298,8 @@ int b200_op_gemm_deferred(const void* w, const void* x, void* out, int32_t N, in
 int b200_op_gemm(const void* w, const void* x, void* out, int32_t N, int32_t T, int32_t K, void* stream);
 /* The decode-shape fused GEMM (T <= 128; csrc/gemm3_tcgen05.cu): acc = X' W^T with the split-K reduction finished in the
  * kernel, a prologue (pro 0: X' = x; 1: X' = RMSNorm(x) from the per-slab sums of squares ssq_in [T, ssq_slabs] and norm_w)
- * and an epilogue on the bf16-rounded result (epi 0: out [T, N]; 1: out (in/out, residual) += acc, ssq_out [T, N/128];
+ * and an epilogue on the bf16-rounded result (epi 0: out [T, N]; 1: out (in/out, residual) += acc, ssq_out [T, N/128], and
+ * optionally the RMSNorm of the new residual for the next projection;
  * 2: out [T, N/2] = silu(gate) * up with gate/up rows interleaved in 64-row blocks of w; 3: neox RoPE of q/k heads, q ->
  * out (the fused qkv buffer, ldo), k/v -> kv_layer pages; 4: argmax_out [T] = argmax_n acc[t, n < n_valid]).
  * force: 0 automatic schedule, 1..4 pairs per tile (cluster split-K through distributed shared memory), < 0 stream-K.
@@ -322,6 +323,9 @@ typedef struct {
   int32_t q_heads, kv_heads, max_pos;
   int32_t* argmax_out;
   int32_t n_valid;
+  /* epi 1 only, optional: also write normed_out [T, N] = RMSNorm(new residual) * norm_w_out (the next projection's input) */
+  void* normed_out;
+  const void* norm_w_out;
 } b200_gemm3_args;
 int b200_op_gemm3(const b200_gemm3_args* a, void* stream, int32_t* schedule_out);
 int b200_op_embed(const void* table, const int32_t* ids, void* out, int32_t T, int32_t H, int32_t vocab, void* stream);

@@ -38,7 +38,7 @@ class Gemm3Args(C.Structure):
                 ("norm_w", C.c_void_p), ("eps", C.c_float), ("out", C.c_void_p), ("ldo", C.c_int32),
                 ("ssq_out", C.c_void_p), ("positions", C.c_void_p), ("slots", C.c_void_p), ("cos_sin", C.c_void_p),
                 ("kv_layer", C.c_void_p), ("q_heads", C.c_int32), ("kv_heads", C.c_int32), ("max_pos", C.c_int32),
-                ("argmax_out", C.c_void_p), ("n_valid", C.c_int32)]
+                ("argmax_out", C.c_void_p), ("n_valid", C.c_int32), ("normed_out", C.c_void_p), ("norm_w_out", C.c_void_p)]
 
 
 class Sampling(C.Structure):

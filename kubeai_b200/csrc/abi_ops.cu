@@ -134,13 +134,13 @@ int b200_op_gemm3(const b200_gemm3_args* a, void* stream, int32_t* schedule_out)
   }
   if (ensure_scratch()) { set_error("workspace allocation failed"); return B200_ERR_OOM; }
   static float2* cand = nullptr;          // [128 tokens][slabs]
-  static int* flags = nullptr;
+  static int* flags = nullptr;            // stream-K neighbour flags [0, 4096) + fused-norm row flags [4096, 8192)
   static int epoch = 0;
   static std::mutex mu;
   std::lock_guard<std::mutex> lk(mu);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (!flags) {
-    if (cudaMalloc(&flags, 4096 * sizeof(int)) != cudaSuccess || cudaMemset(flags, 0, 4096 * sizeof(int)) != cudaSuccess) return B200_ERR_OOM;
+    if (cudaMalloc(&flags, 8192 * sizeof(int)) != cudaSuccess || cudaMemset(flags, 0, 8192 * sizeof(int)) != cudaSuccess) return B200_ERR_OOM;
     if (cudaMalloc(&cand, sizeof(float2) * 128 * 4096) != cudaSuccess) return B200_ERR_OOM;
   }
   if (a->epi == GEMM3_EPI_ARGMAX && (a->N / 128 > 4096 || !a->argmax_out)) { set_error("b200_op_gemm3: argmax needs argmax_out and N <= 524288"); return B200_ERR_INVALID; }
@@ -162,6 +162,12 @@ int b200_op_gemm3(const b200_gemm3_args* a, void* stream, int32_t* schedule_out)
   p.positions = a->positions; p.slots = a->slots; p.cos_sin = static_cast<const __nv_bfloat16*>(a->cos_sin);
   p.kv_layer = static_cast<__nv_bfloat16*>(a->kv_layer); p.Hq = a->q_heads; p.Hkv = a->kv_heads; p.max_pos = a->max_pos;
   p.cand = cand; p.n_valid = a->n_valid > 0 ? a->n_valid : a->N;
+  if (a->epi == GEMM3_EPI_RESADD && a->normed_out) {
+    if (sch.streamk || !a->norm_w_out || a->N / 128 > 1024) { set_error("b200_op_gemm3: the fused norm needs the cluster schedule and norm_w_out"); return B200_ERR_INVALID; }
+    p.normed_out = static_cast<__nv_bfloat16*>(a->normed_out);
+    p.norm_w_out = static_cast<const __nv_bfloat16*>(a->norm_w_out);
+    p.row_flags = flags + 4096;
+  }
   p.ws = g_ws; p.flags = flags; p.epoch = ++epoch;
   p.trace = g_gemm3_trace;
   { const char* e = getenv("B200_GEMM3_DBG"); p.dbg = e ? atoi(e) : 0; }

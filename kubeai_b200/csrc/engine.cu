@@ -484,8 +484,8 @@ int Engine::alloc_all() {
   CK(cudaMallocHost(&sampled_host, static_cast<size_t>(Scap) * 4));
   CK(cudaMalloc(&ssq, static_cast<size_t>(Tcap) * (H / 128) * 4));
   CK(cudaMalloc(&cand, static_cast<size_t>(std::min(Scap, 128)) * (V / 128 + 1) * sizeof(float2)));
-  CK(cudaMalloc(&g3_flags, 4096 * 4));
-  CK(cudaMemset(g3_flags, 0, 4096 * 4));
+  CK(cudaMalloc(&g3_flags, 8192 * 4));     // stream-K neighbour flags [0, 4096) + fused-norm row flags [4096, 8192)
+  CK(cudaMemset(g3_flags, 0, 8192 * 4));
   // split-K workspace: 2 fp32 slots of 512 tokens x 128 rows per CTA (in-kernel fix-up slots == deferred segments)
   size_t ws_bytes = std::max(std::max(gemm_workspace_bytes(sms), gemm_deferred_ws_bytes(sms)), gemm3_ws_bytes(sms));
   gemm_ws_bytes = ws_bytes;
@@ -524,9 +524,9 @@ int Engine::alloc_all() {
     const char* e = getenv("B200_FUSED_DECODE");   // A/B knob: 0 keeps every step on the unfused kernels
     const bool want = !(e && atoi(e) == 0) && gemm_variant() == 2;
     fused_ok = want && QKV % 256 == 0 && H % 256 == 0 && (2 * I) % 256 == 0 && V % 256 == 0 && H <= 4096 &&
-               !gemm3_schedule(QKV, H, 128, GEMM3_PRO_NORM, 0, &sch_qkv) && !gemm3_schedule(H, Hq * kD, 128, GEMM3_PRO_NONE, 0, &sch_o) &&
-               !gemm3_schedule(2 * I, H, 128, GEMM3_PRO_NORM, 0, &sch_gu) && !gemm3_schedule(H, I, 128, GEMM3_PRO_NONE, 0, &sch_down) &&
-               !gemm3_schedule(V, H, 128, GEMM3_PRO_NONE, 0, &sch_lm);
+               !gemm3_schedule(QKV, H, 128, GEMM3_PRO_NONE, 0, &sch_qkv) && !gemm3_schedule(H, Hq * kD, 128, GEMM3_PRO_NONE, 0, &sch_o) &&
+               !gemm3_schedule(2 * I, H, 128, GEMM3_PRO_NONE, 0, &sch_gu) && !gemm3_schedule(H, I, 128, GEMM3_PRO_NONE, 0, &sch_down) &&
+               !gemm3_schedule(V, H, 128, GEMM3_PRO_NONE, 0, &sch_lm) && !sch_o.streamk && !sch_down.streamk && H / 128 <= 1024;
     cudaGetLastError();
   }
 
@@ -733,15 +733,16 @@ int Engine::forward_fused(const StepMeta& m, int32_t* dbuf) {
     p.n_valid = pl.N;
     return p;
   };
-  // embedding rows are the first residual; their sums of squares feed layer 0's norm prologue
-  P(B200_K_EMBED); if (on(B200_K_EMBED)) rc |= embed_gather(embed, ids, res, T, H, V, stream, ssq, slabs); Q();
-  stats.kernel_launches += 1;
+  // embedding rows are the first residual; layer 0's norm is the one standalone RMSNorm of the step — every later norm
+  // rides in the epilogue of the projection that produces its input (o_proj -> norm2, down_proj -> next layer's norm1)
+  P(B200_K_EMBED); if (on(B200_K_EMBED)) rc |= embed_gather(embed, ids, res, T, H, V, stream); Q();
+  P(B200_K_NORM); if (on(B200_K_NORM)) rc |= rmsnorm(res, nullptr, layers[0].norm1, normed, nullptr, T, H, cfg.rms_eps, stream); Q();
+  stats.kernel_launches += 2;
   for (int l = 0; l < L && !rc; ++l) {
     Layer& ly = layers[l];
     bf16* kv_l = kv + static_cast<size_t>(l) * kv_layer_elems;
     {
-      Gemm3Params p = base(ly.p_qkv, xmap(xm_res, 128), T, GEMM3_PRO_NORM, GEMM3_EPI_ROPE_KV);
-      p.norm_w = ly.norm1;
+      Gemm3Params p = base(ly.p_qkv, xmap(xm_normed, 128), T, GEMM3_PRO_NONE, GEMM3_EPI_ROPE_KV);
       p.out = qkv; p.ldo = QKV;
       p.positions = pos; p.slots = slots; p.cos_sin = cos_sin; p.kv_layer = kv_l; p.Hq = Hq; p.Hkv = Hkv; p.max_pos = cfg.max_model_len;
       P(B200_K_GEMM_QKV); if (on(B200_K_GEMM_QKV)) rc |= gemm3_launch(p, sch_qkv, stream); Q();
@@ -751,17 +752,18 @@ int Engine::forward_fused(const StepMeta& m, int32_t* dbuf) {
     {
       Gemm3Params p = base(ly.p_o, xmap(xm_attn, 128), T, GEMM3_PRO_NONE, GEMM3_EPI_RESADD);
       p.out = res; p.ldo = H; p.ssq_out = ssq;
+      p.normed_out = normed; p.norm_w_out = ly.norm2; p.row_flags = g3_flags + 4096;
       P(B200_K_GEMM_O); if (on(B200_K_GEMM_O)) rc |= gemm3_launch(p, sch_o, stream); Q();
     }
     {
-      Gemm3Params p = base(ly.p_gu, xmap(xm_res, 128), T, GEMM3_PRO_NORM, GEMM3_EPI_SILU);
-      p.norm_w = ly.norm2;
+      Gemm3Params p = base(ly.p_gu, xmap(xm_normed, 128), T, GEMM3_PRO_NONE, GEMM3_EPI_SILU);
       p.out = act; p.ldo = I;
       P(B200_K_GEMM_GU); if (on(B200_K_GEMM_GU)) rc |= gemm3_launch(p, sch_gu, stream); Q();
     }
     {
       Gemm3Params p = base(ly.p_down, xmap(xm_act, 128), T, GEMM3_PRO_NONE, GEMM3_EPI_RESADD);
       p.out = res; p.ldo = H; p.ssq_out = ssq;
+      if (l + 1 < L) { p.normed_out = normed; p.norm_w_out = layers[l + 1].norm1; p.row_flags = g3_flags + 4096; }
       P(B200_K_GEMM_DOWN); if (on(B200_K_GEMM_DOWN)) rc |= gemm3_launch(p, sch_down, stream); Q();
     }
     stats.kernel_launches += 4;

@@ -26,6 +26,11 @@ struct Gemm3Params {
   __nv_bfloat16* out;
   int ldo;
   float* ssq_out;     // RESADD: [T, N/128]
+  // RESADD with the next projection's RMSNorm fused (cluster mode only): normed_out [T, N] (leading dimension ldo) =
+  // RMSNorm(new residual) * norm_w_out; row_flags [4 chunks][N/128] ints stamped with `epoch` when a slab's sums are out
+  __nv_bfloat16* normed_out;
+  const __nv_bfloat16* norm_w_out;
+  int* row_flags;
   // ROPE_KV
   const int* positions;
   const int* slots;

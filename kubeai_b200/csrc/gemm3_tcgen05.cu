@@ -437,6 +437,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm3_kernel(const __grid_constan
     uint32_t acc_phase = 0, recv_phase = 0;
     float* xb = reinterpret_cast<float*>(smem + (xbuf - smem_base));
     __nv_bfloat16* ob = reinterpret_cast<__nv_bfloat16*>(smem + (opst - smem_base));
+    // fused-norm epilogue: bf16 [4 chunks][32 tokens][128 rows] of summed rows, in the (idle) ring behind the send staging
+    __nv_bfloat16* zkeep = reinterpret_cast<__nv_bfloat16*>(smem + 3 * kChunkF32);
+    float* inv_tok = reinterpret_cast<float*>(smem + 3 * kChunkF32 + kNumChunks * kOpStage);   // [4][32]
     const int valid_chunks = (n_eff + kChunkTok - 1) / kChunkTok;
 
     for (long long it = it_begin; it < it_end;) {
@@ -589,6 +592,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm3_kernel(const __grid_constan
                 *reinterpret_cast<uint4*>(P.out + static_cast<size_t>(t) * P.ldo + n0 + vv * 8) = z.u;
                 if (vv == 0) P.ssq_out[static_cast<size_t>(t) * (N / kSlab) + slab] = ss;
               }
+              // fused norm: the summed row stays in shared memory until every slab's sum of squares has been published
+              if (P.normed_out) *reinterpret_cast<uint4*>(zkeep + c * (kChunkTok * kSlab) + j * kSlab + vv * 8) = z.u;
             }
           } else if (P.epi == GEMM3_EPI_SILU) {
             // rows 0..63 of the slab are gate rows, 64..127 the matching up rows; act columns [slab*64, slab*64+64)
@@ -695,6 +700,72 @@ __global__ void __launch_bounds__(kThreads, 1) gemm3_kernel(const __grid_constan
         if (lane == 0) {
           if (leader) mbar_arrive(tempty_bar(acc));
           else mbar_arrive_cluster(tempty_bar(acc), leader_cta);
+        }
+        if (P.epi == GEMM3_EPI_RESADD && P.normed_out) {
+          // ---- fused RMSNorm of the summed residual (the input of the NEXT projection): every CTA has published the sums
+          // of squares of its (chunk, slab); a row's norm needs all N/128 slabs, i.e. the other clusters — they finish
+          // within a microsecond or two of each other (all clusters are co-resident in cluster mode), so each CTA marks its
+          // slabs with the launch epoch and waits for the flags of the chunks it owns.  Deterministic: the per-slab sums are
+          // added in slab order.  Rounding as the standalone kernel: bf16(bf16(z * inv) * w).
+          const int slabs = N / kSlab;
+          __threadfence();
+          epi_bar();
+          if (et == 0)
+            for (int c = 0; c < valid_chunks; ++c)
+              if (S == 1 || (c % S) == static_cast<int>(pair)) st_release_gpu(P.row_flags + c * slabs + slab, P.epoch);
+          if (warp == 2) {
+            for (int c = 0; c < valid_chunks; ++c) {
+              if (S > 1 && (c % S) != static_cast<int>(pair)) continue;
+              for (int s0 = 0; s0 < slabs; s0 += 32) {
+                const int sidx = s0 + lane;
+                while (!__all_sync(0xffffffffu, sidx >= slabs || ld_acquire_gpu(P.row_flags + c * slabs + sidx) == P.epoch)) __nanosleep(40);
+              }
+            }
+          }
+          epi_bar();
+          // 1/rms per owned token: 4 threads per token, each adds a quarter of the slabs in order, then a fixed-order combine
+          for (int c = 0; c < valid_chunks; ++c) {
+            if (S > 1 && (c % S) != static_cast<int>(pair)) continue;
+            const int j = et >> 2, part = et & 3, t = c * kChunkTok + j;
+            float ss = 0.f;
+            if (t < T) {
+              const float* sp = P.ssq_out + static_cast<size_t>(t) * slabs;
+              const int q4 = (slabs + 3) >> 2, a0 = part * q4, a1 = min(slabs, a0 + q4);
+              for (int a = a0; a < a1; a += 8) {
+                float v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v[u] = (a + u < a1) ? __ldcg(sp + a + u) : 0.f;
+#pragma unroll
+                for (int u = 0; u < 8; ++u) ss += v[u];
+              }
+            }
+            const float s1 = __shfl_xor_sync(0xffffffffu, ss, 1);
+            const float lo = (part & 1) ? s1 + ss : ss + s1;            // (part0 + part1) or (part2 + part3), same order in both lanes
+            const float s2 = __shfl_xor_sync(0xffffffffu, lo, 2);
+            const float tot = (part & 2) ? s2 + lo : lo + s2;
+            if (part == 0) inv_tok[c * kChunkTok + j] = t < T ? rsqrtf(tot / static_cast<float>(N) + P.eps) : 0.f;
+          }
+          epi_bar();
+          for (int c = 0; c < valid_chunks; ++c) {
+            if (S > 1 && (c % S) != static_cast<int>(pair)) continue;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int item = et + i * 128, j = item >> 4, vv = item & 15, t = c * kChunkTok + j;
+              if (t >= T) continue;
+              const uint4 zv = *reinterpret_cast<const uint4*>(zkeep + c * (kChunkTok * kSlab) + j * kSlab + vv * 8);
+              const uint4 wv = __ldg(reinterpret_cast<const uint4*>(P.norm_w_out + n0 + vv * 8));
+              const float inv = inv_tok[c * kChunkTok + j];
+              const uint32_t zw[4] = {zv.x, zv.y, zv.z, zv.w}, ww[4] = {wv.x, wv.y, wv.z, wv.w};
+              uint32_t ow[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const __nv_bfloat162 nb = __floats2bfloat162_rn(__uint_as_float(zw[e] << 16) * inv, __uint_as_float(zw[e] & 0xffff0000u) * inv);
+                const __nv_bfloat162 prod = __hmul2(nb, *reinterpret_cast<const __nv_bfloat162*>(&ww[e]));
+                ow[e] = *reinterpret_cast<const uint32_t*>(&prod);
+              }
+              *reinterpret_cast<uint4*>(P.normed_out + static_cast<size_t>(t) * P.ldo + n0 + vv * 8) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+            }
+          }
         }
       }
       if (++acc == 2) {

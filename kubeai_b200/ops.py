@@ -47,7 +47,8 @@ EPI_PLAIN, EPI_RESADD, EPI_SILU, EPI_ROPE_KV, EPI_ARGMAX = 0, 1, 2, 3, 4
 
 
 def gemm3(x, w, T=None, pro=PRO_NONE, epi=EPI_PLAIN, force=0, ssq_in=None, norm_w=None, eps=1e-5, out=None, ssq_out=None,
-          positions=None, slots=None, cos_sin=None, kv_layer=None, q_heads=0, kv_heads=0, argmax_out=None, n_valid=0):
+          positions=None, slots=None, cos_sin=None, kv_layer=None, q_heads=0, kv_heads=0, argmax_out=None, n_valid=0,
+          normed_out=None, norm_w_out=None):
     """The decode-shape fused GEMM (b200_op_gemm3).  x: [rows >= T, K] activations (or the residual for PRO_NORM),
     w: [N, K].  Returns (out, schedule) with schedule = (pairs per tile, stream-K flag, CTAs)."""
     from ._lib import Gemm3Args
@@ -65,6 +66,10 @@ def gemm3(x, w, T=None, pro=PRO_NONE, epi=EPI_PLAIN, force=0, ssq_in=None, norm_
         _chk(out)                                               # the residual, updated in place
         ssq_out = torch.zeros(T, N // 128, dtype=torch.float32, device=x.device) if ssq_out is None else ssq_out
         a.ssq_out = ssq_out.data_ptr()
+        if norm_w_out is not None:                              # fused RMSNorm of the new residual for the next projection
+            _chk(norm_w_out)
+            normed_out = torch.empty(T, N, dtype=torch.bfloat16, device=x.device) if normed_out is None else normed_out
+            a.normed_out, a.norm_w_out = normed_out.data_ptr(), norm_w_out.data_ptr()
     elif epi == EPI_SILU:
         out = torch.empty(T, N // 2, dtype=torch.bfloat16, device=x.device) if out is None else out
     elif epi == EPI_ROPE_KV:
@@ -78,7 +83,8 @@ def gemm3(x, w, T=None, pro=PRO_NONE, epi=EPI_PLAIN, force=0, ssq_in=None, norm_
         a.out, a.ldo = out.data_ptr(), out.stride(0)
     sch = (C.c_int32 * 3)()
     check(lib().b200_op_gemm3(C.byref(a), _stream(), sch))
-    res = argmax_out if epi == EPI_ARGMAX else (out, ssq_out) if epi == EPI_RESADD else out
+    res = argmax_out if epi == EPI_ARGMAX else (out, ssq_out, normed_out) if (epi == EPI_RESADD and norm_w_out is not None) \
+        else (out, ssq_out) if epi == EPI_RESADD else out
     return res, tuple(sch)
 
 

@@ -145,6 +145,29 @@ def test_residual_add_epilogue(T, N, K, force):
     assert torch.allclose(ssq, want_ssq, rtol=1e-5, atol=1e-6), float((ssq - want_ssq).abs().max())
 
 
+@pytest.mark.parametrize("force", [0, 1, 2])
+@pytest.mark.parametrize("T,N,K", [(128, 4096, 4096), (128, 4096, 14336), (37, 512, 1024), (1, 512, 512)])
+def test_residual_add_epilogue_with_the_next_norm_fused(T, N, K, force):
+    """EPI_RESADD + fused RMSNorm: the new residual's norm needs every slab's sum of squares, i.e. all clusters of the
+    launch (flag exchange at the end of the kernel); result = the oracle's fused_add_rms_norm on the kernel's own product."""
+    from kubeai_b200 import ops
+    x, w = rnd(T, K, seed=19), rnd(N, K, scale=1 / math.sqrt(K), seed=20)
+    res0 = rnd(T, N, scale=2.0, seed=21)
+    nw = (1.0 + 0.1 * torch.randn(N, device="cuda", generator=torch.Generator(device="cuda").manual_seed(22))).bfloat16()
+    plain, _ = ops.gemm3(x, w, force=force)
+    for rep in range(3):
+        res = res0.clone()
+        (res, ssq, normed), sch = ops.gemm3(x, w, epi=ops.EPI_RESADD, out=res, norm_w_out=nw, force=force)
+        torch.cuda.synchronize()
+        want_h, want_res = O.fused_add_rms_norm(plain.float(), res0.float(), nw.float(), 1e-5)
+        assert torch.equal(res.float(), want_res), f"residual ({sch})"
+        bad = normed.float() != want_h
+        # rsqrtf on the device vs torch.rsqrt: a few normalised values land on the other side of a bf16 boundary
+        assert float(bad.float().mean()) < 2e-3, f"{int(bad.sum())} of {bad.numel()} normalised values differ ({sch}, rep {rep})"
+        err = (normed.float() - want_h).abs()
+        assert bool((err <= ATOL + RTOL * want_h.abs()).all())
+
+
 def _interleave64(wg, wu):
     """gate rows and up rows interleaved in 64-row blocks: the engine's physical gate_up layout."""
     I, K = wg.shape
