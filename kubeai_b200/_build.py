@@ -21,6 +21,7 @@ SOURCES = [
     "gemm_tcgen05.cu",
     "gemm2_tcgen05.cu",
     "gemm3_tcgen05.cu",
+    "chain_tcgen05.cu",
     "attention.cu",
     "attention_tc.cu",
     "elementwise.cu",

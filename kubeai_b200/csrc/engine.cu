@@ -32,6 +32,7 @@
 #include "errors.h"
 #include "gemm.h"
 #include "gemm3.h"
+#include "chain.h"
 #include "kernels.h"
 #include "hostutil.h"
 #include "xxh64.h"
@@ -249,6 +250,11 @@ struct Engine {
   int g3_epoch = 0;
   bool fused_ok = false;
   Gemm3Schedule sch_qkv, sch_o, sch_gu, sch_down, sch_lm;
+  // projection chain (chain_tcgen05.cu): o -> norm -> gate_up -> down -> norm -> next qkv -> rope in one persistent launch
+  bool chain_ok = false;
+  int chain_ctas = 0;
+  unsigned long long* chain_bar = nullptr;
+  unsigned long long chain_bar_count = 0;   // host mirror of the grid-barrier counter
   XMaps xm_res;
   XMaps xm_normed, xm_attn, xm_act, xm_last;
   float* gemm_ws = nullptr;
@@ -299,6 +305,7 @@ struct Engine {
   int alloc_all();
   int forward(const StepMeta& m, int32_t* dbuf, bool all_logits, bf16* logits_out);
   int forward_fused(const StepMeta& m, int32_t* dbuf);
+  int forward_chain(const StepMeta& m, int32_t* dbuf);
   int prefill_attention(bf16* kv_l, const int* btab, const AttnWork* pwork, int np, float scale) {
     if (prefill_attn_query_block() == 64)
       return paged_attention_prefill_tc(qkv, Tcap, QKV, attn, Hq * kD, kv_l, btab, max_blocks_per_seq, pwork, np, Hq, Hkv, scale, stream);
@@ -367,7 +374,7 @@ Engine::~Engine() {
   cudaSetDevice(cfg.device);
   if (stream) cudaStreamSynchronize(stream);
   void* frees[] = {weights_blob, res, x, normed, qkv, attn, gu, act, last_hidden, logits, sampled, gemm_ws,
-                   gemm_counters, kv, ssq, cand, g3_flags};
+                   gemm_counters, kv, ssq, cand, g3_flags, chain_bar};
   for (void* p : frees)
     if (p) cudaFree(p);
   for (auto p : stage_dev)
@@ -528,6 +535,16 @@ int Engine::alloc_all() {
                !gemm3_schedule(2 * I, H, 128, GEMM3_PRO_NONE, 0, &sch_gu) && !gemm3_schedule(H, I, 128, GEMM3_PRO_NONE, 0, &sch_down) &&
                !gemm3_schedule(V, H, 128, GEMM3_PRO_NONE, 0, &sch_lm) && !sch_o.streamk && !sch_down.streamk && H / 128 <= 1024;
     cudaGetLastError();
+    // the chain needs every CTA co-resident (software grid barrier), the segment tables of the deferred reduction, at least
+    // as many gate_up tiles as ... units are clamped to the tile count, and one token row per CTA
+    const char* ce = getenv("B200_CHAIN");   // A/B knob: 0 keeps one launch per projection
+    chain_ok = fused_ok && deferred_ok && !(ce && atoi(ce) == 0) && chain_max_ctas(&chain_ctas) == 0 && chain_ctas >= 128 && chain_ctas >= sms / 2 * 2 &&
+               gemm_ws_bytes >= (48ull << 20) + static_cast<size_t>(chain_ctas) * 128 * 128 * 4;
+    if (chain_ok) {
+      CK(cudaMalloc(&chain_bar, 64));
+      CK(cudaMemset(chain_bar, 0, 64));
+    }
+    cudaGetLastError();
   }
 
   // ---- KV pool
@@ -631,7 +648,7 @@ int Engine::forward(const StepMeta& m, int32_t* dbuf, bool all_logits, bf16* log
   // Steps of at most 128 tokens (the decode steps: ~80% of the bench's steps, all of them weight streams) run the fused
   // chain: 4 GEMMs + attention per layer, the split-K reductions finished inside the GEMMs, RMSNorm / RoPE + KV write /
   // SiLU / residual add / argmax in their prologues and epilogues (gemm3_tcgen05.cu).
-  if (fused_ok && !all_logits && T <= 128 && m.S <= 128) return forward_fused(m, dbuf);
+  if (fused_ok && !all_logits && T <= 128 && m.S <= 128) return chain_ok ? forward_chain(m, dbuf) : forward_fused(m, dbuf);
   P(B200_K_EMBED); if (on(B200_K_EMBED)) rc |= embed_gather(embed, ids, res, T, H, V, stream); Q(); launched(1);
   // T <= 512: every GEMM dumps fp32 stream-K partials and its consumer (norm / rope / silu / argmax) sums them while
   // loading — no in-GEMM reduction handshake.  Larger steps use the in-kernel fix-up and bf16 intermediates.
@@ -783,6 +800,119 @@ int Engine::forward_fused(const StepMeta& m, int32_t* dbuf) {
     stats.kernel_launches += 3;
   }
   if (rc) return cuda_fail("forward_fused(head)", -2);
+  return 0;
+}
+
+// ------------------------------------------------------------------ forward pass, decode-shape projection chain (T <= 128)
+// embed -> norm -> qkv(0) [gemm3, RoPE + KV write in its epilogue] -> per layer: attention, then ONE persistent launch for
+// o_proj .. next layer's qkv (chain_tcgen05.cu) -> final norm of the sampled rows -> lm_head [gemm3, argmax candidates].
+int Engine::forward_chain(const StepMeta& m, int32_t* dbuf) {
+  const int T = m.T;
+  const int* ids = dbuf + m.off_ids;
+  const int* pos = dbuf + m.off_pos;
+  const int* slots = dbuf + m.off_slots;
+  const int* rows = dbuf + m.off_rows;
+  const AttnWork* dwork = reinterpret_cast<const AttnWork*>(dbuf + m.off_dwork);
+  const AttnWork* pwork = reinterpret_cast<const AttnWork*>(dbuf + m.off_pwork);
+  const int* btab = dbuf + m.off_btab;
+  const float scale = 1.0f / sqrtf(static_cast<float>(kD));
+  int rc = 0;
+  auto P = [&](int cls) {
+    if (!profiling) return;
+    if (prof_used + 2 > prof_events.size()) {
+      for (int i = 0; i < 2; ++i) { cudaEvent_t e; cudaEventCreate(&e); prof_events.push_back({cls, e}); }
+    }
+    prof_events[prof_used].first = cls;
+    cudaEventRecord(prof_events[prof_used].second, stream);
+  };
+  auto Q = [&]() {
+    if (!profiling) return;
+    cudaEventRecord(prof_events[prof_used + 1].second, stream);
+    prof_used += 2;
+  };
+  auto g3 = [&](const GemmPlan& pl, const CUtensorMap& tmx, int Tn, int epi) {
+    Gemm3Params p;
+    memset(&p, 0, sizeof(p));
+    p.tm_w = pl.tm_w;
+    p.tm_x = tmx;
+    p.N = pl.N; p.T = Tn; p.K = pl.K;
+    p.pro = GEMM3_PRO_NONE; p.epi = epi;
+    p.eps = cfg.rms_eps;
+    p.ws = gemm_ws; p.flags = g3_flags; p.epoch = ++g3_epoch;
+    p.n_valid = pl.N;
+    return p;
+  };
+  float* ws_sk = gemm_ws + (48ull << 20) / 4;   // gate_up neighbour slots live behind the deferred segments
+  auto deferred = [&](ChainGemm* g, const GemmPlan& pl, const CUtensorMap& tmx, bf16* out, int ldo) {
+    g->tm_w = pl.tm_w;
+    g->tm_x = tmx;
+    g->N = pl.N; g->K = pl.K;
+    g->units = gemm2_units_for(pl, 1);
+    g->mode = CHAIN_DEFERRED;
+    g->seg_table = pl.seg_table + pl.table_off[1];
+    g->out = out; g->ldo = ldo;
+  };
+  P(B200_K_EMBED); rc |= embed_gather(embed, ids, res, T, H, V, stream); Q();
+  P(B200_K_NORM); rc |= rmsnorm(res, nullptr, layers[0].norm1, normed, nullptr, T, H, cfg.rms_eps, stream); Q();
+  {
+    Gemm3Params p = g3(layers[0].p_qkv, xmap(xm_normed, 128), T, GEMM3_EPI_ROPE_KV);
+    p.out = qkv; p.ldo = QKV;
+    p.positions = pos; p.slots = slots; p.cos_sin = cos_sin; p.kv_layer = kv; p.Hq = Hq; p.Hkv = Hkv; p.max_pos = cfg.max_model_len;
+    P(B200_K_GEMM_QKV); rc |= gemm3_launch(p, sch_qkv, stream); Q();
+  }
+  stats.kernel_launches += 3;
+  for (int l = 0; l < L && !rc; ++l) {
+    Layer& ly = layers[l];
+    bf16* kv_l = kv + static_cast<size_t>(l) * kv_layer_elems;
+    if (m.nd) { P(B200_K_ATTN_DECODE); rc |= paged_attention(qkv, QKV, attn, Hq * kD, kv_l, btab, max_blocks_per_seq, dwork, m.nd, Hq, Hkv, scale, 1, stream); Q(); ++stats.kernel_launches; }
+    if (m.np) { P(B200_K_ATTN_PREFILL); rc |= prefill_attention(kv_l, btab, pwork, m.np, scale); Q(); ++stats.kernel_launches; }
+    ChainParams c;
+    memset(&c, 0, sizeof(c));
+    const bool last = l + 1 == L;
+    c.n_gemm = last ? 3 : 4;
+    c.T = T;
+    deferred(&c.g[0], ly.p_o, xmap(xm_attn, 128), x, H);
+    c.g[0].wait_barrier = 0; c.g[0].done_barrier = 1; c.g[0].reduce = CHAIN_REDUCE_RESADD_NORM; c.g[0].reduce_barrier = 2; c.g[0].norm_w = ly.norm2;
+    {
+      ChainGemm& g = c.g[1];
+      g.tm_w = ly.p_gu.tm_w; g.tm_x = xmap(xm_normed, 128);
+      g.N = 2 * I; g.K = H;
+      g.units = std::min(chain_ctas / 2, 2 * I / 256);
+      g.mode = CHAIN_SILU;
+      g.out = act; g.ldo = I;
+      g.wait_barrier = 2; g.done_barrier = 3; g.reduce = CHAIN_REDUCE_NONE;
+    }
+    deferred(&c.g[2], ly.p_down, xmap(xm_act, 128), x, H);
+    c.g[2].wait_barrier = 3; c.g[2].done_barrier = 4; c.g[2].reduce = CHAIN_REDUCE_RESADD_NORM;
+    c.g[2].reduce_barrier = last ? 0 : 5; c.g[2].norm_w = last ? nullptr : layers[l + 1].norm1;
+    if (!last) {
+      deferred(&c.g[3], layers[l + 1].p_qkv, xmap(xm_normed, 128), qkv, QKV);
+      c.g[3].wait_barrier = 5; c.g[3].done_barrier = 6; c.g[3].reduce = CHAIN_REDUCE_ROPE_KV; c.g[3].reduce_barrier = 0;
+      c.kv_layer = kv + static_cast<size_t>(l + 1) * kv_layer_elems;
+    }
+    c.ws_def = gemm_ws; c.ws_sk = ws_sk; c.flags = g3_flags; c.epoch = ++g3_epoch;
+    c.bar = chain_bar; c.bar_base = chain_bar_count;
+    chain_bar_count += static_cast<unsigned long long>(chain_ctas) * (last ? 4 : 6);
+    c.res = res; c.normed = normed; c.eps = cfg.rms_eps;
+    c.positions = pos; c.slots = slots; c.cos_sin = cos_sin; c.Hq = Hq; c.Hkv = Hkv; c.max_pos = cfg.max_model_len;
+    // profiling: the chain is timed as one unit under the gate_up class (its dominant phase)
+    P(B200_K_GEMM_GU); rc |= chain_launch(c, chain_ctas, stream); Q();
+    ++stats.kernel_launches;
+  }
+  if (rc) return cuda_fail("forward_chain", -2);
+  if (m.S > 0) {
+    P(B200_K_NORM); rc |= rmsnorm(res, nullptr, final_norm, last_hidden, rows, m.S, H, cfg.rms_eps, stream); Q();
+    Gemm3Params p = g3(p_lm, xmap(xm_last, 128), m.S, keep_logits ? GEMM3_EPI_PLAIN : GEMM3_EPI_ARGMAX);
+    p.out = logits; p.ldo = V; p.cand = cand;
+    P(B200_K_GEMM_LM); rc |= gemm3_launch(p, sch_lm, stream); Q();
+    P(B200_K_ARGMAX);
+    if (keep_logits) rc |= argmax_rows(logits, sampled, m.S, V, V, stream);
+    else rc |= argmax_candidates(cand, sampled, m.S, V / 128, stream);
+    Q();
+    last_S = m.S;
+    stats.kernel_launches += 3;
+  }
+  if (rc) return cuda_fail("forward_chain(head)", -2);
   return 0;
 }
 
