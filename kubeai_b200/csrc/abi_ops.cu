@@ -11,6 +11,7 @@
 #include "errors.h"
 #include "gemm.h"
 #include "gemm3.h"
+#include "chain.h"
 #include "kernels.h"
 
 namespace b200 {
@@ -190,6 +191,7 @@ int b200_set_gemm_variant(int32_t v) {
 int b200_op_gemm_trace(void* trace_dev) {
   gemm2_set_trace(static_cast<long long*>(trace_dev));
   g_gemm3_trace = static_cast<long long*>(trace_dev);   // b200_op_gemm3 launches stamp 8 values per CTA while this is set
+  chain_set_trace(static_cast<long long*>(trace_dev));  // chain launches: 40 slots x 148 CTAs x 32 stamps
   return 0;
 }
 

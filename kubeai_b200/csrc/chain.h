@@ -48,10 +48,12 @@ struct ChainParams {
   const __nv_bfloat16* cos_sin;
   __nv_bfloat16* kv_layer;       // KV pages of the layer whose qkv projection is phase 3
   int Hq, Hkv, max_pos;
+  long long* trace;              // debug: 32 %globaltimer stamps per CTA, or nullptr
 };
 
 int chain_smem_bytes();
 int chain_max_ctas(int* out);    // co-resident CTAs (148 on a B200): the grid of every chain launch
 int chain_launch(const ChainParams& p, int ctas, cudaStream_t st);
+void chain_set_trace(long long* dev);   // debug (b200_op_gemm_trace)
 
 }  // namespace b200

@@ -106,7 +106,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) chain_k
   float* red = reinterpret_cast<float*>(smem + (misc - smem_base) + 512);   // [8] block-reduction scratch
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + (tmem_slot - smem_base));
 
+  // optional phase trace (debug): 32 %globaltimer stamps per CTA
+  //   [4p+0] epilogue warps done with phase p's segments  [4p+1] done_barrier passed  [4p+2] elementwise phase done
+  //   [16+2p] first MMA of phase p  [17+2p] last MMA of phase p issued  [24+p] first token-tile load of phase p issued
+  //   [30] CTA start  [31] CTA end
+  auto mark = [&](int i) {
+    if (P.trace) {
+      long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      P.trace[static_cast<size_t>(blockIdx.x) * 32 + i] = t;
+    }
+  };
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 64) mark(30);
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
   const int unit = blockIdx.x >> 1;
@@ -200,6 +212,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) chain_k
           }
           if (ready) {
             const int stage = static_cast<int>(ib % kStages);
+            if (ib == base[ph]) mark(24 + ph);
             tma_load_2d_pair(smem_base + stage * kStageBytes + kABytes, &P.g[ph].tm_x, full_bar(stage), kb * kBlockK, row_half0, kEvictLast);
             ++ib;
             progressed = true;
@@ -229,6 +242,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) chain_k
           for (int kb = sg.kb0; kb < sg.kb1; ++kb) {
             mbar_wait(full_bar(stage), phase);
             tc_fence_after();
+            if (it == it_begin && kb == sg.kb0) mark(16 + 2 * p);
             const uint32_t sa = smem_base + stage * kStageBytes;
             const uint64_t a_desc = umma_desc_kmajor_sw128(sa);
             const uint64_t b_desc = umma_desc_kmajor_sw128(sa + kABytes);
@@ -249,6 +263,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) chain_k
           }
           it += sg.kb1 - sg.kb0;
         }
+        mark(17 + 2 * p);
       }
     }
   } else {
@@ -420,9 +435,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) chain_k
       }
 
       // ---- this CTA's part of projection p is out
+      if (et == 0) mark(4 * p);
       if (g.done_barrier > 0) grid_arrive(g.done_barrier);
       if (g.reduce == CHAIN_REDUCE_NONE) continue;
       grid_wait(g.done_barrier);
+      if (et == 0) mark(4 * p + 1);
 
       // ---- elementwise phase: token row blockIdx.x (T <= 128 <= CTAs), the projection's split tiles summed on load
       PartialView pv;
@@ -538,9 +555,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) chain_k
           }
         }
       }
+      if (et == 0) mark(4 * p + 2);
       if (g.reduce_barrier > 0) grid_arrive(g.reduce_barrier);
     }
   }
+  if (threadIdx.x == 64) mark(31);
 
   tc_fence_before();
   cluster_sync_all();
@@ -551,6 +570,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) chain_k
 }
 
 }  // namespace
+
+static long long* g_chain_trace = nullptr;
+static int g_chain_trace_launch = 0;
+void chain_set_trace(long long* dev) {   // debug: 40 slots of CTAs x 32 stamps, launch i writes slot i % 40
+  g_chain_trace = dev;
+  g_chain_trace_launch = 0;
+}
 
 int chain_smem_bytes() { return kSmemBytes; }
 
@@ -582,7 +608,9 @@ int chain_launch(const ChainParams& p, int ctas, cudaStream_t st) {
   static std::atomic<unsigned long long> attr_done{0};
   if (!ensure_dynamic_smem(chain_kernel, kSmemBytes, &attr_done)) return -3;
   if (p.T < 1 || p.T > kBN || p.T > ctas) return -1;
-  return launch_pdl(chain_kernel, dim3(ctas), dim3(kThreads), kSmemBytes, st, p) == cudaSuccess ? 0 : -4;
+  ChainParams q = p;
+  q.trace = g_chain_trace ? g_chain_trace + static_cast<size_t>(g_chain_trace_launch++ % 40) * 148 * 32 : nullptr;
+  return launch_pdl(chain_kernel, dim3(ctas), dim3(kThreads), kSmemBytes, st, q) == cudaSuccess ? 0 : -4;
 }
 
 }  // namespace b200
