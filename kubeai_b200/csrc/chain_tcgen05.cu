@@ -161,64 +161,73 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) chain_k
     // ------------------------------------------------------------ TMA producer: weights run ahead across phases, token
     // tiles of a phase wait for the grid barrier that publishes them
     if (lane == 0) {
-      // flattened iteration space over the phases
-      long long pb[kChainMaxGemm], pe[kChainMaxGemm], base[kChainMaxGemm + 1];
-      base[0] = 0;
-      for (int p = 0; p < P.n_gemm; ++p) {
-        phase_range(P.g[p], unit, &pb[p], &pe[p]);
-        base[p + 1] = base[p] + (pe[p] - pb[p]);
-      }
-      const long long n_it = base[P.n_gemm];
-      long long ia = 0, ib = 0;       // next flattened iteration whose A (weights) / B (tokens) load is to be issued
-      int pa = 0, pbx = 0;            // phases of ia / ib
+      // Two cursors walk this pair's iterations over all phases: `ca` issues weight loads (never waits for anything but a
+      // free ring slot), `cb` issues token-tile loads (waits for the phase's grid barrier).  Pure spinning: a __nanosleep in
+      // this loop let the ring run dry (measured: every mainloop 2x slower, profiles/r02_chain_trace.md).
+      struct Cur {
+        int ph, tile, kb, KB;
+        long long left;      // iterations left in the current phase
+        long long idx;       // flattened index
+      };
+      auto enter = [&](Cur& c) {   // position the cursor at the first iteration of the first non-empty phase >= c.ph
+        while (c.ph < P.n_gemm) {
+          long long b0, e0;
+          phase_range(P.g[c.ph], unit, &b0, &e0);
+          if (e0 > b0) {
+            c.KB = P.g[c.ph].K / kBlockK;
+            c.tile = static_cast<int>(b0 / c.KB);
+            c.kb = static_cast<int>(b0 - static_cast<long long>(c.tile) * c.KB);
+            c.left = e0 - b0;
+            return;
+          }
+          ++c.ph;
+        }
+      };
+      auto advance = [&](Cur& c) {
+        ++c.idx;
+        if (--c.left == 0) {
+          ++c.ph;
+          enter(c);
+        } else if (++c.kb == c.KB) {
+          c.kb = 0;
+          ++c.tile;
+        }
+      };
+      Cur ca{0, 0, 0, 1, 0, 0}, cb{0, 0, 0, 1, 0, 0};
+      enter(ca);
+      enter(cb);
       bool waited_dep = false;
       int passed = 0;                 // highest grid barrier known to have been passed
-      auto locate = [&](long long i, int* ph, int* tile, int* kb) {
-        while (i >= base[*ph + 1]) ++*ph;
-        const long long it = pb[*ph] + (i - base[*ph]);
-        const int KB = P.g[*ph].K / kBlockK;
-        *tile = static_cast<int>(it / KB);
-        *kb = static_cast<int>(it - static_cast<long long>(*tile) * KB);
-      };
-      while (ib < n_it) {
-        bool progressed = false;
-        if (ia < n_it && ia < ib + kStages) {
-          const int stage = static_cast<int>(ia % kStages);
-          const uint32_t use = static_cast<uint32_t>(ia / kStages);
+      while (cb.ph < P.n_gemm) {
+        if (ca.ph < P.n_gemm && ca.idx < cb.idx + kStages) {
+          const int stage = static_cast<int>(ca.idx % kStages);
+          const uint32_t use = static_cast<uint32_t>(ca.idx / kStages);
           if (use == 0 || mbar_try_wait(empty_bar(stage), (use & 1u) ^ 1u)) {
-            int tile, kb;
-            locate(ia, &pa, &tile, &kb);
             if (leader) mbar_arrive_expect_tx(full_bar(stage), 2u * kStageBytes);
-            tma_load_2d_pair(smem_base + stage * kStageBytes, &P.g[pa].tm_w, full_bar(stage), kb * kBlockK,
-                             tile * 2 * kSlab + static_cast<int>(rank) * kSlab, kEvictFirst);
-            ++ia;
-            progressed = true;
+            tma_load_2d_pair(smem_base + stage * kStageBytes, &P.g[ca.ph].tm_w, full_bar(stage), ca.kb * kBlockK,
+                             ca.tile * 2 * kSlab + static_cast<int>(rank) * kSlab, kEvictFirst);
+            advance(ca);
           }
         }
-        if (ib < ia) {
-          int tile, kb;
-          int ph = pbx;
-          locate(ib, &ph, &tile, &kb);
-          pbx = ph;
-          const int need = P.g[ph].wait_barrier;
-          bool ready = true;
+        if (cb.idx < ca.idx) {
           if (!waited_dep) {          // first token tile of the launch: the upstream kernel (attention) must be complete
             griddep_wait();
             waited_dep = true;
           }
-          if (need > passed) {
-            if (ld_acquire_u64(P.bar) >= bar_target(need)) passed = need;
-            else ready = false;
-          }
-          if (ready) {
-            const int stage = static_cast<int>(ib % kStages);
-            if (ib == base[ph]) mark(24 + ph);
-            tma_load_2d_pair(smem_base + stage * kStageBytes + kABytes, &P.g[ph].tm_x, full_bar(stage), kb * kBlockK, row_half0, kEvictLast);
-            ++ib;
-            progressed = true;
+          const int need = P.g[cb.ph].wait_barrier;
+          if (need > passed && ld_acquire_u64(P.bar) >= bar_target(need)) passed = need;
+          if (need <= passed) {
+            const int stage = static_cast<int>(cb.idx % kStages);
+            if (cb.left == 0) {}
+            long long b0, e0;
+            if (P.trace) {
+              phase_range(P.g[cb.ph], unit, &b0, &e0);
+              if (cb.left == e0 - b0) mark(24 + cb.ph);
+            }
+            tma_load_2d_pair(smem_base + stage * kStageBytes + kABytes, &P.g[cb.ph].tm_x, full_bar(stage), cb.kb * kBlockK, row_half0, kEvictLast);
+            advance(cb);
           }
         }
-        if (!progressed) __nanosleep(20);
       }
     }
   } else if (warp == 1) {
@@ -286,7 +295,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) chain_k
       if (et == 0) {
         if (k > 1) {
           const unsigned long long prev = bar_target(k - 1);
-          while (ld_acquire_u64(P.bar) < prev) __nanosleep(40);
+          while (ld_acquire_u64(P.bar) < prev) {
+          }
         }
         atomicAdd(P.bar, 1ULL);
       }
@@ -294,7 +304,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) chain_k
     auto grid_wait = [&](int k) {
       if (et == 0) {
         const unsigned long long tgt = bar_target(k);
-        while (ld_acquire_u64(P.bar) < tgt) __nanosleep(40);
+        while (ld_acquire_u64(P.bar) < tgt) {
+        }
       }
       epi_bar();
     };
@@ -458,7 +469,34 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) chain_k
         float ss = 0.f;
         constexpr int kMaxV = 8;                 // H <= 8192
         uint4 zv[kMaxV];
-        if (t < T) {
+        if (t < T && H == 4096) {
+          // the common shape: all four vectors' table entries, residual loads and segment loads issued before the first add
+          // (one L2 round trip instead of four)
+          int nn[4];
+          int2 ent[4];
+          uint4 rr[4];
+          float xa[4][8];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            nn[i] = (et + i * 128) * 8;
+            rr[i] = *reinterpret_cast<const uint4*>(P.res + static_cast<size_t>(t) * H + nn[i]);
+          }
+          partial_entries<4>(pv, t, nn, ent);
+          load8xM_entries<4>(pv, ent, t, nn, xa);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            V8 r, z;
+            r.u = rr[i];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              z.h[e] = __float2bfloat16_rn(xa[i][e] + __bfloat162float(r.h[e]));
+              const float zf = __bfloat162float(z.h[e]);
+              ss += zf * zf;
+            }
+            *reinterpret_cast<uint4*>(P.res + static_cast<size_t>(t) * H + nn[i]) = z.u;
+            zv[i] = z.u;
+          }
+        } else if (t < T) {
 #pragma unroll
           for (int i = 0; i < kMaxV; ++i) {
             const int idx = et + i * 128;

@@ -13,10 +13,10 @@ from kubeai_b200.engine import Engine, default_config  # noqa: E402
 layers = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 e = Engine(default_config(manual_step=1, num_layers=layers, max_num_seqs=128, max_batched_tokens=1536, max_model_len=2048, kv_fraction=0.3))
 rng = np.random.default_rng(0)
-rids = [e.submit(rng.integers(0, 128000, size=int(rng.integers(380, 480))).tolist(), max_tokens=40) for _ in range(128)]
-for i in range(60):
+rids = [e.submit(rng.integers(0, 128000, size=int(rng.integers(380, 480))).tolist(), max_tokens=400) for _ in range(128)]
+for i in range(120):
     ran, info = e.step()
-    if info.decode_seqs == 128 and info.prefill_seqs == 0 and i > 45:
+    if info.decode_seqs == 128 and info.prefill_seqs == 0:
         break
 buf = torch.zeros(40 * 148 * 32, dtype=torch.int64, device="cuda")
 lib().b200_op_gemm_trace(C.c_void_p(buf.data_ptr()))
