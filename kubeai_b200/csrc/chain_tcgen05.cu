@@ -193,9 +193,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) chain_k
           ++c.tile;
         }
       };
-      Cur ca{0, 0, 0, 1, 0, 0}, cb{0, 0, 0, 1, 0, 0};
+      Cur ca{0, 0, 0, 1, 0, 0}, cb{0, 0, 0, 1, 0, 0}, cp{0, 0, 0, 1, 0, 0};
       enter(ca);
       enter(cb);
+      enter(cp);
+      // While the token tiles are blocked (upstream kernel still running, or a grid barrier not yet passed) and the ring is
+      // full, the weight stream would stop: instead the next kPrefetch weight boxes beyond the ring are pulled into L2, so the
+      // ring refills from L2 once the phase runs.  Only in those gaps: in the steady mainloop HBM is busy anyway.
+      constexpr int kPrefetch = 32;
       bool waited_dep = false;
       int passed = 0;                 // highest grid barrier known to have been passed
       while (cb.ph < P.n_gemm) {
@@ -209,23 +214,32 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) chain_k
             advance(ca);
           }
         }
+        bool blocked = false;
         if (cb.idx < ca.idx) {
           if (!waited_dep) {          // first token tile of the launch: the upstream kernel (attention) must be complete
+            // (griddepcontrol.wait blocks: pull this pair's first weights into L2 before sitting in it)
+            while (cp.ph < P.n_gemm && cp.idx < ca.idx) advance(cp);
+            for (int i = 0; i < kPrefetch && cp.ph < P.n_gemm; ++i) {
+              tma_prefetch_l2_2d(&P.g[cp.ph].tm_w, cp.kb * kBlockK, cp.tile * 2 * kSlab + static_cast<int>(rank) * kSlab);
+              advance(cp);
+            }
             griddep_wait();
             waited_dep = true;
           }
           const int need = P.g[cb.ph].wait_barrier;
           if (need > passed && ld_acquire_u64(P.bar) >= bar_target(need)) passed = need;
+          blocked = need > passed;
           if (need <= passed) {
             const int stage = static_cast<int>(cb.idx % kStages);
-            if (cb.left == 0) {}
-            long long b0, e0;
-            if (P.trace) {
-              phase_range(P.g[cb.ph], unit, &b0, &e0);
-              if (cb.left == e0 - b0) mark(24 + cb.ph);
-            }
             tma_load_2d_pair(smem_base + stage * kStageBytes + kABytes, &P.g[cb.ph].tm_x, full_bar(stage), cb.kb * kBlockK, row_half0, kEvictLast);
             advance(cb);
+          }
+        }
+        if (blocked && ca.idx >= cb.idx + kStages) {   // ring full of the next phase's weights, token tiles not published yet
+          while (cp.ph < P.n_gemm && cp.idx < ca.idx) advance(cp);
+          if (cp.ph < P.n_gemm && cp.idx < ca.idx + kPrefetch) {
+            tma_prefetch_l2_2d(&P.g[cp.ph].tm_w, cp.kb * kBlockK, cp.tile * 2 * kSlab + static_cast<int>(rank) * kSlab);
+            advance(cp);
           }
         }
       }
@@ -424,7 +438,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) chain_k
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
                   const float gv = __bfloat162float(gg.h[e]);
-                  const __nv_bfloat16 s = __float2bfloat16_rn(gv / (1.0f + expf(-gv)));
+                  const __nv_bfloat16 s = silu_bf16(gv);
                   o.h[e] = __float2bfloat16_rn(__bfloat162float(s) * __bfloat162float(uu.h[e]));
                 }
                 if (t < T) *reinterpret_cast<uint4*>(g.out + static_cast<size_t>(t) * g.ldo + slab * 64 + vv * 8) = o.u;
@@ -449,10 +463,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) chain_k
       if (et == 0) mark(4 * p);
       if (g.done_barrier > 0) grid_arrive(g.done_barrier);
       if (g.reduce == CHAIN_REDUCE_NONE) continue;
-      grid_wait(g.done_barrier);
-      if (et == 0) mark(4 * p + 1);
 
-      // ---- elementwise phase: token row blockIdx.x (T <= 128 <= CTAs), the projection's split tiles summed on load
+      // ---- elementwise phase: token row blockIdx.x (T <= 128 <= CTAs), the projection's split tiles summed on load.
+      // Everything that does not come from the projection — segment-table entries (static), the residual row (final since
+      // the previous elementwise phase), the norm weight — is loaded BEFORE the barrier wait.
       PartialView pv;
       pv.ws = P.ws_def;
       pv.table = g.seg_table;
@@ -469,19 +483,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) chain_k
         float ss = 0.f;
         constexpr int kMaxV = 8;                 // H <= 8192
         uint4 zv[kMaxV];
-        if (t < T && H == 4096) {
-          // the common shape: all four vectors' table entries, residual loads and segment loads issued before the first add
-          // (one L2 round trip instead of four)
-          int nn[4];
-          int2 ent[4];
-          uint4 rr[4];
-          float xa[4][8];
+        const bool fast = t < T && H == 4096;
+        int nn[4] = {0, 0, 0, 0};
+        int2 ent[4];
+        uint4 rr[4], wpre[4];
+        if (fast) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             nn[i] = (et + i * 128) * 8;
             rr[i] = *reinterpret_cast<const uint4*>(P.res + static_cast<size_t>(t) * H + nn[i]);
+            if (nw) wpre[i] = __ldg(reinterpret_cast<const uint4*>(nw) + et + i * 128);
           }
           partial_entries<4>(pv, t, nn, ent);
+        }
+        grid_wait(g.done_barrier);
+        if (et == 0) mark(4 * p + 1);
+        if (fast) {
+          // the common shape: all four vectors' segment loads issued before the first add (one L2 round trip)
+          float xa[4][8];
           load8xM_entries<4>(pv, ent, t, nn, xa);
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
@@ -524,7 +543,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) chain_k
             for (int i = 0; i < kMaxV; ++i) {
               const int idx = et + i * 128;
               if (idx * 8 < H) {
-                const uint4 wv = __ldg(reinterpret_cast<const uint4*>(nw) + idx);
+                const uint4 wv = fast ? wpre[i & 3] : __ldg(reinterpret_cast<const uint4*>(nw) + idx);
                 const uint32_t zw[4] = {zv[i].x, zv[i].y, zv[i].z, zv[i].w}, ww[4] = {wv.x, wv.y, wv.z, wv.w};
                 uint32_t ow[4];
 #pragma unroll
@@ -538,7 +557,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) chain_k
             }
           }
         }
-      } else if (g.reduce == CHAIN_REDUCE_ROPE_KV && t < T) {
+      } else if (g.reduce == CHAIN_REDUCE_ROPE_KV) {
+        grid_wait(g.done_barrier);
+        if (et == 0) mark(4 * p + 1);
+        if (t < T) {
         // neox RoPE on the q / k heads of token t, q back into the qkv buffer, k / v into the paged cache
         // (elementwise.cu rope_kv_kernel, 128 threads)
         constexpr int D = 128, HALF = 64;
@@ -591,6 +613,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) chain_k
             val.w = pack_bf16x2(fv[6], fv[7]);
             *reinterpret_cast<uint4*>(vbase + (static_cast<size_t>(head) * 16 + off) * D + c * 8) = val;
           }
+        }
         }
       }
       if (et == 0) mark(4 * p + 2);

@@ -309,7 +309,7 @@ __global__ void silu_mul_kernel(const __nv_bfloat16* __restrict__ gu, __nv_bfloa
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float gv = x[k][j];
-      const __nv_bfloat16 s = __float2bfloat16_rn(gv / (1.0f + expf(-gv)));
+      const __nv_bfloat16 s = silu_bf16(gv);
       r.h[j] = __float2bfloat16_rn(__bfloat162float(s) * x[VPT + k][j]);
     }
     o[i] = r.u;

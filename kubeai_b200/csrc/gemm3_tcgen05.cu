@@ -522,7 +522,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm3_kernel(const __grid_constan
 #pragma unroll
               for (int e = 0; e < 8; ++e) {
                 const float gv = __bfloat162float(g.h[e]);
-                const __nv_bfloat16 s = __float2bfloat16_rn(gv / (1.0f + expf(-gv)));
+                const __nv_bfloat16 s = silu_bf16(gv);
                 o.h[e] = __float2bfloat16_rn(__bfloat162float(s) * __bfloat162float(u.h[e]));
               }
               if (t < T) *reinterpret_cast<uint4*>(P.out + static_cast<size_t>(t) * P.ldo + slab * 64 + vv * 8) = o.u;

@@ -240,6 +240,19 @@ __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+// SiLU in fp32, rounded once to bf16 (vllm activation.py:138-141: silu(gate) is rounded before the multiply with up).
+// Fast exp / reciprocal: their fp32 error (~2 ulp) disappears in the bf16 rounding except at rounding boundaries; every path
+// (elementwise.cu, gemm3, chain) uses this one function so that they stay bit-identical to each other.
+__device__ __forceinline__ __nv_bfloat16 silu_bf16(float g) {
+  return __float2bfloat16_rn(__fdividef(g, 1.0f + __expf(-g)));
+}
+
+// L2 prefetch of one box of a tiled tensor map (no shared-memory destination, no completion to wait for)
+__device__ __forceinline__ void tma_prefetch_l2_2d(const void* tmap, int32_t c0, int32_t c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1)
+               : "memory");
+}
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
