@@ -200,7 +200,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) chain_k
       // While the token tiles are blocked (upstream kernel still running, or a grid barrier not yet passed) and the ring is
       // full, the weight stream would stop: instead the next kPrefetch weight boxes beyond the ring are pulled into L2, so the
       // ring refills from L2 once the phase runs.  Only in those gaps: in the steady mainloop HBM is busy anyway.
-      constexpr int kPrefetch = 32;
+      const int kPrefetch = P.prefetch;
       bool waited_dep = false;
       int passed = 0;                 // highest grid barrier known to have been passed
       while (cb.ph < P.n_gemm) {

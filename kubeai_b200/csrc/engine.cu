@@ -891,6 +891,8 @@ int Engine::forward_chain(const StepMeta& m, int32_t* dbuf) {
       c.kv_layer = kv + static_cast<size_t>(l + 1) * kv_layer_elems;
     }
     c.ws_def = gemm_ws; c.ws_sk = ws_sk; c.flags = g3_flags; c.epoch = ++g3_epoch;
+    static const int pf = [] { const char* e = getenv("B200_CHAIN_PREFETCH"); return e ? atoi(e) : 32; }();
+    c.prefetch = pf;
     c.bar = chain_bar; c.bar_base = chain_bar_count;
     chain_bar_count += static_cast<unsigned long long>(chain_ctas) * (last ? 4 : 6);
     c.res = res; c.normed = normed; c.eps = cfg.rms_eps;
