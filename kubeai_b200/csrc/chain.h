@@ -48,6 +48,7 @@ struct ChainParams {
   const __nv_bfloat16* cos_sin;
   __nv_bfloat16* kv_layer;       // KV pages of the layer whose qkv projection is phase 3
   int Hq, Hkv, max_pos;
+  int dbg;                       // timing experiments only: 1 = epilogues release the accumulators undrained
   int prefetch;                  // weight boxes (16 KB) a CTA pulls into L2 ahead of its ring while its token tiles are blocked
   long long* trace;              // debug: 32 %globaltimer stamps per CTA, or nullptr
 };

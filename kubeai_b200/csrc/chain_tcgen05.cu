@@ -355,7 +355,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) chain_k
         const bool head_only = silu && sg.kb0 == 0 && sg.kb1 < KB;
         const bool tail_only = silu && sg.kb0 > 0;
 
-        if (head_only && et == 0) {   // partner's tail of this tile was parked long ago: fetch it under our mainloop
+        if (head_only && et == 0 && !(P.dbg & 1)) {   // partner's tail of this tile was parked long ago: fetch it under our mainloop
           const int* flag = P.flags + (unit + 1) * 2 + static_cast<int>(rank);
           while (ld_acquire_gpu(flag) != P.epoch) __nanosleep(32);
           asm volatile("fence.proxy.async;" ::: "memory");
@@ -369,7 +369,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) chain_k
         tc_fence_after();
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kBN;
 
-        if (tail_only || (!silu && !complete)) {
+        if (P.dbg & 1) {   // timing experiment: accumulators are released undrained (results are garbage)
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (leader) mbar_arrive(tempty_bar(acc));
+            else mbar_arrive_cluster(tempty_bar(acc), 0);
+          }
+          if (tail_only) {
+            epi_bar();
+            if (et == 0) st_release_gpu(P.flags + unit * 2 + static_cast<int>(rank), P.epoch);
+          }
+        } else if (tail_only || (!silu && !complete)) {
           // fp32 partial [token][128 rows] to L2: the stream-K neighbour (gate_up) or the elementwise phase sums it
           float* dst;
           if (silu) {

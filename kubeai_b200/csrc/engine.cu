@@ -893,6 +893,8 @@ int Engine::forward_chain(const StepMeta& m, int32_t* dbuf) {
     c.ws_def = gemm_ws; c.ws_sk = ws_sk; c.flags = g3_flags; c.epoch = ++g3_epoch;
     static const int pf = [] { const char* e = getenv("B200_CHAIN_PREFETCH"); return e ? atoi(e) : 32; }();
     c.prefetch = pf;
+    static const int cdbg = [] { const char* e = getenv("B200_CHAIN_DBG"); return e ? atoi(e) : 0; }();
+    c.dbg = cdbg;
     c.bar = chain_bar; c.bar_base = chain_bar_count;
     chain_bar_count += static_cast<unsigned long long>(chain_ctas) * (last ? 4 : 6);
     c.res = res; c.normed = normed; c.eps = cfg.rms_eps;
