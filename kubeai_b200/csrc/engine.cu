@@ -537,8 +537,11 @@ int Engine::alloc_all() {
     cudaGetLastError();
     // the chain needs every CTA co-resident (software grid barrier), the segment tables of the deferred reduction, at least
     // as many gate_up tiles as ... units are clamped to the tile count, and one token row per CTA
-    const char* ce = getenv("B200_CHAIN");   // A/B knob: 0 keeps one launch per projection
-    chain_ok = fused_ok && deferred_ok && !(ce && atoi(ce) == 0) && chain_max_ctas(&chain_ctas) == 0 && chain_ctas >= 128 && chain_ctas >= sms / 2 * 2 &&
+    // Opt-in (B200_CHAIN=1): on the same box the chain measured 6.42 ms per decode step against 5.95 ms for one fused launch
+    // per projection and 6.14 ms unfused (profiles/r02_decode_paths.md) — its phases stream at the same in-step rate, but the
+    // four barrier gaps (~10 us each) and the lower SM clock under the power cap cost more than the launches it removes.
+    const char* ce = getenv("B200_CHAIN");
+    chain_ok = fused_ok && deferred_ok && (ce && atoi(ce) != 0) && chain_max_ctas(&chain_ctas) == 0 && chain_ctas >= 128 && chain_ctas >= sms / 2 * 2 &&
                gemm_ws_bytes >= (48ull << 20) + static_cast<size_t>(chain_ctas) * 128 * 128 * 4;
     if (chain_ok) {
       CK(cudaMalloc(&chain_bar, 64));

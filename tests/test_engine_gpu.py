@@ -336,14 +336,14 @@ def test_create_time_validation_of_pool_and_shapes():
 
 
 def test_decode_paths_agree_token_for_token(oracle, monkeypatch):
-    """The three decode paths — unfused kernels (B200_FUSED_DECODE=0), one fused launch per projection (B200_CHAIN=0) and
-    the persistent projection chain (default) — keep the same rounding points and segment orders: same greedy streams, and
+    """The three decode paths — unfused kernels (B200_FUSED_DECODE=0), one fused launch per projection (default) and the
+    persistent projection chain (B200_CHAIN=1) — keep the same rounding points and segment orders: same greedy streams, and
     all of them the oracle's wherever its margin is not a rounding coin-flip."""
     from kubeai_b200.engine import Engine, mini_config
     rng = np.random.default_rng(11)
     prompts = [rng.integers(0, 512, size=n).tolist() for n in (5, 17, 40, 64, 90, 121, 33, 8)]
     outs = {}
-    for name, env in (("unfused", {"B200_FUSED_DECODE": "0"}), ("per_gemm", {"B200_CHAIN": "0"}), ("chain", {})):
+    for name, env in (("unfused", {"B200_FUSED_DECODE": "0"}), ("per_gemm", {}), ("chain", {"B200_CHAIN": "1"})):
         for k in ("B200_FUSED_DECODE", "B200_CHAIN"):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
