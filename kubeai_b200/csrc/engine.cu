@@ -12,6 +12,7 @@
 #include <cuda_runtime.h>
 #include <nvtx3/nvToolsExt.h>
 #include <math.h>
+#include <pthread.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -1305,6 +1306,9 @@ void Engine::fail_all() {
 
 void Engine::loop() {
   cudaSetDevice(cfg.device);
+  char tname[16];
+  snprintf(tname, sizeof(tname), "b200-step-%d", cfg.device);   // visible in /proc/<pid>/task/*/stat and top -H
+  pthread_setname_np(pthread_self(), tname);
   InFlight& f = inflight_;
   while (!stop) {
     StepMeta m;
