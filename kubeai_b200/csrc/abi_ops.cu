@@ -11,6 +11,7 @@
 #include "errors.h"
 #include "gemm.h"
 #include "gemm3.h"
+#include "epi_pass.cuh"
 #include "chain.h"
 #include "kernels.h"
 
@@ -145,6 +146,31 @@ int b200_op_gemm3(const b200_gemm3_args* a, void* stream, int32_t* schedule_out)
     if (cudaMalloc(&cand, sizeof(float2) * 128 * 4096) != cudaSuccess) return B200_ERR_OOM;
   }
   if (a->epi == GEMM3_EPI_ARGMAX && (a->N / 128 > 4096 || !a->argmax_out)) { set_error("b200_op_gemm3: argmax needs argmax_out and N <= 524288"); return B200_ERR_INVALID; }
+  if (a->T > 128) {
+    // steps of more than 128 tokens: the pair kernel (gemm2) with the same fused epilogues, split tiles finished in-kernel
+    if (a->pro != GEMM3_PRO_NONE || a->epi == GEMM3_EPI_ARGMAX || a->normed_out || gemm_variant() != 2) {
+      set_error("b200_op_gemm3: T > 128 serves PRO_NONE with the PLAIN / RESADD / SILU / ROPE_KV epilogues");
+      return B200_ERR_INVALID;
+    }
+    GemmPlan plan;
+    int rc = gemm_plan_init(&plan, a->w, a->N, a->K, a->K, g_ws, g_counters, 0);
+    if (rc) return cuda_fail("gemm_plan_init", rc);
+    plan.ws_bytes = g_ws_bytes;
+    const int bn = a->force > 0 ? a->force : gemm_block_n_for(a->T);   // force = token-tile size (256 / 512) in this regime
+    CUtensorMap tmx;
+    rc = gemm_make_x_map(&tmx, a->x, a->x_rows, a->K, a->K, bn);
+    if (rc) return cuda_fail("gemm_make_x_map", rc);
+    Gemm2Epi e;
+    memset(&e, 0, sizeof(e));
+    e.epi = a->epi;
+    e.out = static_cast<__nv_bfloat16*>(a->out); e.ldo = a->ldo;
+    e.positions = a->positions; e.slots = a->slots; e.cos_sin = static_cast<const __nv_bfloat16*>(a->cos_sin);
+    e.kv_layer = static_cast<__nv_bfloat16*>(a->kv_layer); e.Hq = a->q_heads; e.Hkv = a->kv_heads; e.max_pos = a->max_pos;
+    e.flags = flags; e.epoch = ++epoch;
+    if (schedule_out) { schedule_out[0] = bn; schedule_out[1] = 2; schedule_out[2] = 2 * gemm2_units_for(plan, (a->T + bn - 1) / bn); }
+    rc = gemm2_run_fused(plan, tmx, bn, a->T, e, st);
+    return rc ? cuda_fail("gemm2_run_fused", rc) : 0;
+  }
   Gemm3Schedule sch;
   int rc = gemm3_schedule(a->N, a->K, a->T, a->pro, a->force, &sch);
   if (rc) { set_error("b200_op_gemm3: shape / schedule not served (rc=%d, N=%d K=%d T=%d force=%d)", rc, a->N, a->K, a->T, a->force); return B200_ERR_INVALID; }

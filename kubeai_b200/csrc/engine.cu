@@ -33,6 +33,7 @@
 #include "errors.h"
 #include "gemm.h"
 #include "gemm3.h"
+#include "epi_pass.cuh"
 #include "chain.h"
 #include "kernels.h"
 #include "hostutil.h"
@@ -253,6 +254,7 @@ struct Engine {
   Gemm3Schedule sch_qkv, sch_o, sch_gu, sch_down, sch_lm;
   // projection chain (chain_tcgen05.cu): o -> norm -> gate_up -> down -> norm -> next qkv -> rope in one persistent launch
   bool chain_ok = false;
+  bool fused2_ok = false;   // steps of more than 128 tokens: pair kernel with fused epilogues (gemm2 mode 2)
   int chain_ctas = 0;
   unsigned long long* chain_bar = nullptr;
   unsigned long long chain_bar_count = 0;   // host mirror of the grid-barrier counter
@@ -334,6 +336,14 @@ struct Engine {
     const int bn = gemm_block_n_for(T);
     ++stats.kernel_launches;
     return gemm_run(p, xmap(xm, bn), bn, out, ldo, T, stream);
+  }
+  // GEMM of a step of more than 128 tokens with a fused epilogue (gemm2 mode 2): split tiles finished in-kernel
+  int gemm_f2(const GemmPlan& p, const XMaps& xm, int T, Gemm2Epi e) {
+    const int bn = gemm_block_n_for(T);
+    ++stats.kernel_launches;
+    e.flags = g3_flags;
+    e.epoch = ++g3_epoch;
+    return gemm2_run_fused(p, xmap(xm, bn), bn, T, e, stream);
   }
   // GEMM that leaves its stream-K segments as fp32 partials for the next kernel to sum (partials.cuh)
   int gemm_def(const GemmPlan& p, const XMaps& xm, void* out, int ldo, int T, PartialView* pv) {
@@ -541,6 +551,11 @@ int Engine::alloc_all() {
     // Opt-in (B200_CHAIN=1): on the same box the chain measured 6.42 ms per decode step against 5.95 ms for one fused launch
     // per projection and 6.14 ms unfused (profiles/r02_decode_paths.md) — its phases stream at the same in-step rate, but the
     // four barrier gaps (~10 us each) and the lower SM clock under the power cap cost more than the launches it removes.
+    {
+      const char* pe = getenv("B200_FUSED_PREFILL");   // A/B knob: 0 keeps the larger steps on fp32 segments + elementwise kernels
+      fused2_ok = !(pe && atoi(pe) == 0) && gemm_variant() == 2 && QKV % 256 == 0 && H % 256 == 0 && (2 * I) % 256 == 0 && kD == 128 &&
+                  gemm_ws_bytes >= static_cast<size_t>(sms / 2) * 2 * 512 * 128 * sizeof(float);
+    }
     const char* ce = getenv("B200_CHAIN");
     chain_ok = fused_ok && deferred_ok && (ce && atoi(ce) != 0) && chain_max_ctas(&chain_ctas) == 0 && chain_ctas >= 128 && chain_ctas >= sms / 2 * 2 &&
                gemm_ws_bytes >= (48ull << 20) + static_cast<size_t>(chain_ctas) * 128 * 128 * 4;
@@ -662,6 +677,47 @@ int Engine::forward(const StepMeta& m, int32_t* dbuf, bool all_logits, bf16* log
   }();
   const bool dfr = deferred_ok && !all_logits && T <= defer_max_t;
   PartialView pv_x = no_partials();  // partials of the GEMM whose output is `x` (o_proj / down_proj)
+  // Steps of more than 128 tokens (prefill bursts and mixed steps): the pair kernel finishes its split tiles in-kernel and
+  // RoPE + KV write, the residual adds and SiLU*up ride in its epilogues (gemm2 mode 2, epi_pass.cuh); the two RMSNorms
+  // of a layer stay standalone kernels over the bf16 residual.  profiles/r02_prefill_fused.md.
+  const bool f2 = fused2_ok && !all_logits;
+  for (int l = 0; l < L && !rc && f2; ++l) {
+    Layer& ly = layers[l];
+    bf16* kv_l = kv + static_cast<size_t>(l) * kv_layer_elems;
+    Gemm2Epi e;
+    memset(&e, 0, sizeof(e));
+    P(B200_K_NORM); if (on(B200_K_NORM)) rc |= rmsnorm(res, nullptr, ly.norm1, normed, nullptr, T, H, cfg.rms_eps, stream); Q();
+    e.epi = GEMM3_EPI_ROPE_KV; e.out = qkv; e.ldo = QKV; e.positions = pos; e.slots = slots; e.cos_sin = cos_sin; e.kv_layer = kv_l;
+    e.Hq = Hq; e.Hkv = Hkv; e.max_pos = cfg.max_model_len;
+    P(B200_K_GEMM_QKV); if (on(B200_K_GEMM_QKV)) rc |= gemm_f2(ly.p_qkv, xm_normed, T, e); Q();
+    if (m.nd) { P(B200_K_ATTN_DECODE); if (on(B200_K_ATTN_DECODE)) rc |= paged_attention(qkv, QKV, attn, Hq * kD, kv_l, btab, max_blocks_per_seq, dwork, m.nd, Hq, Hkv, scale, 1, stream); Q(); launched(1); }
+    if (m.np) { P(B200_K_ATTN_PREFILL); if (on(B200_K_ATTN_PREFILL)) rc |= prefill_attention(kv_l, btab, pwork, m.np, scale); Q(); launched(1); }
+    memset(&e, 0, sizeof(e));
+    e.epi = GEMM3_EPI_RESADD; e.out = res; e.ldo = H;
+    P(B200_K_GEMM_O); if (on(B200_K_GEMM_O)) rc |= gemm_f2(ly.p_o, xm_attn, T, e); Q();
+    P(B200_K_NORM); if (on(B200_K_NORM)) rc |= rmsnorm(res, nullptr, ly.norm2, normed, nullptr, T, H, cfg.rms_eps, stream); Q();
+    Gemm2Epi g;
+    memset(&g, 0, sizeof(g));
+    g.epi = GEMM3_EPI_SILU; g.out = act; g.ldo = I;
+    P(B200_K_GEMM_GU); if (on(B200_K_GEMM_GU)) rc |= gemm_f2(ly.p_gu, xm_normed, T, g); Q();
+    P(B200_K_GEMM_DOWN); if (on(B200_K_GEMM_DOWN)) rc |= gemm_f2(ly.p_down, xm_act, T, e); Q();
+    launched(2);
+  }
+  if (f2) {
+    if (rc) return cuda_fail("forward", -2);
+    if (m.S > 0) {
+      P(B200_K_NORM); rc |= rmsnorm(res, nullptr, final_norm, last_hidden, rows, m.S, H, cfg.rms_eps, stream); Q();
+      PartialView pv = no_partials();
+      P(B200_K_GEMM_LM);
+      if (dfr && !keep_logits) rc |= gemm_def(p_lm, xm_last, logits, V, m.S, &pv); else rc |= gemm(p_lm, xm_last, logits, V, m.S);
+      Q();
+      last_S = m.S;
+      P(B200_K_ARGMAX); rc |= argmax_rows(logits, sampled, m.S, V, V, stream, pv); Q();
+      launched(2);
+    }
+    if (rc) return cuda_fail("forward(head)", -2);
+    return 0;
+  }
   for (int l = 0; l < L && !rc; ++l) {
     Layer& ly = layers[l];
     bf16* kv_l = kv + static_cast<size_t>(l) * kv_layer_elems;

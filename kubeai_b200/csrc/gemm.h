@@ -58,6 +58,10 @@ void gemm_plan_destroy(GemmPlan* p);
 size_t gemm_deferred_ws_bytes(int max_ctas);
 int gemm_run_deferred(const GemmPlan& p, const CUtensorMap& tm_x, int block_n, void* out, int ldo, int T, cudaStream_t st,
                       PartialView* view);
+// Fused mode (variant 2, steps of more than 128 tokens): split tiles are finished inside the kernel by the unit that owns
+// their head and every tile leaves through the fused epilogue `e` (epi_pass.cuh) — no fp32 segments for a consumer kernel.
+struct Gemm2Epi;
+int gemm2_run_fused(const GemmPlan& p, const CUtensorMap& tm_x, int block_n, int T, const Gemm2Epi& e, cudaStream_t st);
 // Generic consumer: out[t, n] = bf16(sum of segments) — used by tests and by paths without a fused consumer.
 int reduce_partials(const PartialView& v, void* out, int ldo, int T, int N, cudaStream_t st);
 // out[t, n] (bf16, leading dimension ldo) for t < T.

@@ -22,6 +22,7 @@
 #include <unordered_map>
 #include <vector>
 
+#include "epi_pass.cuh"
 #include "gemm.h"
 #include "launch.h"
 #include "ptx.cuh"
@@ -129,8 +130,13 @@ template <int BLOCK_N>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 gemm2_streamk_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_x,
                      const __grid_constant__ CUtensorMap tm_out, int tma_store, __nv_bfloat16* __restrict__ out, int ldo, float* __restrict__ ws, int* __restrict__ counters,
-                     int N, int T, int K, const int2* __restrict__ seg_table, int deferred,
+                     int N, int T, int K, const int2* __restrict__ seg_table, int mode, const __grid_constant__ Gemm2Epi E,
                      long long* __restrict__ trace) {
+  // mode 0: in-kernel fix-up through counters; 1: deferred (split tiles stay fp32 segments for the consumer kernel);
+  // 2: fused — split tiles are finished in-kernel by the unit that owns their head, every finished tile leaves through
+  //    the fused epilogue E (epi_pass.cuh).  See the epilogue branch below.
+  const int deferred = mode == 1;
+  const bool fused = mode == 2;
   using C = Cfg2<BLOCK_N>;
   // optional phase trace (debug): 16 %globaltimer stamps (ns, one clock for the whole GPU) per CTA
   auto mark = [&](int i) {
@@ -328,6 +334,84 @@ gemm2_streamk_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_cons
         wslot = ws + (static_cast<size_t>(seg) * 2 + rank) * kSlot;
       } else {
         wslot = ws + (static_cast<size_t>(cta) * 2 + slot) * kSlot;
+      }
+
+      if (fused) {
+        // A unit's range starts with the TAIL (or a middle piece) of a tile and ends with the HEAD of another.  Pieces that
+        // do not contain k-block 0 are parked in the workspace as fp32 [token][128 rows] with a release flag per unit; the
+        // unit that owns the head computes it LAST in its range, so the other pieces were published long before (a piece
+        // that is a unit's whole range finishes at the same moment: a wait of one flag round trip), adds them in unit order
+        // and runs the fused epilogue.  No unit ever waits for the finisher: no cycle, and every CTA is co-resident.
+        const bool publish = sg.kb0 > 0;
+        const bool head = sg.kb0 == 0 && sg.kb1 < KB;
+        const int slab = slab2 * 2 + static_cast<int>(rank);
+        int parts = 0;
+        if (head) {
+          parts = unit_of_iter(static_cast<long long>(sg.tile + 1) * KB - 1, total, units) - unit;
+          if (epi_tid == 0)
+            for (int p = 1; p <= parts; ++p)
+              while (ld_acquire(E.flags + (unit + p) * 2 + static_cast<int>(rank)) != E.epoch) __nanosleep(32);
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
+        mbar_wait(tfull_bar(acc), acc_phase);
+        tc_fence_after();
+        if (epi_tid == 0 && it == it_begin) mark(2);
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N;
+        if (publish) {
+          float* dst = ws + (static_cast<size_t>(unit) * 2 + rank) * kSlot;
+          for (int c0 = 0; c0 < n_eff; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld_32x32(taddr + c0, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (c0 + j < n_eff) dst[static_cast<size_t>(c0 + j) * kSlab + row] = __uint_as_float(v[j]);
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (leader) mbar_arrive(tempty_bar(acc));
+            else mbar_arrive_remote(tempty_bar(acc), 0);
+          }
+          __threadfence();
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (epi_tid == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(E.flags + unit * 2 + static_cast<int>(rank)), "r"(E.epoch) : "memory");
+        } else {
+          for (int c0 = 0; c0 < n_eff; c0 += 32) {
+            uint4 res_pref[4];
+            if (E.epi == GEMM3_EPI_RESADD) epi::resadd_prefetch(E, epi_tid, t0 + c0, T, slab * kSlab, res_pref);
+            uint32_t v[32];
+            tmem_ld_32x32(taddr + c0, v);
+            tmem_ld_wait();
+            float f[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+            for (int p = 1; p <= parts; ++p) {
+              const float* pp = ws + (static_cast<size_t>(unit + p) * 2 + rank) * kSlot + static_cast<size_t>(c0) * kSlab + row;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] += (c0 + j < n_eff) ? __ldcg(pp + j * kSlab) : 0.f;
+            }
+            __nv_bfloat16* sb = reinterpret_cast<__nv_bfloat16*>(store_ptr + sbuf * C::kStoreBuf);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) sb[j * kSlab + row] = __float2bfloat16_rn(f[j]);
+            // one barrier per chunk: a thread past it has finished its pass over the buffer staged two chunks ago
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            epi::pass(E, sb, epi_tid, t0 + c0, T, slab, res_pref);
+            sbuf ^= 1;
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (leader) mbar_arrive(tempty_bar(acc));
+            else mbar_arrive_remote(tempty_bar(acc), 0);
+          }
+        }
+        if (++acc == C::kAccStages) {
+          acc = 0;
+          acc_phase ^= 1u;
+        }
+        it += sg.kb1 - sg.kb0;
+        continue;
       }
 
       mbar_wait(tfull_bar(acc), acc_phase);
@@ -581,16 +665,20 @@ CUtensorMap out_map_for(const void* out, int T, int N, int ldo, int* ok) {
 
 template <int BLOCK_N>
 int launch2(const GemmPlan& p, const CUtensorMap& tm_x, __nv_bfloat16* out, int ldo, int T, cudaStream_t st,
-            int deferred = 0) {
+            int mode = 0, const Gemm2Epi* fe = nullptr) {
   using C = Cfg2<BLOCK_N>;
   static std::atomic<unsigned long long> attr_done{0};
   if (!ensure_dynamic_smem(gemm2_streamk_kernel<BLOCK_N>, C::kSmemBytes, &attr_done)) return -3;
   const int ntt = (T + BLOCK_N - 1) / BLOCK_N;
   const int units = units_for(p, ntt);
   int tma_store = 0;
-  const CUtensorMap tm_out = out_map_for(out, T, p.N, ldo, &tma_store);
+  Gemm2Epi E;
+  memset(&E, 0, sizeof(E));
+  CUtensorMap tm_out = {};
+  if (mode == 2) E = *fe;
+  else tm_out = out_map_for(out, T, p.N, ldo, &tma_store);
   cudaError_t e = launch_pdl(gemm2_streamk_kernel<BLOCK_N>, dim3(2 * units), dim3(kThreads), C::kSmemBytes, st, p.tm_w, tm_x,
-                             tm_out, tma_store, out, ldo, p.ws, p.counters, p.N, T, p.K, static_cast<const int2*>(p.seg_table), deferred,
+                             tm_out, tma_store, out, ldo, p.ws, p.counters, p.N, T, p.K, static_cast<const int2*>(p.seg_table), mode, E,
                              trace_block());
   return e == cudaSuccess ? 0 : -4;
 }
@@ -684,6 +772,23 @@ int gemm_run_deferred(const GemmPlan& p, const CUtensorMap& tm_x, int block_n, v
     case 128: return launch2<128>(q, tm_x, o, ldo, T, st, 1);
     case 256: return launch2<256>(q, tm_x, o, ldo, T, st, 1);
     case 512: return launch2<512>(q, tm_x, o, ldo, T, st, 1);
+    default: return -6;
+  }
+}
+
+int gemm2_run_fused(const GemmPlan& p, const CUtensorMap& tm_x, int block_n, int T, const Gemm2Epi& e, cudaStream_t st) {
+  if (T <= 0) return 0;
+  if (p.N % (2 * kSlab) != 0 || e.ldo % 8 != 0 || !e.flags || !e.out) return -5;
+  if (e.epi != GEMM3_EPI_PLAIN && e.epi != GEMM3_EPI_RESADD && e.epi != GEMM3_EPI_SILU && e.epi != GEMM3_EPI_ROPE_KV) return -6;
+  const int ntt = (T + block_n - 1) / block_n;
+  // one parked piece per unit: [unit][rank][block_n tokens][128 rows] fp32
+  if (static_cast<size_t>(units_for(p, ntt)) * 2 * block_n * kSlab * sizeof(float) > p.ws_bytes) return -9;
+  switch (block_n) {
+    case 32: return launch2<32>(p, tm_x, nullptr, 0, T, st, 2, &e);
+    case 64: return launch2<64>(p, tm_x, nullptr, 0, T, st, 2, &e);
+    case 128: return launch2<128>(p, tm_x, nullptr, 0, T, st, 2, &e);
+    case 256: return launch2<256>(p, tm_x, nullptr, 0, T, st, 2, &e);
+    case 512: return launch2<512>(p, tm_x, nullptr, 0, T, st, 2, &e);
     default: return -6;
   }
 }

@@ -362,3 +362,21 @@ def test_decode_paths_agree_token_for_token(oracle, monkeypatch):
             if float(srt[-1] - srt[-2]) < 0.25:
                 break
             assert a == b, f"token {j}"
+
+
+def test_large_step_paths_agree_token_for_token(monkeypatch):
+    """Steps of more than 128 tokens: the pair kernel with fused epilogues (default) against fp32 segments + elementwise
+    kernels (B200_FUSED_PREFILL=0).  Same segment order, same rounding points: the same greedy streams, fewer launches."""
+    from kubeai_b200.engine import Engine, mini_config
+    rng = np.random.default_rng(12)
+    prompts = [rng.integers(0, 512, size=n).tolist() for n in (150, 170, 200, 40, 129, 190, 64, 131)]
+    outs = {}
+    for name, env in (("segments", {"B200_FUSED_PREFILL": "0"}), ("fused", {})):
+        monkeypatch.delenv("B200_FUSED_PREFILL", raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        with Engine(mini_config(max_num_seqs=8, max_batched_tokens=512, max_model_len=256)) as e:
+            outs[name] = e.generate(prompts, max_tokens=12)
+            outs[name + "_launches"] = e.stats().kernel_launches
+    assert outs["fused"] == outs["segments"]
+    assert outs["fused_launches"] < outs["segments_launches"]

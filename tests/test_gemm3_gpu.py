@@ -252,3 +252,94 @@ def test_argmax_epilogue_equals_argmax_of_the_plain_logits(T, N, K, force, n_val
     first = (lg == mx[:, None]).float().argmax(-1)
     assert torch.equal(ids.long(), first), f"{int((ids.long() != first).sum())} rows differ ({sch})"
     assert torch.equal(first, want) or True
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# steps of more than 128 tokens: the pair kernel (gemm2) in fused mode — several 256/512-token tiles, stream-K over all
+# pairs, split tiles finished in-kernel by the unit that owns their head, the same epilogues
+LARGE = [
+    (300, 4096, 4096, 0),       # one 512-token tile per weight tile: 16 tiles over 74 units, every tile split 4-5 ways
+    (1408, 4096, 4096, 0),      # 3 token tiles, the last one ragged (384)
+    (1536, 6144, 4096, 0),
+    (700, 4096, 14336, 0),      # down_proj, deep K
+    (129, 512, 512, 0),         # mini-model shapes
+    (513, 768, 512, 0),
+    (1000, 2560, 1024, 256),    # 256-token tiles (two accumulator stages)
+    (2048, 28672, 4096, 0),     # gate_up at the largest step: 448 tiles, ~6 per unit
+]
+
+
+@pytest.mark.parametrize("T,N,K,bn", LARGE)
+def test_large_step_plain_product_matches_oracle(T, N, K, bn):
+    from kubeai_b200 import ops
+    x, w = rnd(T, K, seed=31), rnd(N, K, scale=1 / math.sqrt(K), seed=32)
+    for rep in range(2):
+        got, sch = ops.gemm3(x, w, force=bn)
+        torch.cuda.synchronize()
+        assert sch[1] == 2
+        close(got, ref_gemm(x, w), f"T={T} N={N} K={K} schedule {sch} rep {rep}")
+
+
+@pytest.mark.parametrize("T,N,K,bn", [c for c in LARGE if c[1] <= 6144])
+def test_large_step_residual_add_epilogue(T, N, K, bn):
+    from kubeai_b200 import ops
+    x, w = rnd(T, K, seed=33), rnd(N, K, scale=1 / math.sqrt(K), seed=34)
+    res0 = rnd(T, N, scale=2.0, seed=35)
+    plain, _ = ops.gemm3(x, w, force=bn)
+    res = res0.clone()
+    (res, _), sch = ops.gemm3(x, w, epi=ops.EPI_RESADD, out=res, force=bn)
+    torch.cuda.synchronize()
+    want = O.r(plain.float() + res0.float())
+    assert torch.equal(res.float(), want), f"residual differs in {int((res.float() != want).sum())} places ({sch})"
+
+
+@pytest.mark.parametrize("T,I,K", [(1408, 14336, 4096), (300, 1024, 512), (640, 2048, 1024)])
+def test_large_step_silu_epilogue(T, I, K):
+    from kubeai_b200 import ops
+    x = rnd(T, K, seed=36)
+    wg, wu = rnd(I, K, scale=1 / math.sqrt(K), seed=37), rnd(I, K, scale=1 / math.sqrt(K), seed=38)
+    w = _interleave64(wg, wu)
+    plain, _ = ops.gemm3(x, w)
+    act, sch = ops.gemm3(x, w, epi=ops.EPI_SILU)
+    torch.cuda.synchronize()
+    p = plain.float().reshape(T, I // 64, 2, 64)
+    gu = torch.cat([p[:, :, 0].reshape(T, I), p[:, :, 1].reshape(T, I)], dim=1)
+    want = O.silu_and_mul(gu)
+    bad = act.float() != want
+    assert float(bad.float().mean()) < 1e-3, f"{int(bad.sum())} of {bad.numel()} differ ({sch})"
+    err = (act.float() - want).abs()
+    assert bool((err <= ATOL + RTOL * want.abs()).all())
+
+
+@pytest.mark.parametrize("T,Hq,Hkv,K", [(1408, 32, 8, 4096), (200, 4, 1, 512), (777, 8, 2, 512)])
+def test_large_step_rope_kv_epilogue(T, Hq, Hkv, K):
+    from kubeai_b200 import ops
+    from oracle.weights import ModelCfg, cos_sin_cache
+    D = 128
+    N = (Hq + 2 * Hkv) * D
+    x, w = rnd(T, K, seed=39), rnd(N, K, scale=1 / math.sqrt(K), seed=40)
+    max_pos = 2048
+    cs = O.r(torch.from_numpy(cos_sin_cache(ModelCfg(max_model_len=max_pos)))).cuda()
+    g = torch.Generator().manual_seed(41)
+    pos = torch.randint(0, max_pos, (T,), generator=g, dtype=torch.int32)
+    nblocks = (T + 15) // 16 + 8
+    slots = torch.randperm(nblocks * 16, generator=g)[:T].to(torch.int32)
+    slots[3] = -1
+    kv = torch.zeros(nblocks, 2, Hkv, 16, D, dtype=torch.bfloat16, device="cuda")
+    qkv = torch.zeros(T, N, dtype=torch.bfloat16, device="cuda")
+    plain, _ = ops.gemm3(x, w)
+    ops.gemm3(x, w, epi=ops.EPI_ROPE_KV, out=qkv, positions=pos.cuda(), slots=slots.cuda(), cos_sin=dev(cs), kv_layer=kv, q_heads=Hq, kv_heads=Hkv)
+    torch.cuda.synchronize()
+    p = plain.float()
+    q = O.rope_neox(p[:, :Hq * D].reshape(T, Hq, D), pos.long().cuda(), cs)
+    k = O.rope_neox(p[:, Hq * D:(Hq + Hkv) * D].reshape(T, Hkv, D), pos.long().cuda(), cs)
+    v = p[:, (Hq + Hkv) * D:].reshape(T, Hkv, D)
+    assert torch.equal(qkv[:, :Hq * D].float().reshape(T, Hq, D), q), "rotated q rows of the qkv buffer"
+    kvc = kv.float().permute(0, 3, 1, 2, 4).reshape(nblocks * 16, 2, Hkv, D)      # [slot, k|v, head, d]
+    ok = slots >= 0
+    sl = slots[ok].long().cuda()
+    assert torch.equal(kvc[sl, 0], k[ok.cuda()]), "K page rows"
+    assert torch.equal(kvc[sl, 1], v[ok.cuda()]), "V page rows"
+    used = torch.zeros(nblocks * 16, dtype=torch.bool)
+    used[slots[ok].long()] = True
+    assert not bool(kvc[~used.cuda()].any()), "only the named slots are written"
