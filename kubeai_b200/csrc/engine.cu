@@ -337,14 +337,6 @@ struct Engine {
     ++stats.kernel_launches;
     return gemm_run(p, xmap(xm, bn), bn, out, ldo, T, stream);
   }
-  // GEMM of a step of more than 128 tokens with a fused epilogue (gemm2 mode 2): split tiles finished in-kernel
-  int gemm_f2(const GemmPlan& p, const XMaps& xm, int T, Gemm2Epi e) {
-    const int bn = gemm_block_n_for(T);
-    ++stats.kernel_launches;
-    e.flags = g3_flags;
-    e.epoch = ++g3_epoch;
-    return gemm2_run_fused(p, xmap(xm, bn), bn, T, e, stream);
-  }
   // GEMM that leaves its stream-K segments as fp32 partials for the next kernel to sum (partials.cuh)
   int gemm_def(const GemmPlan& p, const XMaps& xm, void* out, int ldo, int T, PartialView* pv) {
     const int bn = gemm_block_n_for(T);
@@ -677,88 +669,106 @@ int Engine::forward(const StepMeta& m, int32_t* dbuf, bool all_logits, bf16* log
   }();
   const bool dfr = deferred_ok && !all_logits && T <= defer_max_t;
   PartialView pv_x = no_partials();  // partials of the GEMM whose output is `x` (o_proj / down_proj)
-  // Steps of more than 128 tokens (prefill bursts and mixed steps): the pair kernel finishes its split tiles in-kernel and
-  // RoPE + KV write, the residual adds and SiLU*up ride in its epilogues (gemm2 mode 2, epi_pass.cuh); the two RMSNorms
-  // of a layer stay standalone kernels over the bf16 residual.  profiles/r02_prefill_fused.md.
-  const bool f2 = fused2_ok && !all_logits;
-  for (int l = 0; l < L && !rc && f2; ++l) {
-    Layer& ly = layers[l];
-    bf16* kv_l = kv + static_cast<size_t>(l) * kv_layer_elems;
-    Gemm2Epi e;
-    memset(&e, 0, sizeof(e));
-    P(B200_K_NORM); if (on(B200_K_NORM)) rc |= rmsnorm(res, nullptr, ly.norm1, normed, nullptr, T, H, cfg.rms_eps, stream); Q();
-    e.epi = GEMM3_EPI_ROPE_KV; e.out = qkv; e.ldo = QKV; e.positions = pos; e.slots = slots; e.cos_sin = cos_sin; e.kv_layer = kv_l;
-    e.Hq = Hq; e.Hkv = Hkv; e.max_pos = cfg.max_model_len;
-    P(B200_K_GEMM_QKV); if (on(B200_K_GEMM_QKV)) rc |= gemm_f2(ly.p_qkv, xm_normed, T, e); Q();
-    if (m.nd) { P(B200_K_ATTN_DECODE); if (on(B200_K_ATTN_DECODE)) rc |= paged_attention(qkv, QKV, attn, Hq * kD, kv_l, btab, max_blocks_per_seq, dwork, m.nd, Hq, Hkv, scale, 1, stream); Q(); launched(1); }
-    if (m.np) { P(B200_K_ATTN_PREFILL); if (on(B200_K_ATTN_PREFILL)) rc |= prefill_attention(kv_l, btab, pwork, m.np, scale); Q(); launched(1); }
-    memset(&e, 0, sizeof(e));
-    e.epi = GEMM3_EPI_RESADD; e.out = res; e.ldo = H;
-    P(B200_K_GEMM_O); if (on(B200_K_GEMM_O)) rc |= gemm_f2(ly.p_o, xm_attn, T, e); Q();
-    P(B200_K_NORM); if (on(B200_K_NORM)) rc |= rmsnorm(res, nullptr, ly.norm2, normed, nullptr, T, H, cfg.rms_eps, stream); Q();
-    Gemm2Epi g;
-    memset(&g, 0, sizeof(g));
-    g.epi = GEMM3_EPI_SILU; g.out = act; g.ldo = I;
-    P(B200_K_GEMM_GU); if (on(B200_K_GEMM_GU)) rc |= gemm_f2(ly.p_gu, xm_normed, T, g); Q();
-    P(B200_K_GEMM_DOWN); if (on(B200_K_GEMM_DOWN)) rc |= gemm_f2(ly.p_down, xm_act, T, e); Q();
-    launched(2);
-  }
-  if (f2) {
-    if (rc) return cuda_fail("forward", -2);
-    if (m.S > 0) {
-      P(B200_K_NORM); rc |= rmsnorm(res, nullptr, final_norm, last_hidden, rows, m.S, H, cfg.rms_eps, stream); Q();
-      PartialView pv = no_partials();
-      P(B200_K_GEMM_LM);
-      if (dfr && !keep_logits) rc |= gemm_def(p_lm, xm_last, logits, V, m.S, &pv); else rc |= gemm(p_lm, xm_last, logits, V, m.S);
-      Q();
-      last_S = m.S;
-      P(B200_K_ARGMAX); rc |= argmax_rows(logits, sampled, m.S, V, V, stream, pv); Q();
-      launched(2);
-    }
-    if (rc) return cuda_fail("forward(head)", -2);
-    return 0;
-  }
+  // Steps of more than 128 tokens (prefill bursts and mixed steps), per projection: when the launch has at least one
+  // (256-row x token-tile) tile per CTA pair — gate_up at every T, nothing else at Llama-3-8B's shapes — the pair kernel
+  // finishes its few split tiles in-kernel and the elementwise neighbour rides in its epilogue (gemm2 mode 2, epi_pass.cuh).
+  // With fewer tiles than pairs every tile is cut into several pieces and one finisher per tile would serialise the
+  // reduction: those launches keep the fp32 segments and the elementwise consumer that sums them across all SMs (measured:
+  // fusing them too, with 256-token tiles to get enough tiles, is 1.3% slower per step; profiles/r02_prefill_fused.md).
+  // Both forms round at the same points and add the pieces in the same order
+  // (tests/test_fullsize_gpu.py::test_full_size_prefill_burst_step_matches_oracle compares them bit for bit).
+  auto f2_bn = [&](const GemmPlan& pl) {   // token-tile size of the fused form, 0 = keep the segment form
+    if (!fused2_ok || all_logits || !dfr || T <= 128) return 0;
+    const int bn = gemm_block_n_for(T);    // same tiles, ranges and piece order as the segment form: bit-identical results
+    const int ntt = (T + bn - 1) / bn;
+    return (pl.N / 256) * ntt >= pl.max_ctas / 2 ? bn : 0;
+  };
+  auto run_f2 = [&](const GemmPlan& pl, const XMaps& xm, int bn, Gemm2Epi e) {
+    ++stats.kernel_launches;
+    e.flags = g3_flags;
+    e.epoch = ++g3_epoch;
+    return gemm2_run_fused(pl, xmap(xm, bn), bn, T, e, stream);
+  };
+  bool x_pending = false;   // `x` (+ pv_x) holds a projection output that the next RMSNorm still has to add to the residual
   for (int l = 0; l < L && !rc; ++l) {
     Layer& ly = layers[l];
     bf16* kv_l = kv + static_cast<size_t>(l) * kv_layer_elems;
     P(B200_K_NORM);
     if (!on(B200_K_NORM)) {}
-    else if (l == 0) rc |= rmsnorm(res, nullptr, ly.norm1, normed, nullptr, T, H, cfg.rms_eps, stream);
+    else if (!x_pending) rc |= rmsnorm(res, nullptr, ly.norm1, normed, nullptr, T, H, cfg.rms_eps, stream);
     else rc |= rmsnorm(x, res, ly.norm1, normed, nullptr, T, H, cfg.rms_eps, stream, pv_x);
     Q();
+    launched(1);
     PartialView pv = no_partials();
-    P(B200_K_GEMM_QKV);
-    if (!on(B200_K_GEMM_QKV)) {}
-    else if (dfr) rc |= gemm_def(ly.p_qkv, xm_normed, qkv, QKV, T, &pv); else rc |= gemm(ly.p_qkv, xm_normed, qkv, QKV, T);
-    Q();
-    P(B200_K_ROPE); if (on(B200_K_ROPE)) rc |= rope_kv_write(qkv, pos, slots, cos_sin, kv_l, T, Hq, Hkv, cfg.max_model_len, stream, pv); Q();
-    launched(2);
+    Gemm2Epi e;
+    memset(&e, 0, sizeof(e));
+    if (const int bn = f2_bn(ly.p_qkv)) {
+      e.epi = GEMM3_EPI_ROPE_KV; e.out = qkv; e.ldo = QKV; e.positions = pos; e.slots = slots; e.cos_sin = cos_sin; e.kv_layer = kv_l;
+      e.Hq = Hq; e.Hkv = Hkv; e.max_pos = cfg.max_model_len;
+      P(B200_K_GEMM_QKV); if (on(B200_K_GEMM_QKV)) rc |= run_f2(ly.p_qkv, xm_normed, bn, e); Q();
+    } else {
+      P(B200_K_GEMM_QKV);
+      if (!on(B200_K_GEMM_QKV)) {}
+      else if (dfr) rc |= gemm_def(ly.p_qkv, xm_normed, qkv, QKV, T, &pv); else rc |= gemm(ly.p_qkv, xm_normed, qkv, QKV, T);
+      Q();
+      P(B200_K_ROPE); if (on(B200_K_ROPE)) rc |= rope_kv_write(qkv, pos, slots, cos_sin, kv_l, T, Hq, Hkv, cfg.max_model_len, stream, pv); Q();
+      launched(1);
+    }
     if (m.nd) { P(B200_K_ATTN_DECODE); if (on(B200_K_ATTN_DECODE)) rc |= paged_attention(qkv, QKV, attn, Hq * kD, kv_l, btab, max_blocks_per_seq, dwork, m.nd, Hq, Hkv, scale, 1, stream); Q(); launched(1); }
     if (m.np) { P(B200_K_ATTN_PREFILL); if (on(B200_K_ATTN_PREFILL)) rc |= prefill_attention(kv_l, btab, pwork, m.np, scale); Q(); launched(1); }
+    memset(&e, 0, sizeof(e));
+    e.epi = GEMM3_EPI_RESADD; e.out = res; e.ldo = H;
     P(B200_K_GEMM_O);
-    if (!on(B200_K_GEMM_O)) {}
-    else if (dfr) rc |= gemm_def(ly.p_o, xm_attn, x, H, T, &pv_x); else rc |= gemm(ly.p_o, xm_attn, x, H, T);
+    if (const int bn = f2_bn(ly.p_o)) {
+      if (on(B200_K_GEMM_O)) rc |= run_f2(ly.p_o, xm_attn, bn, e);
+      x_pending = false;
+    } else {
+      if (!on(B200_K_GEMM_O)) {}
+      else if (dfr) rc |= gemm_def(ly.p_o, xm_attn, x, H, T, &pv_x); else { rc |= gemm(ly.p_o, xm_attn, x, H, T); pv_x = no_partials(); }
+      x_pending = true;
+    }
     Q();
-    P(B200_K_NORM); if (on(B200_K_NORM)) rc |= rmsnorm(x, res, ly.norm2, normed, nullptr, T, H, cfg.rms_eps, stream, pv_x); Q();
+    P(B200_K_NORM);
+    if (!on(B200_K_NORM)) {}
+    else if (!x_pending) rc |= rmsnorm(res, nullptr, ly.norm2, normed, nullptr, T, H, cfg.rms_eps, stream);
+    else rc |= rmsnorm(x, res, ly.norm2, normed, nullptr, T, H, cfg.rms_eps, stream, pv_x);
+    Q();
+    launched(1);
     pv = no_partials();
-    P(B200_K_GEMM_GU);
-    if (!on(B200_K_GEMM_GU)) {}
-    else if (dfr) rc |= gemm_def(ly.p_gu, xm_normed, gu, 2 * I, T, &pv); else rc |= gemm(ly.p_gu, xm_normed, gu, 2 * I, T);
-    Q();
-    P(B200_K_SILU); if (on(B200_K_SILU)) rc |= silu_mul(gu, act, T, I, stream, pv, 1); Q();
+    if (const int bn = f2_bn(ly.p_gu)) {
+      Gemm2Epi g;
+      memset(&g, 0, sizeof(g));
+      g.epi = GEMM3_EPI_SILU; g.out = act; g.ldo = I;
+      P(B200_K_GEMM_GU); if (on(B200_K_GEMM_GU)) rc |= run_f2(ly.p_gu, xm_normed, bn, g); Q();
+    } else {
+      P(B200_K_GEMM_GU);
+      if (!on(B200_K_GEMM_GU)) {}
+      else if (dfr) rc |= gemm_def(ly.p_gu, xm_normed, gu, 2 * I, T, &pv); else rc |= gemm(ly.p_gu, xm_normed, gu, 2 * I, T);
+      Q();
+      P(B200_K_SILU); if (on(B200_K_SILU)) rc |= silu_mul(gu, act, T, I, stream, pv, 1); Q();
+      launched(1);
+    }
     P(B200_K_GEMM_DOWN);
-    if (!on(B200_K_GEMM_DOWN)) {}
-    else if (dfr) rc |= gemm_def(ly.p_down, xm_act, x, H, T, &pv_x); else rc |= gemm(ly.p_down, xm_act, x, H, T);
+    if (const int bn = f2_bn(ly.p_down)) {
+      if (on(B200_K_GEMM_DOWN)) rc |= run_f2(ly.p_down, xm_act, bn, e);
+      x_pending = false;
+    } else {
+      if (!on(B200_K_GEMM_DOWN)) {}
+      else if (dfr) rc |= gemm_def(ly.p_down, xm_act, x, H, T, &pv_x); else { rc |= gemm(ly.p_down, xm_act, x, H, T); pv_x = no_partials(); }
+      x_pending = true;
+    }
     Q();
-    launched(2);
   }
   if (rc) return cuda_fail("forward", -2);
   if (all_logits) {
-    rc |= rmsnorm(x, res, final_norm, normed, nullptr, T, H, cfg.rms_eps, stream);
+    rc |= rmsnorm(x, res, final_norm, normed, nullptr, T, H, cfg.rms_eps, stream, pv_x);
     rc |= gemm(p_lm, xm_normed, logits_out, V, T);
     launched(1);
   } else if (m.S > 0) {
-    P(B200_K_NORM); rc |= rmsnorm(x, res, final_norm, last_hidden, rows, m.S, H, cfg.rms_eps, stream, pv_x); Q();
+    P(B200_K_NORM);
+    if (x_pending) rc |= rmsnorm(x, res, final_norm, last_hidden, rows, m.S, H, cfg.rms_eps, stream, pv_x);
+    else rc |= rmsnorm(res, nullptr, final_norm, last_hidden, rows, m.S, H, cfg.rms_eps, stream);
+    Q();
     PartialView pv = no_partials();
     P(B200_K_GEMM_LM);
     if (dfr && !keep_logits) rc |= gemm_def(p_lm, xm_last, logits, V, m.S, &pv); else rc |= gemm(p_lm, xm_last, logits, V, m.S);

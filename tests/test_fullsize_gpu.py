@@ -150,6 +150,37 @@ def test_full_size_decode_step_of_128_sequences_matches_oracle(layer):
     assert (G.argmax(-1)[solid] == Wn.argmax(-1)[solid]).all()
 
 
+@pytest.mark.parametrize("mode", ["fused_epilogues", "fp32_segments"])
+def test_full_size_prefill_burst_step_matches_oracle(layer, mode, monkeypatch):
+    """A prefill burst as the scheduler runs it (T = 1500 new tokens of four prompts in ONE step, the sampled rows only):
+    the pair kernel with RoPE + KV write / residual add / SiLU*up in its epilogues (default) and the fp32-segment form
+    (B200_FUSED_PREFILL=0) against the oracle, and against each other bit for bit."""
+    from kubeai_b200.engine import Engine, default_config
+    _, cfg, w, cs = layer
+    monkeypatch.setenv("B200_FUSED_PREFILL", "0" if mode == "fp32_segments" else "1")
+    rng = np.random.default_rng(77)
+    lens = [700, 450, 300, 50]
+    prompts = [rng.integers(0, cfg.vocab, size=n).tolist() for n in lens]
+    with Engine(default_config(manual_step=1, max_num_seqs=8, max_batched_tokens=1536, num_kv_blocks=256, **SHAPE)) as e:
+        e.set_keep_logits(True)
+        rids = [e.submit(p, max_tokens=2) for p in prompts]
+        ran, info = e.step()
+        assert ran and info.tokens == sum(lens) and info.prefill_seqs == len(lens) and info.sampled == len(lens)
+        got = e.read_logits(len(lens))
+        launches = e.stats().kernel_launches
+        for r in rids:
+            e.release(r)
+    want = np.stack([oracle_layer(cfg, w, cs, p, [len(p) - 1])[0] for p in prompts])
+    logits_close(got, want, f"prefill burst T={sum(lens)} ({mode})")
+    _BURST[mode] = (got, launches)
+    if len(_BURST) == 2:
+        assert np.array_equal(_BURST["fused_epilogues"][0], _BURST["fp32_segments"][0]), "the two forms differ"
+        assert _BURST["fused_epilogues"][1] < _BURST["fp32_segments"][1]
+
+
+_BURST = {}
+
+
 # --------------------------------------------------------------------------------------------- attention, production shape
 def _pool(seq_lens, Hkv, seed, extra=7):
     """Random bf16 K/V for every sequence scattered into a shuffled page pool [blocks][K|V][head][16][128]."""
