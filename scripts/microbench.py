@@ -74,6 +74,27 @@ def gemm3_bench():
             del x, w
 
 
+def large_bench():
+    """steps of more than 128 tokens: the pair kernel with in-kernel finished split tiles (the engine's gate_up form, plain and
+    SiLU epilogue) and with fp32 segments + the generic reducer (an upper bound for the engine's segment form, whose
+    consumer does useful work while it sums) vs cuBLAS"""
+    print("== large steps: pair kernel (fused form / segments+reducer) vs cuBLAS, us median, L2 flushed")
+    tf_peak = json.load(open("MEASURED_PEAKS.json")).get("bf16_tflops", 0) if __import__("os").path.exists("MEASURED_PEAKS.json") else 0
+    shapes = [("qkv", 6144, 4096), ("o", 4096, 4096), ("gate_up", 28672, 4096), ("down", 4096, 14336)]
+    for T in (256, 512, 1408, 2048):
+        for name, N, K in shapes:
+            x = torch.randn(T, K, device="cuda").bfloat16()
+            w = (torch.randn(N, K, device="cuda") / math.sqrt(K)).bfloat16()
+            fl = 2.0 * T * N * K
+            t_f = timeit(lambda: ops.gemm3(x, w))
+            t_s = timeit(lambda: ops.gemm3(x, w, epi=ops.EPI_SILU)) if name == "gate_up" else float("nan")
+            t_d = timeit(lambda: ops.gemm_deferred(x, w))
+            t_c = timeit(lambda: torch.nn.functional.linear(x, w))
+            print(f"T={T:5d} {name:8s} fused {t_f:7.1f} us ({fl / t_f / 1e6:6.0f} TF/s)  fused+silu {t_s:7.1f}  segments+reducer {t_d:7.1f}  "
+                  f"cublas {t_c:7.1f} us ({fl / t_c / 1e6:6.0f} TF/s)  ratio {t_c / t_f:4.2f}x")
+            del x, w
+
+
 def attn_bench():
     print("== paged decode attention, B=128, Hq=32/Hkv=8")
     Hq, Hkv, D = 32, 8, 128
