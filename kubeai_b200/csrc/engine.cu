@@ -681,7 +681,11 @@ int Engine::forward(const StepMeta& m, int32_t* dbuf, bool all_logits, bf16* log
     if (!fused2_ok || all_logits || !dfr || T <= 128) return 0;
     const int bn = gemm_block_n_for(T);    // same tiles, ranges and piece order as the segment form: bit-identical results
     const int ntt = (T + bn - 1) / bn;
-    return (pl.N / 256) * ntt >= pl.max_ctas / 2 ? bn : 0;
+    const int tiles = (pl.N / 256) * ntt;
+    // A/B knob: also fuse the launches that run one whole tile per pair (qkv / o_proj of a burst).  Measured slower: their
+    // epilogue is the tail of the kernel, +170 us of qkv per step against -95 us of RoPE kernel (profiles/r02_prefill_fused.md)
+    static const int whole = [] { const char* e = getenv("B200_F2_WHOLE"); return e ? atoi(e) : 0; }();
+    return (tiles >= pl.max_ctas / 2 || (whole && gemm2_units_for(pl, ntt) == tiles)) ? bn : 0;
   };
   auto run_f2 = [&](const GemmPlan& pl, const XMaps& xm, int bn, Gemm2Epi e) {
     ++stats.kernel_launches;

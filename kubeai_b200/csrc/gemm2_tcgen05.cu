@@ -627,6 +627,12 @@ int units_for(const GemmPlan& p, int ntt) {
   long long u = total / 4;
   if (u < 1) u = 1;
   const int max_units = p.max_ctas / 2;
+  // Several token tiles, a shallow K and almost as many tiles as pairs (qkv / o_proj of a prefill burst: 72 and 48 tiles
+  // for 74 pairs): one whole tile per pair.  Stream-K over all pairs would cut EVERY tile into 2-3 fp32 pieces — two exposed
+  // 512-token epilogues per pair and ~75 MB of segments for the consumer kernel to sum — for the sake of a mainloop that is
+  // only ~20 us long; idling a third of the pairs costs less (ncu, T = 1481: RMSNorm after o_proj 30 us -> bf16 input only).
+  const int tiles = pairs_n * ntt;
+  if (ntt > 1 && KB <= 64 && tiles <= max_units && tiles * 5 >= max_units * 3) return tiles;
   return static_cast<int>(u < max_units ? u : max_units);
 }
 

@@ -56,7 +56,7 @@ def run(strategy_name, args):
            "output_tok_s": round(r["run_output_throughput"], 1), "total_tok_s": round(r["run_total_throughput"], 1),
            "ttft_p50_ms": round(r["ttft_p50_s"] * 1e3, 1), "ttft_p99_ms": round(r["ttft_p99_s"] * 1e3, 1), "ttft_mean_ms": round(r["ttft_mean_s"] * 1e3, 1),
            "itl_mean_ms": round(r["itl_mean_s"] * 1e3, 2), "duration_s": round(r["duration_s"], 2), "requests": r["request_count"],
-           "failed_threads": r["failed_threads"], "prompt_tokens": r["prompt_tokens"], "cached_prompt_tokens": r["cached_prompt_tokens"],
+           "failed_threads": r["failed_threads"], "first_error": r.get("first_error", ""), "prompt_tokens": r["prompt_tokens"], "cached_prompt_tokens": r["cached_prompt_tokens"],
            "cached_ratio": round(r["cached_prompt_tokens"] / max(1, r["prompt_tokens"]), 4),
            "completion_tokens": r["completion_tokens"],
            "host_cpu_cores_busy": round(cpu / wall, 2), "host_cpu_seconds_by_thread_name": by_thread, "per_replica": per}
