@@ -377,26 +377,45 @@ gemm2_streamk_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_cons
           asm volatile("bar.sync 1, 128;" ::: "memory");
           if (epi_tid == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(E.flags + unit * 2 + static_cast<int>(rank)), "r"(E.epoch) : "memory");
         } else {
-          for (int c0 = 0; c0 < n_eff; c0 += 32) {
-            uint4 res_pref[4];
-            if (E.epi == GEMM3_EPI_RESADD) epi::resadd_prefetch(E, epi_tid, t0 + c0, T, slab * kSlab, res_pref);
-            uint32_t v[32];
-            tmem_ld_32x32(taddr + c0, v);
+          // 64 tokens per round: two tcgen05.ld in flight, one wait, one barrier — the accumulator drain is exposed at
+          // 512-token tiles (TMEM has a single accumulator stage), so its latency chain is what the tensor pipe waits for
+          for (int c0 = 0; c0 < n_eff; c0 += E.wide ? 64 : 32) {
+            const bool two = E.wide && c0 + 32 < n_eff;
+            uint4 res_pref[2][4];
+            if (E.epi == GEMM3_EPI_RESADD) {
+              epi::resadd_prefetch(E, epi_tid, t0 + c0, T, slab * kSlab, res_pref[0]);
+              if (two) epi::resadd_prefetch(E, epi_tid, t0 + c0 + 32, T, slab * kSlab, res_pref[1]);
+            }
+            uint32_t v0[32], v1[32];
+            tmem_ld_32x32(taddr + c0, v0);
+            if (two) tmem_ld_32x32(taddr + c0 + 32, v1);
             tmem_ld_wait();
-            float f[32];
+            float f0[32], f1[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+            for (int j = 0; j < 32; ++j) {
+              f0[j] = __uint_as_float(v0[j]);
+              f1[j] = two ? __uint_as_float(v1[j]) : 0.f;
+            }
             for (int p = 1; p <= parts; ++p) {
               const float* pp = ws + (static_cast<size_t>(unit + p) * 2 + rank) * kSlot + static_cast<size_t>(c0) * kSlab + row;
 #pragma unroll
-              for (int j = 0; j < 32; ++j) f[j] += (c0 + j < n_eff) ? __ldcg(pp + j * kSlab) : 0.f;
-            }
-            __nv_bfloat16* sb = reinterpret_cast<__nv_bfloat16*>(store_ptr + sbuf * C::kStoreBuf);
+              for (int j = 0; j < 32; ++j) f0[j] += (c0 + j < n_eff) ? __ldcg(pp + j * kSlab) : 0.f;
+              if (two) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) sb[j * kSlab + row] = __float2bfloat16_rn(f[j]);
-            // one barrier per chunk: a thread past it has finished its pass over the buffer staged two chunks ago
+                for (int j = 0; j < 32; ++j) f1[j] += (c0 + 32 + j < n_eff) ? __ldcg(pp + (32 + j) * kSlab) : 0.f;
+              }
+            }
+            __nv_bfloat16* sb = reinterpret_cast<__nv_bfloat16*>(store_ptr + sbuf * C::kStoreBuf);   // 64 tokens x 128 rows bf16
+#pragma unroll
+            for (int j = 0; j < 32; ++j) sb[j * kSlab + row] = __float2bfloat16_rn(f0[j]);
+            if (two) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) sb[(32 + j) * kSlab + row] = __float2bfloat16_rn(f1[j]);
+            }
+            // one barrier per round: a thread past it has finished its pass over the buffer staged two rounds ago
             asm volatile("bar.sync 1, 128;" ::: "memory");
-            epi::pass(E, sb, epi_tid, t0 + c0, T, slab, res_pref);
+            epi::pass(E, sb, epi_tid, t0 + c0, T, slab, res_pref[0]);
+            if (two) epi::pass(E, sb + 32 * kSlab, epi_tid, t0 + c0 + 32, T, slab, res_pref[1]);
             sbuf ^= 1;
           }
           tc_fence_before();
@@ -418,7 +437,35 @@ gemm2_streamk_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_cons
       tc_fence_after();
       if (epi_tid == 0 && it == it_begin) mark(2);
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N;
-      for (int c0 = 0; c0 < n_eff; c0 += 32) {
+      const bool wide = complete && tma_store && BLOCK_N >= 256 && E.wide;
+      // complete tiles of the large steps: 64 tokens per round (two tcgen05.ld in flight, one pair of barriers, two TMA
+      // stores in one bulk group) — the drain of a 512-token tile is exposed, its latency chain is tensor-pipe idle time
+      for (int c0 = 0; wide && c0 < n_eff; c0 += 64) {
+        const bool two = c0 + 32 < n_eff;
+        uint32_t v0[32], v1[32];
+        tmem_ld_32x32(taddr + c0, v0);
+        if (two) tmem_ld_32x32(taddr + c0 + 32, v1);
+        tmem_ld_wait();
+        if (epi_tid == 0) bulk_wait_group_read<1>();  // the stores issued two rounds ago have left their buffer
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        __nv_bfloat16* sb = reinterpret_cast<__nv_bfloat16*>(store_ptr + sbuf * C::kStoreBuf);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) sb[j * kSlab + row] = __float2bfloat16_rn(__uint_as_float(v0[j]));
+        if (two) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) sb[(32 + j) * kSlab + row] = __float2bfloat16_rn(__uint_as_float(v1[j]));
+        }
+        fence_proxy_async();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (epi_tid == 0) {
+          const int n_first = (slab2 * 2 + static_cast<int>(rank)) * kSlab;
+          tma_store_2d(&tm_out, store_stage + sbuf * C::kStoreBuf, n_first, t0 + c0);
+          if (two) tma_store_2d(&tm_out, store_stage + sbuf * C::kStoreBuf + 32 * kSlab * 2, n_first, t0 + c0 + 32);
+          bulk_commit_group();
+        }
+        sbuf ^= 1;
+      }
+      for (int c0 = 0; !wide && c0 < n_eff; c0 += 32) {
         uint32_t v[32];
         tmem_ld_32x32(taddr + c0, v);
         tmem_ld_wait();
@@ -683,6 +730,8 @@ int launch2(const GemmPlan& p, const CUtensorMap& tm_x, __nv_bfloat16* out, int 
   CUtensorMap tm_out = {};
   if (mode == 2) E = *fe;
   else tm_out = out_map_for(out, T, p.N, ldo, &tma_store);
+  static const int wide = [] { const char* e = getenv("B200_GEMM_WIDE_EPI"); return e ? atoi(e) : 1; }();
+  E.wide = wide;
   cudaError_t e = launch_pdl(gemm2_streamk_kernel<BLOCK_N>, dim3(2 * units), dim3(kThreads), C::kSmemBytes, st, p.tm_w, tm_x,
                              tm_out, tma_store, out, ldo, p.ws, p.counters, p.N, T, p.K, static_cast<const int2*>(p.seg_table), mode, E,
                              trace_block());
