@@ -339,6 +339,11 @@ int b200_op_argmax(const void* logits, int32_t* out, int32_t S, int32_t V, int32
 int b200_op_paged_attn(const void* q, int32_t ldq, void* out, int32_t ldo, const void* kv_layer,
                        const int32_t* block_tables, int32_t max_blocks, const int32_t* work, int32_t num_work,
                        int32_t q_heads, int32_t kv_heads, float scale, int32_t decode, void* stream);
+/* Decode attention with each work item's context split over `split` >= 1 CTAs per KV head (what the engine does when a step
+ * has fewer decoding sequences than the device has SMs / kv_heads) and a merge of the partial softmax states. */
+int b200_op_paged_attn_decode_split(const void* q, int32_t ldq, void* out, int32_t ldo, const void* kv_layer,
+                                    const int32_t* block_tables, int32_t max_blocks, const int32_t* work, int32_t num_work,
+                                    int32_t q_heads, int32_t kv_heads, float scale, int32_t split, void* stream);
 /* Chunked-prefill attention on the tensor cores (csrc/attention_tc.cu): work items (q_tok0, q_count <= 64, q_pos0, seq); q rows
  * are read from the fused qkv buffer [q_rows, ldq] (q heads first) through a 3-D TMA map. */
 int b200_op_paged_attn_prefill_tc(const void* qkv, int32_t q_rows, int32_t ldq, void* out, int32_t ldo, const void* kv_layer,

@@ -267,6 +267,29 @@ int b200_op_paged_attn(const void* q, int32_t ldq, void* out, int32_t ldo, const
   return rc ? cuda_fail("paged_attention", rc) : 0;
 }
 
+int b200_op_paged_attn_decode_split(const void* q, int32_t ldq, void* out, int32_t ldo, const void* kv_layer,
+                                    const int32_t* block_tables, int32_t max_blocks, const int32_t* work, int32_t num_work,
+                                    int32_t q_heads, int32_t kv_heads, float scale, int32_t split, void* stream) {
+  if (int rc = require_device()) return rc;
+  if (split < 1 || split > 64 || num_work <= 0) { set_error("b200_op_paged_attn_decode_split: bad arguments"); return B200_ERR_INVALID; }
+  static float* ws = nullptr;
+  static size_t ws_bytes = 0;
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lk(mu);
+  const size_t need = attn_split_ws_bytes(num_work, kv_heads, split);
+  if (need > ws_bytes) {
+    cudaDeviceSynchronize();
+    if (ws) cudaFree(ws);
+    ws = nullptr;
+    ws_bytes = 0;
+    if (cudaMalloc(&ws, need) != cudaSuccess) { set_error("workspace allocation failed"); return B200_ERR_OOM; }
+    ws_bytes = need;
+  }
+  int rc = paged_attention(q, ldq, out, ldo, kv_layer, block_tables, max_blocks, reinterpret_cast<const AttnWork*>(work), num_work,
+                           q_heads, kv_heads, scale, 1, static_cast<cudaStream_t>(stream), ws, split);
+  return rc ? cuda_fail("paged_attention(split)", rc) : 0;
+}
+
 int b200_op_paged_attn_prefill_tc(const void* qkv, int32_t q_rows, int32_t ldq, void* out, int32_t ldo, const void* kv_layer,
                                   const int32_t* block_tables, int32_t max_blocks, const int32_t* work, int32_t num_work,
                                   int32_t q_heads, int32_t kv_heads, float scale, void* stream) {

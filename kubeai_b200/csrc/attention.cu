@@ -51,7 +51,7 @@ template <bool DECODE, int S>  // S = tiles in flight per CTA
 __global__ void __launch_bounds__(128)
 paged_attn_kernel(const __grid_constant__ CUtensorMap tm_kv, const __nv_bfloat16* __restrict__ q, int ldq,
                   __nv_bfloat16* __restrict__ out, int ldo, const int* __restrict__ block_tables, int max_blocks,
-                  const AttnWork* __restrict__ work, int Hkv, float scale_log2) {
+                  const AttnWork* __restrict__ work, int Hkv, float scale_log2, float* __restrict__ split_ws) {
   constexpr int WT = DECODE ? 16 : 64;  // tokens of each tile handled by one warp
   constexpr int NT = WT / 8;
   extern __shared__ uint8_t smem_raw[];
@@ -69,6 +69,13 @@ paged_attn_kernel(const __grid_constant__ CUtensorMap tm_kv, const __nv_bfloat16
   const int kv_end = wk.q_pos0 + wk.q_count;  // tokens [0, kv_end) are visible to the last query
   const int ntiles = (kv_end + kTile - 1) / kTile;
   const int last_page = (kv_end - 1) >> 4;
+  // split-KV (decode with few sequences: gridDim.z parts per work item so that the context streams on all SMs): this CTA
+  // owns tiles [t_begin, t_end) and leaves an unnormalised (max, sum, acc) per head for attn_merge_kernel
+  const int parts = DECODE ? static_cast<int>(gridDim.z) : 1;
+  const int part = DECODE ? static_cast<int>(blockIdx.z) : 0;
+  const int tpp = (ntiles + parts - 1) / parts;
+  const int t_begin = part * tpp;
+  const int t_end = min(ntiles, t_begin + tpp);
   const int* btab = block_tables + static_cast<size_t>(wk.seq) * max_blocks;
 
   if (tid == 0) {
@@ -107,11 +114,11 @@ paged_attn_kernel(const __grid_constant__ CUtensorMap tm_kv, const __nv_bfloat16
   bool waited = false;
 #pragma unroll
   for (int i = 0; i < S; ++i) {
-    if (!waited && safe_tiles < i + 1) {
+    if (!waited && safe_tiles < t_begin + i + 1) {
       griddep_enter();
       waited = true;
     }
-    if (tid == 0 && i < ntiles) issue_tile(i, i);
+    if (tid == 0 && t_begin + i < t_end) issue_tile(t_begin + i, i);
   }
   if (!waited) griddep_enter();
 
@@ -143,9 +150,9 @@ paged_attn_kernel(const __grid_constant__ CUtensorMap tm_kv, const __nv_bfloat16
   float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
   const int wo = DECODE ? warp * 16 : 0;  // this warp's token offset inside a tile
 
-  for (int t = 0; t < ntiles; ++t) {
-    const int stage = t % S;
-    mbar_wait(full_bar(stage), static_cast<uint32_t>(t / S) & 1u);
+  for (int t = t_begin; t < t_end; ++t) {
+    const int stage = (t - t_begin) % S;
+    mbar_wait(full_bar(stage), static_cast<uint32_t>((t - t_begin) / S) & 1u);
 
     const int tok_base = t * kTile + wo;
     if (tok_base < kv_end) {
@@ -234,7 +241,7 @@ paged_attn_kernel(const __grid_constant__ CUtensorMap tm_kv, const __nv_bfloat16
       }
     }
     __syncthreads();  // every warp is done reading this stage
-    if (tid == 0 && t + S < ntiles) issue_tile(t + S, stage);
+    if (tid == 0 && t + S < t_end) issue_tile(t + S, stage);
   }
 
   l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
@@ -289,9 +296,41 @@ paged_attn_kernel(const __grid_constant__ CUtensorMap tm_kv, const __nv_bfloat16
         num += so[(w * 4 + h) * kD + d] * wgt;
         den += sl[w * 4 + h] * wgt;
       }
-      out[static_cast<size_t>(wk.q_tok0) * ldo + (kvh * 4 + h) * kD + d] =
-          __float2bfloat16_rn(den > 0.f ? num / den : 0.f);
+      if (parts == 1) {
+        out[static_cast<size_t>(wk.q_tok0) * ldo + (kvh * 4 + h) * kD + d] = __float2bfloat16_rn(den > 0.f ? num / den : 0.f);
+      } else {
+        // [work][kv head][part][4 heads][128 acc | max | sum]
+        float* dst = split_ws + ((static_cast<size_t>(blockIdx.y) * Hkv + kvh) * parts + part) * (4 * (kD + 2)) + h * (kD + 2);
+        dst[d] = num;
+        if (d == 0) {
+          dst[kD] = mm;
+          dst[kD + 1] = den;
+        }
+      }
     }
+  }
+}
+
+// out[token, head, :] = sum_p acc_p 2^(m_p - M) / sum_p l_p 2^(m_p - M) over the parts of a split decode work item
+__global__ void __launch_bounds__(128)
+attn_merge_kernel(const float* __restrict__ split_ws, __nv_bfloat16* __restrict__ out, int ldo, const AttnWork* __restrict__ work,
+                  int Hkv, int parts) {
+  griddep_enter();
+  const AttnWork wk = work[blockIdx.y];
+  const int kvh = blockIdx.x, d = threadIdx.x;
+  const float* base = split_ws + (static_cast<size_t>(blockIdx.y) * Hkv + kvh) * parts * (4 * (kD + 2));
+#pragma unroll
+  for (int h = 0; h < 4; ++h) {
+    float mm = -INFINITY;
+    for (int p = 0; p < parts; ++p) mm = fmaxf(mm, base[(p * 4 + h) * (kD + 2) + kD]);
+    float num = 0.f, den = 0.f;
+    for (int p = 0; p < parts; ++p) {
+      const float* s = base + (p * 4 + h) * (kD + 2);
+      const float wgt = (s[kD] == -INFINITY) ? 0.f : exp2f(s[kD] - mm);
+      num += s[d] * wgt;
+      den += s[kD + 1] * wgt;
+    }
+    out[static_cast<size_t>(wk.q_tok0) * ldo + (kvh * 4 + h) * kD + d] = __float2bfloat16_rn(den > 0.f ? num / den : 0.f);
   }
 }
 
@@ -331,12 +370,19 @@ namespace {
 
 template <bool DECODE, int S>
 int launch_attn(const CUtensorMap& tm, dim3 grid, cudaStream_t st, const __nv_bfloat16* q, int ldq, __nv_bfloat16* out,
-                int ldo, const int* block_tables, int max_blocks, const AttnWork* work, int Hkv, float scale_log2) {
+                int ldo, const int* block_tables, int max_blocks, const AttnWork* work, int Hkv, float scale_log2,
+                float* split_ws = nullptr) {
   static std::atomic<unsigned long long> attr_done{0};
   if (!ensure_dynamic_smem(paged_attn_kernel<DECODE, S>, attn_smem_bytes<S>(), &attr_done)) return -3;
   launch_pdl(paged_attn_kernel<DECODE, S>, grid, dim3(128), attn_smem_bytes<S>(), st, tm, q, ldq, out, ldo, block_tables,
-             max_blocks, work, Hkv, scale_log2);
-  return cudaGetLastError() == cudaSuccess ? 0 : -2;
+             max_blocks, work, Hkv, scale_log2, split_ws);
+  if (cudaGetLastError() != cudaSuccess) return -2;
+  if (DECODE && grid.z > 1) {
+    launch_pdl(attn_merge_kernel, dim3(grid.x, grid.y), dim3(128), 0, st, static_cast<const float*>(split_ws), out, ldo, work, Hkv,
+               static_cast<int>(grid.z));
+    if (cudaGetLastError() != cudaSuccess) return -2;
+  }
+  return 0;
 }
 
 }  // namespace
@@ -349,23 +395,39 @@ int prefill_attn_query_block() {
   return v;
 }
 
+size_t attn_split_ws_bytes(int num_work, int Hkv, int parts) {
+  return static_cast<size_t>(num_work) * Hkv * parts * 4 * (kD + 2) * sizeof(float);
+}
+
+// Parts per decode work item such that the launch has about two CTAs per SM, each with at least two 64-token tiles.
+int attn_decode_split(int num_work, int Hkv, int max_ctx, int sms) {
+  const int ctas = num_work * Hkv;
+  if (ctas <= 0 || ctas >= sms) return 1;
+  int p = (2 * sms + ctas - 1) / ctas;
+  const int by_ctx = (max_ctx + 2 * kTile - 1) / (2 * kTile);
+  if (p > by_ctx) p = by_ctx;
+  if (p > 32) p = 32;
+  return p < 1 ? 1 : p;
+}
+
 int paged_attention(const void* q, int ldq, void* out, int ldo, const void* kv_layer, const int* block_tables,
                     int max_blocks, const AttnWork* work, int num_work, int Hq, int Hkv, float scale,
-                    int decode, cudaStream_t st) {
+                    int decode, cudaStream_t st, float* split_ws, int split) {
   if (num_work <= 0) return 0;
   if (Hq != 4 * Hkv) return -1;
+  if (split > 1 && (!decode || !split_ws)) return -1;
   CUtensorMap tm;
   if (int rc = kv_map_for(kv_layer, &tm)) return rc;
   const float scale_log2 = scale * 1.4426950408889634f;
-  dim3 grid(Hkv, num_work);
+  dim3 grid(Hkv, num_work, split > 1 ? split : 1);
   const __nv_bfloat16* qq = static_cast<const __nv_bfloat16*>(q);
   __nv_bfloat16* oo = static_cast<__nv_bfloat16*>(out);
   if (!decode)
     return launch_attn<false, kPrefillStages>(tm, grid, st, qq, ldq, oo, ldo, block_tables, max_blocks, work, Hkv, scale_log2);
   switch (decode_stages()) {
-    case 3: return launch_attn<true, 3>(tm, grid, st, qq, ldq, oo, ldo, block_tables, max_blocks, work, Hkv, scale_log2);
-    case 4: return launch_attn<true, 4>(tm, grid, st, qq, ldq, oo, ldo, block_tables, max_blocks, work, Hkv, scale_log2);
-    default: return launch_attn<true, 2>(tm, grid, st, qq, ldq, oo, ldo, block_tables, max_blocks, work, Hkv, scale_log2);
+    case 3: return launch_attn<true, 3>(tm, grid, st, qq, ldq, oo, ldo, block_tables, max_blocks, work, Hkv, scale_log2, split_ws);
+    case 4: return launch_attn<true, 4>(tm, grid, st, qq, ldq, oo, ldo, block_tables, max_blocks, work, Hkv, scale_log2, split_ws);
+    default: return launch_attn<true, 2>(tm, grid, st, qq, ldq, oo, ldo, block_tables, max_blocks, work, Hkv, scale_log2, split_ws);
   }
 }
 

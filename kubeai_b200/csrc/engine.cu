@@ -211,6 +211,7 @@ struct StepMeta {
   int words = 0;
   int64_t kv_tokens = 0;
   int out_tokens = 0;  // sampled rows that produce a generated token
+  int dmax_ctx = 0;    // longest context among the decode work items (split-KV decision)
 };
 
 struct XMaps {
@@ -254,6 +255,9 @@ struct Engine {
   Gemm3Schedule sch_qkv, sch_o, sch_gu, sch_down, sch_lm;
   // projection chain (chain_tcgen05.cu): o -> norm -> gate_up -> down -> norm -> next qkv -> rope in one persistent launch
   bool chain_ok = false;
+  float* attn_ws = nullptr;  // split-KV decode partials
+  int attn_split_force = 0;  // B200_ATTN_SPLIT=<parts> (A/B knob; 1 = never split)
+  static constexpr int kSplitMaxWork = 18, kSplitMaxParts = 32;
   bool fused2_ok = false;   // steps of more than 128 tokens: pair kernel with fused epilogues (gemm2 mode 2)
   int chain_ctas = 0;
   unsigned long long* chain_bar = nullptr;
@@ -309,6 +313,13 @@ struct Engine {
   int forward(const StepMeta& m, int32_t* dbuf, bool all_logits, bf16* logits_out);
   int forward_fused(const StepMeta& m, int32_t* dbuf);
   int forward_chain(const StepMeta& m, int32_t* dbuf);
+  // decode attention; with few sequences the context of each is split over several CTAs (attention.cu attn_decode_split)
+  int decode_attention(const StepMeta& m, bf16* kv_l, const int* btab, const AttnWork* dwork, float scale) {
+    int split = 1;
+    if (m.nd <= kSplitMaxWork) split = std::min(attn_split_force > 0 ? attn_split_force : attn_decode_split(m.nd, Hkv, m.dmax_ctx, sms), kSplitMaxParts);
+    if (split > 1) ++stats.kernel_launches;   // the merge kernel
+    return paged_attention(qkv, QKV, attn, Hq * kD, kv_l, btab, max_blocks_per_seq, dwork, m.nd, Hq, Hkv, scale, 1, stream, attn_ws, split);
+  }
   int prefill_attention(bf16* kv_l, const int* btab, const AttnWork* pwork, int np, float scale) {
     if (prefill_attn_query_block() == 64)
       return paged_attention_prefill_tc(qkv, Tcap, QKV, attn, Hq * kD, kv_l, btab, max_blocks_per_seq, pwork, np, Hq, Hkv, scale, stream);
@@ -377,7 +388,7 @@ Engine::~Engine() {
   cudaSetDevice(cfg.device);
   if (stream) cudaStreamSynchronize(stream);
   void* frees[] = {weights_blob, res, x, normed, qkv, attn, gu, act, last_hidden, logits, sampled, gemm_ws,
-                   gemm_counters, kv, ssq, cand, g3_flags, chain_bar};
+                   gemm_counters, kv, ssq, cand, g3_flags, chain_bar, attn_ws};
   for (void* p : frees)
     if (p) cudaFree(p);
   for (auto p : stage_dev)
@@ -494,6 +505,8 @@ int Engine::alloc_all() {
   CK(cudaMallocHost(&sampled_host, static_cast<size_t>(Scap) * 4));
   CK(cudaMalloc(&ssq, static_cast<size_t>(Tcap) * (H / 128) * 4));
   CK(cudaMalloc(&cand, static_cast<size_t>(std::min(Scap, 128)) * (V / 128 + 1) * sizeof(float2)));
+  CK(cudaMalloc(&attn_ws, attn_split_ws_bytes(kSplitMaxWork, Hkv, kSplitMaxParts)));
+  { const char* e = getenv("B200_ATTN_SPLIT"); attn_split_force = e ? atoi(e) : 0; }
   CK(cudaMalloc(&g3_flags, 8192 * 4));     // stream-K neighbour flags [0, 4096) + fused-norm row flags [4096, 8192)
   CK(cudaMemset(g3_flags, 0, 8192 * 4));
   // split-K workspace: 2 fp32 slots of 512 tokens x 128 rows per CTA (in-kernel fix-up slots == deferred segments)
@@ -718,7 +731,7 @@ int Engine::forward(const StepMeta& m, int32_t* dbuf, bool all_logits, bf16* log
       P(B200_K_ROPE); if (on(B200_K_ROPE)) rc |= rope_kv_write(qkv, pos, slots, cos_sin, kv_l, T, Hq, Hkv, cfg.max_model_len, stream, pv); Q();
       launched(1);
     }
-    if (m.nd) { P(B200_K_ATTN_DECODE); if (on(B200_K_ATTN_DECODE)) rc |= paged_attention(qkv, QKV, attn, Hq * kD, kv_l, btab, max_blocks_per_seq, dwork, m.nd, Hq, Hkv, scale, 1, stream); Q(); launched(1); }
+    if (m.nd) { P(B200_K_ATTN_DECODE); if (on(B200_K_ATTN_DECODE)) rc |= decode_attention(m, kv_l, btab, dwork, scale); Q(); launched(1); }
     if (m.np) { P(B200_K_ATTN_PREFILL); if (on(B200_K_ATTN_PREFILL)) rc |= prefill_attention(kv_l, btab, pwork, m.np, scale); Q(); launched(1); }
     memset(&e, 0, sizeof(e));
     e.epi = GEMM3_EPI_RESADD; e.out = res; e.ldo = H;
@@ -838,7 +851,7 @@ int Engine::forward_fused(const StepMeta& m, int32_t* dbuf) {
       p.positions = pos; p.slots = slots; p.cos_sin = cos_sin; p.kv_layer = kv_l; p.Hq = Hq; p.Hkv = Hkv; p.max_pos = cfg.max_model_len;
       P(B200_K_GEMM_QKV); if (on(B200_K_GEMM_QKV)) rc |= gemm3_launch(p, sch_qkv, stream); Q();
     }
-    if (m.nd) { P(B200_K_ATTN_DECODE); if (on(B200_K_ATTN_DECODE)) rc |= paged_attention(qkv, QKV, attn, Hq * kD, kv_l, btab, max_blocks_per_seq, dwork, m.nd, Hq, Hkv, scale, 1, stream); Q(); ++stats.kernel_launches; }
+    if (m.nd) { P(B200_K_ATTN_DECODE); if (on(B200_K_ATTN_DECODE)) rc |= decode_attention(m, kv_l, btab, dwork, scale); Q(); ++stats.kernel_launches; }
     if (m.np) { P(B200_K_ATTN_PREFILL); if (on(B200_K_ATTN_PREFILL)) rc |= prefill_attention(kv_l, btab, pwork, m.np, scale); Q(); ++stats.kernel_launches; }
     {
       Gemm3Params p = base(ly.p_o, xmap(xm_attn, 128), T, GEMM3_PRO_NONE, GEMM3_EPI_RESADD);
@@ -938,7 +951,7 @@ int Engine::forward_chain(const StepMeta& m, int32_t* dbuf) {
   for (int l = 0; l < L && !rc; ++l) {
     Layer& ly = layers[l];
     bf16* kv_l = kv + static_cast<size_t>(l) * kv_layer_elems;
-    if (m.nd) { P(B200_K_ATTN_DECODE); rc |= paged_attention(qkv, QKV, attn, Hq * kD, kv_l, btab, max_blocks_per_seq, dwork, m.nd, Hq, Hkv, scale, 1, stream); Q(); ++stats.kernel_launches; }
+    if (m.nd) { P(B200_K_ATTN_DECODE); rc |= decode_attention(m, kv_l, btab, dwork, scale); Q(); ++stats.kernel_launches; }
     if (m.np) { P(B200_K_ATTN_PREFILL); rc |= prefill_attention(kv_l, btab, pwork, m.np, scale); Q(); ++stats.kernel_launches; }
     ChainParams c;
     memset(&c, 0, sizeof(c));
@@ -1185,6 +1198,7 @@ int Engine::launch(InFlight* f, StepMeta* mp) {
   std::stable_sort(dwork_.begin(), dwork_.end(), longer);
   std::stable_sort(pwork_.begin(), pwork_.end(), longer);
   m.nd = static_cast<int>(dwork_.size());
+  m.dmax_ctx = m.nd ? dwork_[0].q_pos0 + 1 : 0;   // sorted longest-first
   m.np = static_cast<int>(pwork_.size());
   m.S = static_cast<int>(rows_.size());
   m.out_tokens = m.S;

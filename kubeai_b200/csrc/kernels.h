@@ -42,7 +42,11 @@ struct AttnWork {
 //   decode != 0: every work item has q_count == 1 and the CTA's 4 warps split the KV range.
 int paged_attention(const void* q, int ldq, void* out, int ldo, const void* kv_layer, const int* block_tables,
                     int max_blocks, const AttnWork* work, int num_work, int Hq, int Hkv, float scale,
-                    int decode, cudaStream_t st);
+                    int decode, cudaStream_t st, float* split_ws = nullptr, int split = 1);
+// split-KV decode (few sequences): `split` CTAs per (work item, KV head) each stream a slice of the context and leave an
+// unnormalised partial in split_ws (attn_split_ws_bytes), merged by a second tiny kernel.  attn_decode_split picks `split`.
+size_t attn_split_ws_bytes(int num_work, int Hkv, int parts);
+int attn_decode_split(int num_work, int Hkv, int max_ctx, int sms);
 
 // Chunked-prefill attention on tcgen05 (attention_tc.cu): work items of up to 64 query tokens; q rows are read from the
 // fused qkv buffer [qkv_rows, ldq] through a 3-D TMA map.

@@ -125,12 +125,19 @@ def argmax(logits):
     return out
 
 
-def paged_attn(qkv, kv_layer, block_tables, work, q_heads, kv_heads, decode: bool, out=None):
-    """qkv: [T, (Hq+2Hkv)*128] (q read from it), work: int32 [n, 4] = (q_tok0, q_count, q_pos0, seq)."""
+def paged_attn(qkv, kv_layer, block_tables, work, q_heads, kv_heads, decode: bool, out=None, split: int = 0):
+    """qkv: [T, (Hq+2Hkv)*128] (q read from it), work: int32 [n, 4] = (q_tok0, q_count, q_pos0, seq).
+    split >= 1 (decode only): split-KV form with that many CTAs per (work item, KV head)."""
     _chk(qkv), _chk(kv_layer), _chk(block_tables, torch.int32), _chk(work, torch.int32)
     T = qkv.shape[0]
     if out is None:
         out = torch.zeros(T, q_heads * 128, dtype=torch.bfloat16, device=qkv.device)
+    if split:
+        assert decode
+        check(lib().b200_op_paged_attn_decode_split(_p(qkv), qkv.shape[1], _p(out), out.shape[1], _p(kv_layer), _p(block_tables),
+                                                    block_tables.shape[1], _p(work), work.shape[0], q_heads, kv_heads,
+                                                    128 ** -0.5, split, _stream()))
+        return out
     check(lib().b200_op_paged_attn(_p(qkv), qkv.shape[1], _p(out), out.shape[1], _p(kv_layer), _p(block_tables),
                                    block_tables.shape[1], _p(work), work.shape[0], q_heads, kv_heads,
                                    128 ** -0.5, 1 if decode else 0, _stream()))

@@ -382,3 +382,27 @@ def test_large_step_paths_agree_token_for_token(monkeypatch):
     # the test model's projections have fewer tiles than the device has CTA pairs, so most of its launches keep the segment
     # form either way; tests/test_fullsize_gpu.py::test_full_size_prefill_burst_step_matches_oracle covers the full shapes
     assert outs["fused_launches"] <= outs["segments_launches"]
+
+
+def test_few_long_sequences_decode_through_split_kv_attention(oracle, monkeypatch):
+    """Two sequences with long contexts: the engine splits each context over several attention CTAs (attn_decode_split);
+    same tokens as with the split disabled, and the oracle's wherever its margin is not a rounding coin-flip."""
+    from kubeai_b200.engine import Engine, mini_config
+    rng = np.random.default_rng(21)
+    prompts = [rng.integers(0, 512, size=n).tolist() for n in (230, 150)]
+    outs = {}
+    for name, env in (("split", None), ("one_cta", "1")):
+        monkeypatch.delenv("B200_ATTN_SPLIT", raising=False)
+        if env:
+            monkeypatch.setenv("B200_ATTN_SPLIT", env)
+        with Engine(mini_config(max_num_seqs=4, max_batched_tokens=256, max_model_len=256)) as e:
+            outs[name] = e.generate(prompts, max_tokens=16)
+            outs[name + "_launches"] = e.stats().kernel_launches
+    assert outs["split_launches"] > outs["one_cta_launches"], "the split path (with its merge kernel) did not run"
+    for p, a, b in zip(prompts, outs["split"], outs["one_cta"]):
+        w, rows = oracle.generate(p, 16)
+        for j, (x, y, z) in enumerate(zip(a, b, w)):
+            srt = torch.sort(rows[j])[0]
+            if float(srt[-1] - srt[-2]) < 0.25:
+                break
+            assert x == z and y == z, f"token {j}"

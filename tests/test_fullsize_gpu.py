@@ -230,6 +230,30 @@ def test_decode_attention_at_production_shape():
         _attn_close(got[i:i + 1], want, f"decode seq {i} ctx {L}")
 
 
+@pytest.mark.parametrize("split", [2, 5, 16, 32])
+def test_split_kv_decode_attention_matches_oracle_and_the_unsplit_kernel(split):
+    """Few decoding sequences: each context is cut into `split` slices streamed by different CTAs, partial softmax states
+    merged by a second kernel.  Slices may be empty (a 1-token context split 32 ways)."""
+    from kubeai_b200 import ops
+    Hq, Hkv = 32, 8
+    lens = [2048, 1023, 17, 300, 1, 64, 65, 1999]
+    kv, btab, ks, vs = _pool(lens, Hkv, seed=23)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    q = torch.randn(len(lens), (Hq + 2 * Hkv) * 128, generator=g, device="cuda").bfloat16()
+    work = torch.tensor([[i, 1, L - 1, i] for i, L in enumerate(lens)], dtype=torch.int32).cuda()
+    base = ops.paged_attn(q, kv, btab, work, Hq, Hkv, decode=True).float()
+    for rep in range(2):
+        got = ops.paged_attn(q, kv, btab, work, Hq, Hkv, decode=True, split=split).float()
+        torch.cuda.synchronize()
+        for i, L in enumerate(lens):
+            qi = q[i, :Hq * 128].float().reshape(1, Hq, 128)
+            want = O.attention(qi, ks[i], vs[i], torch.tensor([L - 1], device="cuda"), 128 ** -0.5).reshape(1, Hq * 128)
+            _attn_close(got[i:i + 1], want, f"split {split} seq {i} ctx {L}")
+        # against the one-CTA form: only the order of the fp32 merge differs
+        assert float((got - base).abs().max()) <= 2 ** -7 * float(base.abs().max()) + 1e-3
+    assert torch.equal(ops.paged_attn(q, kv, btab, work, Hq, Hkv, decode=True, split=1).float(), base)
+
+
 @pytest.mark.parametrize("kernel", ["tensor_core", "mma_sync"])
 def test_chunked_prefill_attention_at_production_shape_with_cached_prefix(kernel):
     from kubeai_b200 import ops
