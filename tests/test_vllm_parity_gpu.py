@@ -11,7 +11,10 @@ minutes to start).  Two things are compared on >= 32 prompts:
     |d logprob| 0.20 on the 2-layer model (3.2 ulps), 0.50 on the 32-layer Llama-3-8B shape (4 ulps), means 0.03 / 0.08,
     i.e. under one ulp.  The measured maxima of every run go to gpurun_out/vllm_parity.json.
   * greedy TOKENS: streams may part only where vLLM's own top-2 candidates are within MARGIN_ULPS bf16 ulps of the top
-    logit of each other (observed: never above 0.25 = 2 ulps at |logit| 16..32).
+    logit of each other.  MARGIN_ULPS = 4 is the measured bound on how far ONE logit of the 32-layer model moves between the
+    two pipelines (max |d logprob| 3.7-4 ulps over three runs): a margin below it can flip.  Observed first-difference
+    margins over three runs of 64 prompts: 0 (exact ties) .. 0.375 = 3 ulps at |logit| 16..32; the seeded random weights
+    give near-flat distributions, which is what makes ties this common.
 """
 import json
 import os
@@ -34,7 +37,7 @@ def _vllm_ok():
 
 pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not _vllm_ok(), reason="vllm is not importable (or B200_SKIP_VLLM=1)")]
 LOGPROB_ULPS = 6.0
-MARGIN_ULPS = 2.0
+MARGIN_ULPS = 4.0
 REPORT = Path(__file__).resolve().parent.parent / "gpurun_out" / "vllm_parity.json"
 
 
