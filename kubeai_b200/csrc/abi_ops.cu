@@ -152,6 +152,7 @@ int b200_op_gemm3(const b200_gemm3_args* a, void* stream, int32_t* schedule_out)
       set_error("b200_op_gemm3: T > 128 serves PRO_NONE with the PLAIN / RESADD / SILU / ROPE_KV epilogues");
       return B200_ERR_INVALID;
     }
+    gemm2_read_env();
     GemmPlan plan;
     int rc = gemm_plan_init(&plan, a->w, a->N, a->K, a->K, g_ws, g_counters, 0);
     if (rc) return cuda_fail("gemm_plan_init", rc);

@@ -507,6 +507,7 @@ int Engine::alloc_all() {
   CK(cudaMalloc(&cand, static_cast<size_t>(std::min(Scap, 128)) * (V / 128 + 1) * sizeof(float2)));
   CK(cudaMalloc(&attn_ws, attn_split_ws_bytes(kSplitMaxWork, Hkv, kSplitMaxParts)));
   { const char* e = getenv("B200_ATTN_SPLIT"); attn_split_force = e ? atoi(e) : 0; }
+  gemm2_read_env();
   CK(cudaMalloc(&g3_flags, 8192 * 4));     // stream-K neighbour flags [0, 4096) + fused-norm row flags [4096, 8192)
   CK(cudaMemset(g3_flags, 0, 8192 * 4));
   // split-K workspace: 2 fp32 slots of 512 tokens x 128 rows per CTA (in-kernel fix-up slots == deferred segments)

@@ -24,6 +24,7 @@ struct Gemm2Epi {
   int Hq, Hkv, max_pos;
   int* flags;              // one int per (unit, CTA rank): stamped with `epoch` when that unit's partial tile is in the workspace
   int epoch;
+  int hybrid;              // whole-tile waves first, stream-K over the remaining tiles (A/B knob B200_GEMM_HYBRID=0)
   int wide;                // 64-token epilogue rounds (two tcgen05.ld in flight); 0 = 32-token rounds (A/B knob B200_GEMM_WIDE_EPI=0)
 };
 

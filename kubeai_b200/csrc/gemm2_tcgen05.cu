@@ -166,12 +166,38 @@ gemm2_streamk_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_cons
   const int pairs_n = (N + 2 * kSlab - 1) / (2 * kSlab);  // 256-row tiles
   const int ntt = (T + BLOCK_N - 1) / BLOCK_N;
   const int KB = (K + kBlockK - 1) / kBlockK;
-  const long long total = static_cast<long long>(pairs_n) * ntt * KB;
   const int units = gridDim.x >> 1;
   const int unit = blockIdx.x >> 1;
   const int cta = blockIdx.x;
+  // Schedule.  Stream-K: one contiguous range of (tile, k-block) iterations per pair.  Fused mode with more tiles than pairs
+  // (gate_up of a large step) runs a HYBRID: first `dp_waves` waves of whole tiles, wave w giving pair u tile w*units + u,
+  // then stream-K over the tiles that are left.  Tiles are ordered token-tile-minor, so in every wave each 256-row weight
+  // slab is in use by ntt neighbouring pairs at the same time and is fetched from HBM once; with contiguous ranges the
+  // pairs sit ~4.5 tiles apart, every pair streams its own slab, 74 slabs x 2 MB do not fit L2 together with the
+  // activations and each slab came from DRAM once per token tile (ncu, T = 2048: 2.95x the algorithmic bytes).
+  const int tiles_total = pairs_n * ntt;
+  // a short stream-K tail would cut each of its few tiles into many pieces for one finisher to add (4 tiles over 74 pairs:
+  // 18 pieces each, +120 us at T = 2048): when less than half a wave is left, one whole wave joins the stream-K part
+  int dp_waves = (mode == 2 && E.hybrid && tiles_total >= units) ? tiles_total / units : 0;
+  if (dp_waves > 0 && (tiles_total - dp_waves * units) * 2 < units && tiles_total != dp_waves * units) --dp_waves;
+  const int dp_tiles = dp_waves * units;
+  const long long total = static_cast<long long>(tiles_total - dp_tiles) * KB;   // the stream-K part
   const long long it_begin = range_begin(unit, total, units);
   const long long it_end = range_begin(unit + 1, total, units);
+  // this pair's iterations as one virtual index v: [0, v_dp) the whole tiles, [v_dp, v_end) its stream-K range
+  const long long v_dp = static_cast<long long>(dp_waves) * KB;
+  const long long v_end = v_dp + (it_end - it_begin);
+  auto tile_kb_at = [&](long long v, int* kb) {
+    if (v < v_dp) {
+      const int w = static_cast<int>(v / KB);
+      *kb = static_cast<int>(v - static_cast<long long>(w) * KB);
+      return w * units + unit;
+    }
+    const long long it = it_begin + (v - v_dp);
+    const int t = static_cast<int>(it / KB);
+    *kb = static_cast<int>(it - static_cast<long long>(t) * KB);
+    return dp_tiles + t;
+  };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_w);
@@ -202,12 +228,11 @@ gemm2_streamk_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_cons
   griddep_launch();
   if (threadIdx.x == 64) mark(1);
 
-  auto seg_at = [&](long long it) {
+  auto seg_at = [&](long long v) {
     Seg s;
-    s.tile = static_cast<int>(it / KB);
-    s.kb0 = static_cast<int>(it - static_cast<long long>(s.tile) * KB);
-    long long rem = it_end - it;
-    s.kb1 = (KB - s.kb0 <= rem) ? KB : s.kb0 + static_cast<int>(rem);
+    s.tile = tile_kb_at(v, &s.kb0);
+    const long long rem = v_end - v;
+    s.kb1 = (v < v_dp || KB - s.kb0 <= rem) ? KB : s.kb0 + static_cast<int>(rem);
     return s;
   };
   // token layout of a tile: chunk c covers tokens [t0 + c*256, ...), nc_c = its (16-padded) width
@@ -221,8 +246,9 @@ gemm2_streamk_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_cons
     if (lane == 0) {
       const uint64_t w_hint = ntt > 1 ? kEvictNormal : kEvictFirst;
       int pre = 0;
-      for (long long it = it_begin; it < it_end && pre < C::kStages; ++it, ++pre) {
-        const int tile = static_cast<int>(it / KB), kb = static_cast<int>(it - static_cast<long long>(tile) * KB);
+      for (long long v = 0; v < v_end && pre < C::kStages; ++v, ++pre) {
+        int kb;
+        const int tile = tile_kb_at(v, &kb);
         if (leader) mbar_arrive_expect_tx(full_bar(pre), 2u * C::kStageBytes);
         tma_load_2d_pair(smem_base + pre * C::kStageBytes, &tm_w, full_bar(pre), kb * kBlockK,
                          (tile / ntt) * 2 * kSlab + static_cast<int>(rank) * kSlab, w_hint);
@@ -231,8 +257,9 @@ gemm2_streamk_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_cons
       mark(12);
       int stage = 0, idx = 0;
       uint32_t phase = 0;
-      for (long long it = it_begin; it < it_end; ++it, ++idx) {
-        const int tile = static_cast<int>(it / KB), kb = static_cast<int>(it - static_cast<long long>(tile) * KB);
+      for (long long v = 0; v < v_end; ++v, ++idx) {
+        int kb;
+        const int tile = tile_kb_at(v, &kb);
         const int slab2 = tile / ntt, tt = tile - slab2 * ntt;
         const uint32_t sa = smem_base + stage * C::kStageBytes;
         if (idx >= pre) {
@@ -261,7 +288,7 @@ gemm2_streamk_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_cons
       griddep_wait();
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
-      for (long long it = it_begin; it < it_end;) {
+      for (long long it = 0; it < v_end;) {
         Seg sg = seg_at(it);
         const int slab2 = sg.tile / ntt, tt = sg.tile - slab2 * ntt;
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
@@ -269,7 +296,7 @@ gemm2_streamk_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_cons
         for (int kb = sg.kb0; kb < sg.kb1; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
-          if (it == it_begin && kb == sg.kb0) mark(10);
+          if (it == 0 && kb == sg.kb0) mark(10);
           const uint32_t sa = smem_base + stage * C::kStageBytes;
           const uint64_t a_desc = umma_desc_kmajor_sw128(sa);
 #pragma unroll
@@ -316,7 +343,7 @@ gemm2_streamk_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_cons
     const uint32_t store_stage = bar_base + 256;
     uint8_t* store_ptr = smem_raw + (store_stage - smem_u32(smem_raw));
     int sbuf = 0;
-    for (long long it = it_begin; it < it_end;) {
+    for (long long it = 0; it < v_end;) {   // `it` is the virtual index here (== offset into the stream-K range when dp_waves == 0)
       Seg sg = seg_at(it);
       const int slab2 = sg.tile / ntt, tt = sg.tile - slab2 * ntt;
       const int t0 = tt * BLOCK_N;
@@ -325,11 +352,11 @@ gemm2_streamk_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_cons
       for (int c = 0; c < C::kNch; ++c) n_eff += chunk_n(tt, c);
       const int n = (slab2 * 2 + static_cast<int>(rank)) * kSlab + row;
       const bool complete = (sg.kb0 == 0 && sg.kb1 == KB);
-      const int slot = (it == it_begin) ? 0 : 1;
+      const int slot = (it == 0) ? 0 : 1;
       float* wslot;
       if (deferred) {
         // partial segment index = table[tile].first + (this unit's position among the units sharing the tile)
-        const int u0 = unit_of_iter(static_cast<long long>(sg.tile) * KB, total, units);
+        const int u0 = unit_of_iter(static_cast<long long>(sg.tile - dp_tiles) * KB, total, units);
         const int seg = complete ? 0 : __ldg(&seg_table[sg.tile]).x + (unit - u0);
         wslot = ws + (static_cast<size_t>(seg) * 2 + rank) * kSlot;
       } else {
@@ -347,7 +374,7 @@ gemm2_streamk_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_cons
         const int slab = slab2 * 2 + static_cast<int>(rank);
         int parts = 0;
         if (head) {
-          parts = unit_of_iter(static_cast<long long>(sg.tile + 1) * KB - 1, total, units) - unit;
+          parts = unit_of_iter(static_cast<long long>(sg.tile - dp_tiles + 1) * KB - 1, total, units) - unit;
           if (epi_tid == 0)
             for (int p = 1; p <= parts; ++p)
               while (ld_acquire(E.flags + (unit + p) * 2 + static_cast<int>(rank)) != E.epoch) __nanosleep(32);
@@ -355,7 +382,7 @@ gemm2_streamk_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_cons
         }
         mbar_wait(tfull_bar(acc), acc_phase);
         tc_fence_after();
-        if (epi_tid == 0 && it == it_begin) mark(2);
+        if (epi_tid == 0 && it == 0) mark(2);
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N;
         if (publish) {
           float* dst = ws + (static_cast<size_t>(unit) * 2 + rank) * kSlot;
@@ -435,7 +462,7 @@ gemm2_streamk_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_cons
 
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      if (epi_tid == 0 && it == it_begin) mark(2);
+      if (epi_tid == 0 && it == 0) mark(2);
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N;
       const bool wide = complete && tma_store && BLOCK_N >= 256 && E.wide;
       // complete tiles of the large steps: 64 tokens per round (two tcgen05.ld in flight, one pair of barriers, two TMA
@@ -716,6 +743,10 @@ CUtensorMap out_map_for(const void* out, int T, int N, int ldo, int* ok) {
   return it->second;
 }
 
+// A/B knobs, re-read from the environment whenever an engine (or the op-level ABI) initialises: B200_GEMM_WIDE_EPI=0 selects
+// 32-token epilogue rounds, B200_GEMM_HYBRID=0 plain stream-K ranges in fused mode
+int g_wide_epi = 1, g_hybrid = 1;
+
 template <int BLOCK_N>
 int launch2(const GemmPlan& p, const CUtensorMap& tm_x, __nv_bfloat16* out, int ldo, int T, cudaStream_t st,
             int mode = 0, const Gemm2Epi* fe = nullptr) {
@@ -730,8 +761,8 @@ int launch2(const GemmPlan& p, const CUtensorMap& tm_x, __nv_bfloat16* out, int 
   CUtensorMap tm_out = {};
   if (mode == 2) E = *fe;
   else tm_out = out_map_for(out, T, p.N, ldo, &tma_store);
-  static const int wide = [] { const char* e = getenv("B200_GEMM_WIDE_EPI"); return e ? atoi(e) : 1; }();
-  E.wide = wide;
+  E.wide = g_wide_epi;
+  E.hybrid = g_hybrid;
   cudaError_t e = launch_pdl(gemm2_streamk_kernel<BLOCK_N>, dim3(2 * units), dim3(kThreads), C::kSmemBytes, st, p.tm_w, tm_x,
                              tm_out, tma_store, out, ldo, p.ws, p.counters, p.N, T, p.K, static_cast<const int2*>(p.seg_table), mode, E,
                              trace_block());
@@ -762,6 +793,13 @@ __global__ void reduce_partials_kernel(PartialView v, __nv_bfloat16* __restrict_
 }  // namespace
 
 int gemm2_units_for(const GemmPlan& p, int ntt) { return units_for(p, ntt); }
+
+void gemm2_read_env() {
+  const char* w = getenv("B200_GEMM_WIDE_EPI");
+  const char* h = getenv("B200_GEMM_HYBRID");
+  g_wide_epi = w ? atoi(w) : 1;
+  g_hybrid = h ? atoi(h) : 1;
+}
 
 int gemm_plan_build_table(GemmPlan* p, int max_tokens) {
   if (p->seg_table) return 0;

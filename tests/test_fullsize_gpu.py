@@ -150,14 +150,16 @@ def test_full_size_decode_step_of_128_sequences_matches_oracle(layer):
     assert (G.argmax(-1)[solid] == Wn.argmax(-1)[solid]).all()
 
 
-@pytest.mark.parametrize("mode", ["fused_epilogues", "fp32_segments"])
+@pytest.mark.parametrize("mode", ["fused_epilogues", "fused_stream_k_only", "fp32_segments"])
 def test_full_size_prefill_burst_step_matches_oracle(layer, mode, monkeypatch):
     """A prefill burst as the scheduler runs it (T = 1500 new tokens of four prompts in ONE step, the sampled rows only):
-    the pair kernel with RoPE + KV write / residual add / SiLU*up in its epilogues (default) and the fp32-segment form
-    (B200_FUSED_PREFILL=0) against the oracle, and against each other bit for bit."""
+    the pair kernel with SiLU*up in gate_up's epilogue and the whole-tile-waves + stream-K-tail schedule (default), the same
+    with plain stream-K ranges (B200_GEMM_HYBRID=0), and the fp32-segment form (B200_FUSED_PREFILL=0), each against the
+    oracle; the last two cut the tiles at the same k-blocks and must agree bit for bit."""
     from kubeai_b200.engine import Engine, default_config
     _, cfg, w, cs = layer
     monkeypatch.setenv("B200_FUSED_PREFILL", "0" if mode == "fp32_segments" else "1")
+    monkeypatch.setenv("B200_GEMM_HYBRID", "0" if mode == "fused_stream_k_only" else "1")
     rng = np.random.default_rng(77)
     lens = [700, 450, 300, 50]
     prompts = [rng.integers(0, cfg.vocab, size=n).tolist() for n in lens]
@@ -173,9 +175,9 @@ def test_full_size_prefill_burst_step_matches_oracle(layer, mode, monkeypatch):
     want = np.stack([oracle_layer(cfg, w, cs, p, [len(p) - 1])[0] for p in prompts])
     logits_close(got, want, f"prefill burst T={sum(lens)} ({mode})")
     _BURST[mode] = (got, launches)
-    if len(_BURST) == 2:
-        assert np.array_equal(_BURST["fused_epilogues"][0], _BURST["fp32_segments"][0]), "the two forms differ"
-        assert _BURST["fused_epilogues"][1] < _BURST["fp32_segments"][1]
+    if len(_BURST) == 3:
+        assert np.array_equal(_BURST["fused_stream_k_only"][0], _BURST["fp32_segments"][0]), "the two forms differ"
+        assert _BURST["fused_epilogues"][1] == _BURST["fused_stream_k_only"][1] < _BURST["fp32_segments"][1]
 
 
 _BURST = {}
