@@ -350,7 +350,7 @@ struct Engine {
   }
   // GEMM that leaves its stream-K segments as fp32 partials for the next kernel to sum (partials.cuh)
   int gemm_def(const GemmPlan& p, const XMaps& xm, void* out, int ldo, int T, PartialView* pv) {
-    const int bn = gemm_block_n_for(T);
+    const int bn = gemm_variant() == 2 ? gemm2_block_n_for_plan(p, T) : gemm_block_n_for(T);
     ++stats.kernel_launches;
     return gemm_run_deferred(p, xmap(xm, bn), bn, out, ldo, T, stream, pv);
   }

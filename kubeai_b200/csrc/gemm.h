@@ -47,6 +47,7 @@ int tmap_encode_bf16_3d(CUtensorMap* tm, const void* base, uint64_t d0, uint64_t
 int gemm_make_out_map(CUtensorMap* tm, const void* out, int rows, int N, int ldo);
 // variant-2 internals (gemm2_tcgen05.cu)
 int gemm2_block_n_for(int T);
+int gemm2_block_n_for_plan(const GemmPlan& p, int T);   // 384-token tiles where they give one whole tile per pair
 int gemm2_x_box_rows(int block_n);
 void gemm2_set_trace(long long* dev_ptr);  // debug: 8 clock64 stamps per CTA, or nullptr
 int gemm2_run(const GemmPlan& p, const CUtensorMap& tm_x, int block_n, void* out, int ldo, int T, cudaStream_t st);

@@ -41,14 +41,15 @@ constexpr uint32_t kPeerMask = 0xFEFFFFFFu;  // clears the CTA-rank bit of a sha
 template <int BLOCK_N>
 struct Cfg2 {
   static constexpr int kChunk = BLOCK_N > 256 ? 256 : BLOCK_N;  // tokens per MMA instruction
-  static constexpr int kNch = BLOCK_N / kChunk;                 // instructions per k-step (1 or 2)
+  static constexpr int kNch = (BLOCK_N + kChunk - 1) / kChunk;  // instructions per k-step (1 or 2; 384 = 256 + 128)
   static constexpr int kHalf = kChunk / 2;                      // token rows of one chunk staged by one CTA
   static constexpr int kBBytes = kNch * kHalf * kBlockK * 2;    // B bytes per CTA per stage
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStagesRaw = (200 * 1024) / kStageBytes;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
   static constexpr int kAccStages = (2 * BLOCK_N <= 512) ? 2 : 1;
-  static constexpr int kTmemCols = kAccStages * BLOCK_N < 32 ? 32 : kAccStages * BLOCK_N;
+  static constexpr int kTmemNeed = kAccStages * BLOCK_N < 32 ? 32 : kAccStages * BLOCK_N;
+  static constexpr int kTmemCols = kTmemNeed <= 32 ? 32 : kTmemNeed <= 64 ? 64 : kTmemNeed <= 128 ? 128 : kTmemNeed <= 256 ? 256 : 512;  // power of two
   static constexpr int kStoreBuf = 32 * kSlab * 4;        // one staging buffer: [32 tokens][128 rows], fp32 or bf16
   static constexpr int kStoreStage = 2 * kStoreBuf;       // double buffered
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256 + kStoreStage;
@@ -237,7 +238,8 @@ gemm2_streamk_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_cons
   };
   // token layout of a tile: chunk c covers tokens [t0 + c*256, ...), nc_c = its (16-padded) width
   auto chunk_n = [&](int tt, int c) {
-    const int rem = T - tt * BLOCK_N - c * C::kChunk;
+    const int tile_end = (tt + 1) * BLOCK_N < T ? (tt + 1) * BLOCK_N : T;   // a 384-token tile's second chunk is 128 wide
+    const int rem = tile_end - tt * BLOCK_N - c * C::kChunk;
     return rem <= 0 ? 0 : (rem >= C::kChunk ? C::kChunk : ((rem + 15) & ~15));
   };
 
@@ -805,7 +807,7 @@ int gemm_plan_build_table(GemmPlan* p, int max_tokens) {
   if (p->seg_table) return 0;
   const int pairs_n = (p->N + 2 * kSlab - 1) / (2 * kSlab);
   const int KB = (p->K + kBlockK - 1) / kBlockK;
-  int max_ntt = (max_tokens + 511) / 512;
+  int max_ntt = (max_tokens + 383) / 384;   // 384-token tiles are the narrowest multi-tile form
   if (max_ntt < 1) max_ntt = 1;
   if (max_ntt > 64) max_ntt = 64;
   p->max_ntt = max_ntt;
@@ -844,7 +846,8 @@ int gemm_run_deferred(const GemmPlan& p, const CUtensorMap& tm_x, int block_n, v
   if (T <= 0 || !p.seg_table) return -8;
   if (ldo % 8 != 0) return -5;  // consumers read the dense tiles with 16-byte loads
   const int ntt = (T + block_n - 1) / block_n;
-  if (ntt > 1 && block_n != 512) return -8;   // tables are built for 512-token tiles when there are several
+  const bool whole = units_for(p, ntt) == ((p.N + 2 * kSlab - 1) / (2 * kSlab)) * ntt;   // one whole tile per pair: no segments
+  if (ntt > 1 && block_n != 512 && !(block_n == 384 && whole)) return -8;   // consumers index segment tables by 512-token tiles
   if (ntt > p.max_ntt) return -8;
   const size_t need = static_cast<size_t>(p.table_segs[ntt]) * 2 * block_n * kSlab * sizeof(float);
   if (need > p.ws_bytes) return -9;
@@ -858,12 +861,14 @@ int gemm_run_deferred(const GemmPlan& p, const CUtensorMap& tm_x, int block_n, v
   view->ntt = ntt;
   view->block_n = block_n;
   view->bn_shift = block_n == 32 ? 5 : block_n == 64 ? 6 : block_n == 128 ? 7 : block_n == 256 ? 8 : 9;
+  if (whole && ntt > 1) *view = no_partials();   // every tile is complete: the consumer reads the bf16 tensor, no table look-ups
   __nv_bfloat16* o = static_cast<__nv_bfloat16*>(out);
   switch (block_n) {
     case 32: return launch2<32>(q, tm_x, o, ldo, T, st, 1);
     case 64: return launch2<64>(q, tm_x, o, ldo, T, st, 1);
     case 128: return launch2<128>(q, tm_x, o, ldo, T, st, 1);
     case 256: return launch2<256>(q, tm_x, o, ldo, T, st, 1);
+    case 384: return launch2<384>(q, tm_x, o, ldo, T, st, 1);
     case 512: return launch2<512>(q, tm_x, o, ldo, T, st, 1);
     default: return -6;
   }
@@ -881,13 +886,14 @@ int gemm2_run_fused(const GemmPlan& p, const CUtensorMap& tm_x, int block_n, int
     case 64: return launch2<64>(p, tm_x, nullptr, 0, T, st, 2, &e);
     case 128: return launch2<128>(p, tm_x, nullptr, 0, T, st, 2, &e);
     case 256: return launch2<256>(p, tm_x, nullptr, 0, T, st, 2, &e);
+    case 384: return launch2<384>(p, tm_x, nullptr, 0, T, st, 2, &e);
     case 512: return launch2<512>(p, tm_x, nullptr, 0, T, st, 2, &e);
     default: return -6;
   }
 }
 
 int reduce_partials(const PartialView& v, void* out, int ldo, int T, int N, cudaStream_t st) {
-  if (T <= 0) return 0;
+  if (T <= 0 || !v.ws) return 0;   // no segments (every tile complete): `out` already holds the bf16 result
   dim3 grid((N / 8 + 127) / 128 + 1, T);
   cudaError_t e = launch_pdl(reduce_partials_kernel, grid, dim3(128), 0, st, v, static_cast<__nv_bfloat16*>(out), ldo, T, N);
   return e == cudaSuccess ? 0 : -4;
@@ -899,6 +905,19 @@ void gemm2_set_trace(long long* dev_ptr) {
 }
 
 int gemm2_block_n_for(int T) { return T <= 32 ? 32 : T <= 64 ? 64 : T <= 128 ? 128 : T <= 256 ? 256 : 512; }
+
+// Token-tile size for one projection of a step: 512 (256 up to 256 tokens, ...) unless 384-token tiles turn a launch with
+// fewer tiles than pairs into one whole tile per pair with more pairs busy (o_proj of a prefill burst: 48 -> 64 tiles for 74).
+int gemm2_block_n_for_plan(const GemmPlan& p, int T) {
+  const int bn = gemm2_block_n_for(T);
+  static const int allow = [] { const char* e = getenv("B200_GEMM_BN384"); return e ? atoi(e) : 1; }();
+  if (bn != 512 || T <= 512 || !allow) return bn;
+  const int pairs_n = (p.N + 2 * kSlab - 1) / (2 * kSlab), pairs = p.max_ctas / 2;
+  const int KB = (p.K + kBlockK - 1) / kBlockK;
+  const int t512 = pairs_n * ((T + 511) / 512), t384 = pairs_n * ((T + 383) / 384);
+  if (KB <= 64 && t512 < pairs && t384 <= pairs && t384 > t512 && units_for(p, (T + 383) / 384) == t384) return 384;
+  return bn;
+}
 int gemm2_x_box_rows(int block_n) { return (block_n > 256 ? 256 : block_n) / 2; }
 
 int gemm2_run(const GemmPlan& p, const CUtensorMap& tm_x, int block_n, void* out, int ldo, int T, cudaStream_t st) {
@@ -909,6 +928,7 @@ int gemm2_run(const GemmPlan& p, const CUtensorMap& tm_x, int block_n, void* out
     case 64: return launch2<64>(p, tm_x, o, ldo, T, st);
     case 128: return launch2<128>(p, tm_x, o, ldo, T, st);
     case 256: return launch2<256>(p, tm_x, o, ldo, T, st);
+    case 384: return launch2<384>(p, tm_x, o, ldo, T, st);
     case 512: return launch2<512>(p, tm_x, o, ldo, T, st);
     default: return -6;
   }

@@ -266,6 +266,9 @@ LARGE = [
     (513, 768, 512, 0),
     (1000, 2560, 1024, 256),    # 256-token tiles (two accumulator stages)
     (2048, 28672, 4096, 0),     # gate_up at the largest step: 448 tiles, ~6 per unit
+    (1408, 4096, 4096, 384),    # 384-token tiles (256 + 128 tokens per k-step): o_proj of a burst as 64 whole tiles
+    (1340, 6144, 4096, 384),    # ragged last tile
+    (900, 28672, 4096, 384),    # three 384-token tiles per weight tile, waves + stream-K tail
 ]
 
 
