@@ -288,6 +288,12 @@ int b200_harness_run(b200_server* server, const char* host, int32_t port, const 
 /* GEMM kernel variant for plans/engines created afterwards: 2 = CTA-pair tcgen05 cta_group::2 (default),
  * 1 = single-CTA kernel (kept for A/B measurements).  Returns the active variant. */
 int b200_set_gemm_variant(int32_t v);
+/* Host-only (no GPU needed): how a projection [N, K] of a step of T > 128 tokens is scheduled on a device with `sms` SMs.
+ * out8: [0] token-tile size, [1] token tiles, [2] tiles, [3] CTA pairs launched, [4] 1 = one whole tile per pair, [5] 1 = the
+ * engine fuses the elementwise neighbour into the launch, [6] whole-tile waves ahead of the stream-K tail, [7] 0. */
+int b200_schedule_query(int32_t N, int32_t K, int32_t T, int32_t sms, int32_t* out8);
+/* Host-only: CTAs per (sequence, KV head) the engine gives decode attention when `num_work` sequences decode. */
+int b200_attn_split_query(int32_t num_work, int32_t kv_heads, int32_t max_ctx, int32_t sms);
 /* Debug: subsequent pair-GEMM launches write 8 clock64() phase stamps per CTA into trace_dev (int64[grid][8]);
  * NULL turns it off.  Stamps: 0 entry, 1 after prologue, 2 first tile accumulated, 3 main loop + partial stores
  * done, 4 peers' partials visible, 5 bulk pull landed, 6 before final cluster sync, 7 exit. */

@@ -210,6 +210,17 @@ int b200_op_gemm3(const b200_gemm3_args* a, void* stream, int32_t* schedule_out)
   return 0;
 }
 
+int b200_schedule_query(int32_t N, int32_t K, int32_t T, int32_t sms, int32_t* out8) {
+  if (N <= 0 || K <= 0 || T <= 0 || sms < 2 || !out8) { set_error("b200_schedule_query: bad arguments"); return B200_ERR_INVALID; }
+  gemm2_schedule_query(N, K, T, sms, out8);
+  return 0;
+}
+
+int b200_attn_split_query(int32_t num_work, int32_t kv_heads, int32_t max_ctx, int32_t sms) {
+  if (num_work <= 0 || kv_heads <= 0 || max_ctx <= 0 || sms <= 0) return 1;
+  return attn_decode_split(num_work, kv_heads, max_ctx, sms);
+}
+
 int b200_set_gemm_variant(int32_t v) {
   gemm_set_variant(v);
   return gemm_variant();

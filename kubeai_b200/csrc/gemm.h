@@ -52,6 +52,7 @@ int gemm2_x_box_rows(int block_n);
 void gemm2_set_trace(long long* dev_ptr);  // debug: 8 clock64 stamps per CTA, or nullptr
 int gemm2_run(const GemmPlan& p, const CUtensorMap& tm_x, int block_n, void* out, int ldo, int T, cudaStream_t st);
 int gemm2_units_for(const GemmPlan& p, int ntt);
+void gemm2_schedule_query(int N, int K, int T, int sms, int* out8);   // host-only: see gemm2_tcgen05.cu
 void gemm2_read_env();   // (re)read the pair kernel's A/B knobs; called when an engine is created
 // Deferred mode (variant 2): complete tiles go to `out` as bf16, split tiles stay as fp32 segments in p.ws; the
 // consumer kernel reads both through the returned view (partials.cuh).  No in-kernel reduction handshake.

@@ -59,6 +59,14 @@ struct Seg {
   int tile, kb0, kb1;
 };
 
+// whole-tile waves ahead of the stream-K tail in fused mode (see the schedule comment in the kernel); host and device
+__host__ __device__ __forceinline__ int hybrid_dp_waves(int tiles_total, int units) {
+  int w = tiles_total >= units ? tiles_total / units : 0;
+  // a short tail would cut each of its few tiles into many pieces for one finisher to add (4 tiles over 74 pairs: 18 pieces
+  // each, +120 us at T = 2048): when less than half a wave is left, one whole wave joins the stream-K part
+  if (w > 0 && (tiles_total - w * units) * 2 < units && tiles_total != w * units) --w;
+  return w;
+}
 __device__ __forceinline__ long long range_begin(int unit, long long total, int units) {
   return (static_cast<long long>(unit) * total) / units;
 }
@@ -177,10 +185,7 @@ gemm2_streamk_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_cons
   // pairs sit ~4.5 tiles apart, every pair streams its own slab, 74 slabs x 2 MB do not fit L2 together with the
   // activations and each slab came from DRAM once per token tile (ncu, T = 2048: 2.95x the algorithmic bytes).
   const int tiles_total = pairs_n * ntt;
-  // a short stream-K tail would cut each of its few tiles into many pieces for one finisher to add (4 tiles over 74 pairs:
-  // 18 pieces each, +120 us at T = 2048): when less than half a wave is left, one whole wave joins the stream-K part
-  int dp_waves = (mode == 2 && E.hybrid && tiles_total >= units) ? tiles_total / units : 0;
-  if (dp_waves > 0 && (tiles_total - dp_waves * units) * 2 < units && tiles_total != dp_waves * units) --dp_waves;
+  const int dp_waves = (mode == 2 && E.hybrid) ? hybrid_dp_waves(tiles_total, units) : 0;
   const int dp_tiles = dp_waves * units;
   const long long total = static_cast<long long>(tiles_total - dp_tiles) * KB;   // the stream-K part
   const long long it_begin = range_begin(unit, total, units);
@@ -795,6 +800,31 @@ __global__ void reduce_partials_kernel(PartialView v, __nv_bfloat16* __restrict_
 }  // namespace
 
 int gemm2_units_for(const GemmPlan& p, int ntt) { return units_for(p, ntt); }
+
+// Host-only view of the large-step schedule for (N, K, T) on a device with `sms` SMs: what gemm2_block_n_for_plan, units_for and
+// the engine's fusion rule decide.  out[0] token-tile size, [1] token tiles, [2] tiles, [3] CTA pairs launched, [4] 1 = one whole
+// tile per pair (no split tile), [5] 1 = the engine fuses the elementwise neighbour into this launch (a tile per pair or
+// more), [6] whole-tile waves ahead of the stream-K tail in that fused form, [7] 0.
+void gemm2_schedule_query(int N, int K, int T, int sms, int* out) {
+  GemmPlan p;
+  memset(&p, 0, sizeof(p));
+  p.N = N;
+  p.K = K;
+  p.max_ctas = sms;
+  const int bn = gemm2_block_n_for_plan(p, T);
+  const int ntt = (T + bn - 1) / bn;
+  const int pairs_n = (N + 2 * kSlab - 1) / (2 * kSlab);
+  const int tiles = pairs_n * ntt;
+  const int units = units_for(p, ntt);
+  out[0] = bn;
+  out[1] = ntt;
+  out[2] = tiles;
+  out[3] = units;
+  out[4] = units == tiles && ntt > 1;
+  out[5] = T > 128 && tiles >= sms / 2;
+  out[6] = out[5] && g_hybrid ? hybrid_dp_waves(tiles, units) : 0;
+  out[7] = 0;
+}
 
 void gemm2_read_env() {
   const char* w = getenv("B200_GEMM_WIDE_EPI");
