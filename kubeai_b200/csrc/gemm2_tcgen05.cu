@@ -60,11 +60,15 @@ struct Seg {
 };
 
 // whole-tile waves ahead of the stream-K tail in fused mode (see the schedule comment in the kernel); host and device
-__host__ __device__ __forceinline__ int hybrid_dp_waves(int tiles_total, int units) {
+__host__ __device__ __forceinline__ int hybrid_dp_waves(int tiles_total, int units, int KB) {
   int w = tiles_total >= units ? tiles_total / units : 0;
   // a short tail would cut each of its few tiles into many pieces for one finisher to add (4 tiles over 74 pairs: 18 pieces
   // each, +120 us at T = 2048): when less than half a wave is left, one whole wave joins the stream-K part
   if (w > 0 && (tiles_total - w * units) * 2 < units && tiles_total != w * units) --w;
+  // every pair must own at least one iteration of the tail: a pair with an empty range publishes nothing, and the finisher of
+  // a tile counts on a piece from every pair between the owners of the tile's first and last k-block
+  const long long tail = static_cast<long long>(tiles_total - w * units) * KB;
+  if (tail != 0 && tail < units) w = 0;
   return w;
 }
 __device__ __forceinline__ long long range_begin(int unit, long long total, int units) {
@@ -185,7 +189,7 @@ gemm2_streamk_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_cons
   // pairs sit ~4.5 tiles apart, every pair streams its own slab, 74 slabs x 2 MB do not fit L2 together with the
   // activations and each slab came from DRAM once per token tile (ncu, T = 2048: 2.95x the algorithmic bytes).
   const int tiles_total = pairs_n * ntt;
-  const int dp_waves = (mode == 2 && E.hybrid) ? hybrid_dp_waves(tiles_total, units) : 0;
+  const int dp_waves = (mode == 2 && E.hybrid) ? hybrid_dp_waves(tiles_total, units, KB) : 0;
   const int dp_tiles = dp_waves * units;
   const long long total = static_cast<long long>(tiles_total - dp_tiles) * KB;   // the stream-K part
   const long long it_begin = range_begin(unit, total, units);
@@ -822,7 +826,7 @@ void gemm2_schedule_query(int N, int K, int T, int sms, int* out) {
   out[3] = units;
   out[4] = units == tiles && ntt > 1;
   out[5] = T > 128 && tiles >= sms / 2;
-  out[6] = out[5] && g_hybrid ? hybrid_dp_waves(tiles, units) : 0;
+  out[6] = out[5] && g_hybrid ? hybrid_dp_waves(tiles, units, (K + kBlockK - 1) / kBlockK) : 0;
   out[7] = 0;
 }
 
