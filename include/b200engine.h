@@ -288,6 +288,22 @@ int b200_harness_run(b200_server* server, const char* host, int32_t port, const 
 /* GEMM kernel variant for plans/engines created afterwards: 2 = CTA-pair tcgen05 cta_group::2 (default),
  * 1 = single-CTA kernel (kept for A/B measurements).  Returns the active variant. */
 int b200_set_gemm_variant(int32_t v);
+/* ---- byte-level BPE tokenizer over a local HF tokenizer.json of the Llama-3 family (csrc/tokenizer.cc).  Replaces, on the
+ * host side of this ABI, the tokenizer + chat template the reference's backend pod applies to the model directory it is given
+ * (internal/modelcontroller/engine_vllm.go:34-41).  Host-only: no GPU needed.  Other pipelines are refused at load time. */
+typedef struct b200_tokenizer b200_tokenizer;
+int b200_tokenizer_load(const char* tokenizer_json_path, b200_tokenizer** out);
+void b200_tokenizer_destroy(b200_tokenizer* t);
+int32_t b200_tokenizer_vocab_size(const b200_tokenizer* t);
+int32_t b200_tokenizer_token_id(const b200_tokenizer* t, const char* content);   /* -1 if absent */
+/* Both return the full length (which may exceed cap: call again with a larger buffer), -1 on bad arguments.
+ * allow_special: added / special tokens spelled in the text become their ids (as HF `encode` does). */
+int64_t b200_tokenizer_encode(const b200_tokenizer* t, const char* text, size_t len, int32_t allow_special, int32_t* ids, size_t cap);
+int64_t b200_tokenizer_decode(const b200_tokenizer* t, const int32_t* ids, size_t n, int32_t skip_special, char* buf, size_t cap);
+/* Llama-3 instruct chat framing of n (role, content) messages; add_generation_prompt appends the assistant header. */
+int64_t b200_tokenizer_chat_llama3(const b200_tokenizer* t, const char* const* roles, const char* const* contents, int32_t n,
+                                   int32_t add_generation_prompt, int32_t* ids, size_t cap);
+
 /* Host-only (no GPU needed): how a projection [N, K] of a step of T > 128 tokens is scheduled on a device with `sms` SMs.
  * out8: [0] token-tile size, [1] token tiles, [2] tiles, [3] CTA pairs launched, [4] 1 = one whole tile per pair, [5] 1 = the
  * engine fuses the elementwise neighbour into the launch, [6] whole-tile waves ahead of the stream-K tail, [7] 0. */

@@ -29,6 +29,7 @@ SOURCES = [
     "engine.cu",
     "router.cc",
     "loader.cc",
+    "tokenizer.cc",
     "server.cc",
     "harness.cc",
 ]
