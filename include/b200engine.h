@@ -38,6 +38,7 @@ const char* b200_version(void);
 /* ------------------------------------------------------------------ engine (one per GPU replica)
  * Replaces the backend pod that internal/modelcontroller/engine_vllm.go:82-100 launches. */
 
+typedef struct b200_tokenizer b200_tokenizer;   /* csrc/tokenizer.cc, declared with its functions below */
 typedef struct b200_engine b200_engine;
 
 typedef struct {
@@ -241,6 +242,14 @@ int b200_server_listen(b200_server* s, const char* host, int32_t port, int32_t* 
 int b200_server_metrics(b200_server* s, char* buf, size_t cap);
 /* Fault injection for the retry path: the next `count` submits on `replica` fail; count < 0 = every submit fails, which
  * stands for an engine in the failed state: the first failure drops the replica from the router's endpoint set. */
+/* Attach a tokenizer (b200_tokenizer_load; not owned, must outlive the server; NULL detaches): prompts are then rendered with
+ * the Llama-3 chat framing / <|begin_of_text|> + encoded text, <|eot_id|> and <|end_of_text|> end a generation, and output text is
+ * detokenised incrementally.  Without one the server keeps the synthetic tokenizer. */
+int b200_server_set_tokenizer(b200_server* s, const b200_tokenizer* t);
+/* Host-only: the token ids the server would submit for this request body (parse + chat template + tokenizer).  Returns the
+ * count (may exceed cap), -1 with b200_last_error() = "<status> <message>" when the request is rejected. */
+int64_t b200_server_render_prompt(b200_server* s, const char* path, const char* content_type, const char* body, size_t len,
+                                  int32_t* ids, size_t cap);
 int b200_server_inject_fault(b200_server* s, int32_t replica, int32_t count);
 /* Synthetic tokenizer (ids 0..255 = bytes; " wxyz" spellings round-trip every id). Return the full count/length. */
 int b200_tokenize(int32_t vocab, const char* text, size_t len, int32_t* out, int32_t cap);
@@ -291,7 +300,6 @@ int b200_set_gemm_variant(int32_t v);
 /* ---- byte-level BPE tokenizer over a local HF tokenizer.json of the Llama-3 family (csrc/tokenizer.cc).  Replaces, on the
  * host side of this ABI, the tokenizer + chat template the reference's backend pod applies to the model directory it is given
  * (internal/modelcontroller/engine_vllm.go:34-41).  Host-only: no GPU needed.  Other pipelines are refused at load time. */
-typedef struct b200_tokenizer b200_tokenizer;
 int b200_tokenizer_load(const char* tokenizer_json_path, b200_tokenizer** out);
 void b200_tokenizer_destroy(b200_tokenizer* t);
 int32_t b200_tokenizer_vocab_size(const b200_tokenizer* t);
@@ -300,6 +308,12 @@ int32_t b200_tokenizer_token_id(const b200_tokenizer* t, const char* content);  
  * allow_special: added / special tokens spelled in the text become their ids (as HF `encode` does). */
 int64_t b200_tokenizer_encode(const b200_tokenizer* t, const char* text, size_t len, int32_t allow_special, int32_t* ids, size_t cap);
 int64_t b200_tokenizer_decode(const b200_tokenizer* t, const int32_t* ids, size_t n, int32_t skip_special, char* buf, size_t cap);
+/* Incremental detokenisation of a generated stream: a token may end inside a UTF-8 sequence, so push returns only complete text
+ * (id < 0 flushes what is held).  The pushes concatenated equal b200_tokenizer_decode of all ids. */
+typedef struct b200_detok_stream b200_detok_stream;
+b200_detok_stream* b200_tokenizer_stream_new(const b200_tokenizer* t, int32_t skip_special);
+void b200_tokenizer_stream_free(b200_detok_stream* d);
+int64_t b200_tokenizer_stream_push(b200_detok_stream* d, int32_t id, char* buf, size_t cap);
 /* Llama-3 instruct chat framing of n (role, content) messages; add_generation_prompt appends the assistant header. */
 int64_t b200_tokenizer_chat_llama3(const b200_tokenizer* t, const char* const* roles, const char* const* contents, int32_t n,
                                    int32_t add_generation_prompt, int32_t* ids, size_t cap);

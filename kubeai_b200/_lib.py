@@ -175,12 +175,17 @@ SYMBOLS = {
     "b200_op_silu_mul": (C.c_int, [_vp, _vp, _i32, _i32, _vp]),
     "b200_op_argmax": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp]),
     "b200_op_paged_attn": (C.c_int, [_vp, _i32, _vp, _i32, _vp, _vp, _i32, _vp, _i32, _i32, _i32, _f, _i32, _vp]),
+    "b200_server_set_tokenizer": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "b200_server_render_prompt": (C.c_int64, [C.c_void_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_size_t, _vp, C.c_size_t]),
     "b200_tokenizer_load": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
     "b200_tokenizer_destroy": (None, [C.c_void_p]),
     "b200_tokenizer_vocab_size": (C.c_int32, [C.c_void_p]),
     "b200_tokenizer_token_id": (C.c_int32, [C.c_void_p, C.c_char_p]),
     "b200_tokenizer_encode": (C.c_int64, [C.c_void_p, C.c_char_p, C.c_size_t, _i32, _vp, C.c_size_t]),
     "b200_tokenizer_decode": (C.c_int64, [C.c_void_p, _vp, C.c_size_t, _i32, C.c_char_p, C.c_size_t]),
+    "b200_tokenizer_stream_new": (C.c_void_p, [C.c_void_p, _i32]),
+    "b200_tokenizer_stream_free": (None, [C.c_void_p]),
+    "b200_tokenizer_stream_push": (C.c_int64, [C.c_void_p, _i32, C.c_char_p, C.c_size_t]),
     "b200_tokenizer_chat_llama3": (C.c_int64, [C.c_void_p, _vp, _vp, _i32, _i32, _vp, C.c_size_t]),
     "b200_schedule_query": (C.c_int, [_i32, _i32, _i32, _i32, _vp]),
     "b200_attn_split_query": (C.c_int, [_i32, _i32, _i32, _i32]),

@@ -30,6 +30,7 @@
 #include "../../include/b200engine.h"
 #include "errors.h"
 #include "hostutil.h"
+#include "tokenizer.h"
 
 namespace b200 {
 
@@ -45,6 +46,8 @@ struct Server {
   b200_router* router = nullptr;
   Tokenizer tok;
   int max_model_len = 2048;
+  // optional real tokenizer (b200_server_set_tokenizer): a checkpoint's tokenizer.json instead of the synthetic byte/word ids
+  const b200_tokenizer* real_tok = nullptr;
 
   std::mutex mmu;
   std::map<std::string, int64_t> active;  // kubeai_inference_requests_active{request_model=...}
@@ -301,6 +304,42 @@ const char* finish_str(int code) { return code == B200_FINISH_STOP ? "stop" : co
 }  // namespace
 
 // modelproxy.Handler.ServeHTTP + proxyHTTP with the engine in place of the reverse proxy.
+// K13: the ids the backend would see for this request.  With a real tokenizer attached: the Llama-3 chat framing for chat
+// requests, <|begin_of_text|> + the encoded text for completions (what the reference's vLLM pod does with the checkpoint's
+// tokenizer.json and chat_template); otherwise the synthetic tokenizer and ChatML of hostutil.h.
+static void render_prompt(const Server& sv, const ParsedRequest& pr, std::vector<int32_t>* ids) {
+  if (pr.prompt_is_ids && !pr.chat) {
+    *ids = pr.prompt_ids;
+  } else if (sv.real_tok) {
+    std::vector<int32_t> buf(1024);
+    int64_t n = 0;
+    if (pr.chat) {
+      std::vector<const char*> roles, contents;
+      for (auto& m : pr.messages) { roles.push_back(m.first.c_str()); contents.push_back(m.second.c_str()); }
+      const bool gen = pr.messages.empty() || pr.messages.back().first != "assistant";
+      n = b200_tokenizer_chat_llama3(sv.real_tok, roles.data(), contents.data(), static_cast<int>(roles.size()), gen ? 1 : 0, buf.data(), buf.size());
+      if (n > static_cast<int64_t>(buf.size())) {
+        buf.resize(static_cast<size_t>(n));
+        n = b200_tokenizer_chat_llama3(sv.real_tok, roles.data(), contents.data(), static_cast<int>(roles.size()), gen ? 1 : 0, buf.data(), buf.size());
+      }
+      if (n > 0) ids->assign(buf.begin(), buf.begin() + n);
+    } else {
+      if (tokenizer_bos(sv.real_tok) >= 0) ids->push_back(tokenizer_bos(sv.real_tok));
+      n = b200_tokenizer_encode(sv.real_tok, pr.prompt_text.data(), pr.prompt_text.size(), 1, buf.data(), buf.size());
+      if (n > static_cast<int64_t>(buf.size())) {
+        buf.resize(static_cast<size_t>(n));
+        n = b200_tokenizer_encode(sv.real_tok, pr.prompt_text.data(), pr.prompt_text.size(), 1, buf.data(), buf.size());
+      }
+      if (n > 0) ids->insert(ids->end(), buf.begin(), buf.begin() + n);
+    }
+  } else if (pr.chat) {
+    sv.tok.chat_prompt(pr.messages, ids);
+  } else {
+    sv.tok.encode(pr.prompt_text, ids);
+  }
+  if (ids->empty()) ids->push_back(sv.real_tok && tokenizer_bos(sv.real_tok) >= 0 ? tokenizer_bos(sv.real_tok) : sv.tok.im_start());
+}
+
 static int serve_inference(Server& sv, const std::string& path, const std::string& ctype, const char* body,
                            size_t len, Writer& w) {
   ParsedRequest pr;
@@ -312,10 +351,7 @@ static int serve_inference(Server& sv, const std::string& path, const std::strin
   }
   // tokenise (K13)
   std::vector<int32_t> ids;
-  if (pr.chat) sv.tok.chat_prompt(pr.messages, &ids);
-  else if (pr.prompt_is_ids) ids = pr.prompt_ids;
-  else sv.tok.encode(pr.prompt_text, &ids);
-  if (ids.empty()) ids.push_back(sv.tok.im_start());
+  render_prompt(sv, pr, &ids);
   for (auto t : ids)
     if (t < 0 || t >= sv.tok.vocab) return send_error(w, 400, "bad request: prompt token id out of range");
   int max_tokens = pr.max_tokens > 0 ? pr.max_tokens : sv.default_max_tokens;
@@ -367,8 +403,15 @@ static int serve_inference(Server& sv, const std::string& path, const std::strin
     sp.max_tokens = max_tokens;
     sp.temperature = 0.f;
     sp.ignore_eos = pr.ignore_eos ? 1 : 0;
-    sp.num_stop_ids = static_cast<int>(pr.stop_ids.size());
-    sp.stop_ids = pr.stop_ids.empty() ? nullptr : pr.stop_ids.data();
+    std::vector<int32_t> stops = pr.stop_ids;
+    if (sv.real_tok && !pr.ignore_eos) {   // the checkpoint's end-of-turn / end-of-text tokens end the generation
+      for (const char* name : {"<|eot_id|>", "<|end_of_text|>"}) {
+        const int32_t t = b200_tokenizer_token_id(sv.real_tok, name);
+        if (t >= 0) stops.push_back(t);
+      }
+    }
+    sp.num_stop_ids = static_cast<int>(stops.size());
+    sp.stop_ids = stops.empty() ? nullptr : stops.data();
     uint64_t rid = 0;
     bool failed = false;
     if (sv.faults[replica]->load() < 0) failed = true;  // permanent fault: stands for an engine in the failed state
@@ -376,6 +419,8 @@ static int serve_inference(Server& sv, const std::string& path, const std::strin
     if (!failed && b200_submit(eng, ids.data(), static_cast<int>(ids.size()), &sp, &rid)) failed = true;
 
     std::vector<int32_t> all;
+    DetokStream detok;
+    detok.tok = sv.real_tok;
     int fin = 0;
     b200_usage usage{};
     bool sent_any = false;
@@ -396,7 +441,9 @@ static int serve_inference(Server& sv, const std::string& path, const std::strin
           for (int i = 0; i < n; ++i) {
             const bool last = fin && i == n - 1;
             const std::string fr = last ? std::string("\"") + finish_str(fin) + "\"" : "null";
-            const std::string piece = json_str(sv.tok.piece(buf[i]));
+            // one chunk per token; with a real tokenizer a chunk carries the text that token completed (possibly none: a
+            // token may end inside a UTF-8 sequence), and the last chunk also what was still held
+            const std::string piece = json_str(sv.real_tok ? detok.push(buf[i]) + (last ? detok.flush() : std::string()) : sv.tok.piece(buf[i]));
             if (pr.chat)
               w.write("data: " + head + ",\"choices\":[{\"index\":0,\"delta\":{\"content\":" + piece + "},\"logprobs\":null,\"finish_reason\":" + fr +
                       (last ? ",\"stop_reason\":null" : "") + "}]}\n\n");
@@ -430,7 +477,14 @@ static int serve_inference(Server& sv, const std::string& path, const std::strin
       w.write("data: [DONE]\n\n");
     } else {
       std::string text;
-      for (auto t : all) text += sv.tok.piece(t);
+      if (sv.real_tok) {
+        DetokStream whole;
+        whole.tok = sv.real_tok;
+        for (auto t : all) text += whole.push(t);
+        text += whole.flush();
+      } else {
+        for (auto t : all) text += sv.tok.piece(t);
+      }
       std::string out = "{\"id\":\"" + id + "\",\"object\":\"" + (pr.chat ? "chat.completion" : "text_completion") +
                         "\",\"created\":" + std::to_string(created) + ",\"model\":" + json_str(pr.requested_model) + ",\"choices\":[{\"index\":0,";
       if (pr.chat) out += "\"message\":{\"role\":\"assistant\",\"content\":" + json_str(text) + "},";
@@ -770,6 +824,31 @@ int b200_server_metrics(b200_server* s, char* buf, size_t cap) {
   std::string m = metrics_text(s->impl);
   snprintf(buf, cap, "%s", m.c_str());
   return static_cast<int>(m.size());
+}
+
+int b200_server_set_tokenizer(b200_server* s, const b200_tokenizer* t) {
+  if (!s) { set_error("b200_server_set_tokenizer: bad arguments"); return B200_ERR_INVALID; }
+  if (t && b200_tokenizer_vocab_size(t) > s->impl.tok.vocab) {
+    set_error("the tokenizer has %d ids, the model's vocabulary %d", b200_tokenizer_vocab_size(t), s->impl.tok.vocab);
+    return B200_ERR_INVALID;
+  }
+  s->impl.real_tok = t;
+  return 0;
+}
+
+int64_t b200_server_render_prompt(b200_server* s, const char* path, const char* content_type, const char* body, size_t len, int32_t* ids,
+                                  size_t cap) {
+  if (!s || !path || (!body && len)) { set_error("b200_server_render_prompt: bad arguments"); return -1; }
+  ParsedRequest pr;
+  std::string err;
+  if (int st = parse_request(s->impl, path, content_type ? content_type : "application/json", body, len, &pr, &err)) {
+    set_error("%d %s", st, err.c_str());
+    return -1;
+  }
+  std::vector<int32_t> out;
+  render_prompt(s->impl, pr, &out);
+  for (size_t i = 0; i < out.size() && i < cap; ++i) ids[i] = out[i];
+  return static_cast<int64_t>(out.size());
 }
 
 int b200_server_inject_fault(b200_server* s, int32_t replica, int32_t count) {

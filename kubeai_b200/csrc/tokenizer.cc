@@ -26,6 +26,7 @@
 #include "../../include/b200engine.h"
 #include "errors.h"
 #include "hostutil.h"
+#include "tokenizer.h"
 #include "unicode_ranges.h"
 
 namespace b200 {
@@ -231,7 +232,112 @@ void b200_tokenizer::encode(const char* s, size_t n, bool allow_special, std::ve
   if (n > seg) encode_plain(s + seg, n - seg, out);
 }
 
+namespace b200 {
+
+void tokenizer_token_bytes(const b200_tokenizer* t, int32_t id, bool skip_special, std::string* out) {
+  if (!t || id < 0 || static_cast<size_t>(id) >= t->id_to_token.size()) return;
+  const size_t i = static_cast<size_t>(id);
+  if (t->is_added[i]) {
+    if (!(skip_special && t->is_special[i])) *out += t->id_to_token[i];
+    return;
+  }
+  std::vector<uint32_t> cps, offs;
+  const std::string& tok = t->id_to_token[i];
+  decode_utf8(tok.data(), tok.size(), &cps, &offs);
+  for (uint32_t cp : cps) {
+    auto it = t->cp_to_byte.find(cp);
+    if (it != t->cp_to_byte.end()) out->push_back(static_cast<char>(it->second));
+  }
+}
+int32_t tokenizer_bos(const b200_tokenizer* t) { return t ? t->bos : -1; }
+int32_t tokenizer_eot(const b200_tokenizer* t) { return t ? t->eot : -1; }
+
+namespace {
+// [0, n) -> valid UTF-8; every maximal invalid subpart (a byte that cannot start a sequence, or a lead byte with the valid
+// continuation bytes that follow it when fewer than it announces) becomes ONE U+FFFD — the substitution Rust's
+// String::from_utf8_lossy (hence HF tokenizers' decode) and Python's errors="replace" perform
+std::string sanitize_utf8(const char* s, size_t n) {
+  std::string out;
+  out.reserve(n);
+  auto u = [&](size_t k) { return static_cast<unsigned char>(s[k]); };
+  auto cont = [&](size_t k) { return k < n && (u(k) & 0xC0) == 0x80; };
+  size_t i = 0;
+  while (i < n) {
+    const unsigned char c = u(i);
+    size_t need = 0;
+    unsigned lo = 0x80, hi = 0xBF;
+    if (c < 0x80) { out.push_back(static_cast<char>(c)); ++i; continue; }
+    if (c >= 0xC2 && c <= 0xDF) need = 1;
+    else if (c >= 0xE0 && c <= 0xEF) { need = 2; if (c == 0xE0) lo = 0xA0; if (c == 0xED) hi = 0x9F; }
+    else if (c >= 0xF0 && c <= 0xF4) { need = 3; if (c == 0xF0) lo = 0x90; if (c == 0xF4) hi = 0x8F; }
+    size_t got = 0;
+    if (need >= 1 && i + 1 < n && u(i + 1) >= lo && u(i + 1) <= hi) {
+      got = 1;
+      while (got < need && cont(i + 1 + got)) ++got;
+    }
+    if (need > 0 && got == need) {
+      out.append(s + i, need + 1);
+      i += need + 1;
+    } else {
+      append_utf8(&out, 0xFFFD);
+      i += 1 + got;
+    }
+  }
+  return out;
+}
+// number of trailing bytes that are the beginning of a multi-byte sequence whose remaining bytes have not arrived yet
+size_t incomplete_tail(const std::string& b) {
+  const size_t n = b.size();
+  for (size_t back = 1; back <= 3 && back <= n; ++back) {
+    const unsigned char c = static_cast<unsigned char>(b[n - back]);
+    if ((c & 0xC0) == 0x80) continue;                 // continuation byte: keep looking for its lead
+    size_t need = (c & 0xE0) == 0xC0 ? 2 : (c & 0xF0) == 0xE0 ? 3 : (c & 0xF8) == 0xF0 ? 4 : 1;
+    return need > back ? back : 0;                    // lead byte with fewer continuation bytes than it announces
+  }
+  return 0;
+}
+}  // namespace
+
+std::string DetokStream::push(int32_t id) {
+  tokenizer_token_bytes(tok, id, skip_special, &pending);
+  const size_t hold = incomplete_tail(pending);
+  std::string out = sanitize_utf8(pending.data(), pending.size() - hold);
+  pending.erase(0, pending.size() - hold);
+  return out;
+}
+std::string DetokStream::flush() {
+  std::string out = sanitize_utf8(pending.data(), pending.size());
+  pending.clear();
+  return out;
+}
+
+}  // namespace b200
+
+struct b200_detok_stream {
+  b200::DetokStream s;
+};
+
 extern "C" {
+
+b200_detok_stream* b200_tokenizer_stream_new(const b200_tokenizer* t, int32_t skip_special) {
+  if (!t) return nullptr;
+  auto* d = new b200_detok_stream();
+  d->s.tok = t;
+  d->s.skip_special = skip_special != 0;
+  return d;
+}
+void b200_tokenizer_stream_free(b200_detok_stream* d) { delete d; }
+/* id >= 0: feed one token; id < 0: flush what is held.  Returns the length of the newly complete text (copied to buf, NUL-terminated). */
+int64_t b200_tokenizer_stream_push(b200_detok_stream* d, int32_t id, char* buf, size_t cap) {
+  if (!d) return -1;
+  const std::string out = id >= 0 ? d->s.push(id) : d->s.flush();
+  if (buf && cap) {
+    const size_t k = std::min(out.size(), cap - 1);
+    memcpy(buf, out.data(), k);
+    buf[k] = 0;
+  }
+  return static_cast<int64_t>(out.size());
+}
 
 int b200_tokenizer_load(const char* path, b200_tokenizer** out) {
   using namespace b200;

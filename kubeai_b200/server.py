@@ -105,6 +105,22 @@ class Server:
         check(self._l.b200_server_metrics(self._h, buf, len(buf)))
         return buf.value.decode()
 
+    def set_tokenizer(self, tokenizer):
+        """Attach a kubeai_b200.tokenizer.Tokenizer (or None): Llama-3 chat framing, eot stop ids, incremental detokenisation."""
+        self._tokenizer = tokenizer          # keep alive: the server does not own it
+        check(self._l.b200_server_set_tokenizer(self._h, tokenizer._h if tokenizer is not None else None))
+
+    def render_prompt(self, path: str, body: bytes | str, content_type: str = "application/json") -> list:
+        """The token ids the server would submit for this request (host-only)."""
+        if isinstance(body, str):
+            body = body.encode("utf-8")
+        n = self._l.b200_server_render_prompt(self._h, path.encode(), content_type.encode(), body, len(body), None, 0)
+        if n < 0:
+            check(-1)
+        buf = (C.c_int32 * max(int(n), 1))()
+        self._l.b200_server_render_prompt(self._h, path.encode(), content_type.encode(), body, len(body), buf, n)
+        return list(buf[:n])
+
     def inject_fault(self, replica: int, count: int):
         check(self._l.b200_server_inject_fault(self._h, replica, count))
 

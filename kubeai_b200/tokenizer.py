@@ -55,3 +55,29 @@ class Tokenizer:
         buf = (C.c_int32 * max(int(k), 1))()
         self._l.b200_tokenizer_chat_llama3(self._h, roles, contents, n, 1 if add_generation_prompt else 0, buf, k)
         return list(buf[:k])
+
+
+class DetokStream:
+    """Incremental detokenisation (b200_tokenizer_stream_*): push(id) returns the text that id completed."""
+
+    def __init__(self, tokenizer: Tokenizer, skip_special: bool = True):
+        self._l = lib()
+        self._tok = tokenizer
+        self._h = self._l.b200_tokenizer_stream_new(tokenizer._h, 1 if skip_special else 0)
+
+    def _call(self, token_id: int) -> str:
+        buf = C.create_string_buffer(256)
+        n = self._l.b200_tokenizer_stream_push(self._h, token_id, buf, len(buf))
+        assert 0 <= n < len(buf)
+        return buf.raw[:n].decode("utf-8")        # strict: a push never returns a broken sequence
+
+    def push(self, token_id: int) -> str:
+        return self._call(token_id)
+
+    def flush(self) -> str:
+        return self._call(-1)
+
+    def close(self):
+        if self._h:
+            self._l.b200_tokenizer_stream_free(self._h)
+            self._h = None

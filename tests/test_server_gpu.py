@@ -185,3 +185,50 @@ def test_destroy_with_idle_keepalive_client_returns_promptly(stack):
     for c in socks:
         assert c.recv(16) == b""                                  # peer closed
         c.close()
+
+
+def test_real_tokenizer_end_to_end(stack, tmp_path):
+    """A tokenizer.json of the Llama-3 pipeline attached to the server: the prompt the engine sees is the chat template's,
+    the streamed deltas are valid text whose concatenation is the detokenised generation, non-stream text is the same."""
+    tokenizers = pytest.importorskip("tokenizers")
+    from tokenizers import Regex, Tokenizer as HFTokenizer, decoders, models, pre_tokenizers, trainers
+    from kubeai_b200.tokenizer import Tokenizer
+    pat = r"(?i:'s|'t|'re|'ve|'m|'ll|'d)|[^\r\n\p{L}\p{N}]?\p{L}+|\p{N}{1,3}| ?[^\s\p{L}\p{N}]+[\r\n]*|\s*[\r\n]+|\s+(?!\S)|\s+"
+    hf = HFTokenizer(models.BPE(ignore_merges=True))
+    hf.pre_tokenizer = pre_tokenizers.Sequence([pre_tokenizers.Split(Regex(pat), behavior="isolated"), pre_tokenizers.ByteLevel(add_prefix_space=False, use_regex=False)])
+    hf.decoder = decoders.ByteLevel()
+    specials = ["<|begin_of_text|>", "<|end_of_text|>", "<|start_header_id|>", "<|end_header_id|>", "<|eot_id|>"]
+    hf.train_from_iterator(["hello world, how are you today? I'm fine thanks; it's 12345 o'clock"] * 50,
+                           trainers.BpeTrainer(vocab_size=V - 8, special_tokens=specials, initial_alphabet=pre_tokenizers.ByteLevel.alphabet(), show_progress=False))
+    hf.save(str(tmp_path / "tokenizer.json"))
+    srv, engines = stack
+    with Tokenizer(tmp_path / "tokenizer.json") as tok:
+        assert tok.vocab_size <= V
+        srv.set_tokenizer(tok)
+        msgs = [{"role": "user", "content": "hello world, how are you?"}]
+        body = dict(model="mini", messages=msgs, max_tokens=24, temperature=0)
+        prompt = srv.render_prompt("/v1/chat/completions", json.dumps(body))
+        assert prompt == tok.chat(msgs) and prompt[0] == tok.token_id("<|begin_of_text|>")
+        # what the engine generates for that prompt, with the stop ids the server adds
+        stops = [tok.token_id("<|eot_id|>"), tok.token_id("<|end_of_text|>")]
+        rid = engines[0].submit(prompt, max_tokens=24, ignore_eos=False, stop_ids=stops)
+        gen = []
+        while True:
+            assert engines[0].wait(rid, 30.0)
+            pr = engines[0].poll(rid)
+            gen += pr.tokens
+            if pr.finished:
+                break
+        engines[0].release(rid)
+        want = tok.decode([t for t in gen if t not in stops], skip_special=True)
+        r = srv.handle("POST", "/openai/v1/chat/completions", json.dumps(dict(body, stream=True)))
+        chunks = [json.loads(e) for e in r.sse_events()[:-1]]
+        deltas = [c["choices"][0]["delta"].get("content", "") for c in chunks if c["choices"]]
+        assert len(deltas) == 1 + len(gen)                  # role chunk + one chunk per token, whatever text each completes
+        for d in deltas:
+            d.encode("utf-8")                               # every delta is well-formed text on its own
+        assert "".join(deltas) == want
+        r = srv.handle("POST", "/openai/v1/chat/completions", json.dumps(body))
+        assert r.json()["choices"][0]["message"]["content"] == want
+        assert r.json()["usage"]["prompt_tokens"] == len(prompt)
+        srv.set_tokenizer(None)

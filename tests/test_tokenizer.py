@@ -137,3 +137,52 @@ def test_other_pipelines_are_refused_not_approximated(pair, tmp_path):
         Tokenizer(tmp_path / "nfc.json")
     with pytest.raises(B200Error):
         Tokenizer(tmp_path / "missing.json")
+
+
+def test_incremental_detokenisation_never_emits_a_broken_utf8_sequence(pair):
+    from kubeai_b200.tokenizer import DetokStream
+    hf, mine, _ = pair
+    rng = random.Random(3)
+    texts = ["naïve café 你好 \U0001f642\U0001f44d\U0001f3fd done", "日本語のテキスト ①②③ ½", "plain ascii only", "\U0001f680" * 5]
+    seqs = [mine.encode(t) for t in texts]
+    seqs += [[rng.randrange(6, mine.vocab_size) for _ in range(60)] for _ in range(40)]     # random ids: arbitrary byte soup
+    for ids in seqs:
+        st = DetokStream(mine, skip_special=False)
+        out = "".join(st.push(i) for i in ids) + st.flush()        # push() decodes strictly: raises on a broken sequence
+        st.close()
+        assert out == mine.decode(ids)
+        assert out == hf.decode(ids, skip_special_tokens=False)
+    st = DetokStream(mine, skip_special=True)
+    ids = mine.encode("a<|eot_id|>b")
+    assert "".join(st.push(i) for i in ids) + st.flush() == "ab"
+    st.close()
+
+
+def test_server_renders_prompts_with_the_attached_tokenizer(pair):
+    transformers = pytest.importorskip("transformers")
+    from kubeai_b200.server import Server
+    hf, mine, _ = pair
+    fast = transformers.PreTrainedTokenizerFast(tokenizer_object=hf, bos_token="<|begin_of_text|>", eos_token="<|eot_id|>", chat_template=LLAMA3_TEMPLATE)
+    with Server([None], model="m", vocab=4096) as srv:
+        msgs = [{"role": "system", "content": "Be brief."}, {"role": "user", "content": "What's up? 你好 12345"}]
+        body = json.dumps({"model": "m", "messages": msgs})
+        synthetic = srv.render_prompt("/v1/chat/completions", body)
+        srv.set_tokenizer(mine)
+        want = fast.apply_chat_template(msgs, tokenize=True, add_generation_prompt=True)
+        want = want["input_ids"] if hasattr(want, "keys") else want
+        assert srv.render_prompt("/v1/chat/completions", body) == list(want) != synthetic
+        # a conversation that already ends with an assistant turn is continued, not re-opened
+        cont = msgs + [{"role": "assistant", "content": "Not much"}]
+        want = fast.apply_chat_template(cont, tokenize=True, add_generation_prompt=False)
+        want = want["input_ids"] if hasattr(want, "keys") else want
+        assert srv.render_prompt("/v1/chat/completions", json.dumps({"model": "m", "messages": cont})) == list(want)
+        # completions: <|begin_of_text|> + the text, as vLLM's add_special_tokens default does for this family
+        text = "Once upon a time, in 1999"
+        assert srv.render_prompt("/v1/completions", json.dumps({"model": "m", "prompt": text})) == [mine.token_id("<|begin_of_text|>")] + hf.encode(text).ids
+        assert srv.render_prompt("/v1/completions", json.dumps({"model": "m", "prompt": [5, 6, 7]})) == [5, 6, 7]
+        srv.set_tokenizer(None)
+        assert srv.render_prompt("/v1/chat/completions", body) == synthetic
+    from kubeai_b200 import B200Error
+    with Server([None], model="m", vocab=300) as small:
+        with pytest.raises(B200Error, match="vocabulary"):
+            small.set_tokenizer(mine)
