@@ -21,7 +21,7 @@ static void on_signal(int) { g_stop = 1; }
 
 int main(int argc, char** argv) {
   int gpus = 1, port = 8000, max_seqs = 128, max_len = 2048, budget = 2048;
-  std::string model = "llama-3-8b", model_dir, strategy = "LeastLoad", host = "0.0.0.0", adapters;
+  std::string model = "llama-3-8b", model_dir, strategy = "LeastLoad", host = "0.0.0.0", adapters, tokenizer_path;
   double kv_fraction = 0.85;
   unsigned long long seed = 0;
   for (int i = 1; i < argc; ++i) {
@@ -33,6 +33,7 @@ int main(int argc, char** argv) {
     else if (a == "--model") model = next();
     else if (a == "--model-dir") model_dir = next();
     else if (a == "--adapters") adapters = next();
+    else if (a == "--tokenizer") tokenizer_path = next();   // tokenizer.json; default: <model-dir>/tokenizer.json when present
     else if (a == "--strategy") strategy = next();
     else if (a == "--max-num-seqs") max_seqs = atoi(next());
     else if (a == "--max-model-len") max_len = atoi(next());
@@ -68,6 +69,16 @@ int main(int argc, char** argv) {
   sc.max_model_len = cfg.max_model_len;
   b200_server* srv = nullptr;
   if (b200_server_create(&sc, engines.data(), gpus, &srv)) { fprintf(stderr, "server: %s\n", b200_last_error()); return 1; }
+  // the checkpoint's tokenizer + Llama-3 chat template when there is one; the synthetic tokenizer otherwise
+  b200_tokenizer* tokenizer = nullptr;
+  if (tokenizer_path.empty() && !model_dir.empty()) {
+    const std::string cand = model_dir + "/tokenizer.json";
+    if (FILE* f = fopen(cand.c_str(), "rb")) { fclose(f); tokenizer_path = cand; }
+  }
+  if (!tokenizer_path.empty()) {
+    if (b200_tokenizer_load(tokenizer_path.c_str(), &tokenizer) || b200_server_set_tokenizer(srv, tokenizer)) { fprintf(stderr, "tokenizer: %s\n", b200_last_error()); return 1; }
+    fprintf(stderr, "[b200serve] tokenizer %s (%d ids)\n", tokenizer_path.c_str(), b200_tokenizer_vocab_size(tokenizer));
+  }
   int bound = 0;
   if (b200_server_listen(srv, host.c_str(), port, &bound)) { fprintf(stderr, "listen: %s\n", b200_last_error()); return 1; }
   fprintf(stderr, "[b200serve] %s (%s) on http://%s:%d/openai/v1/chat/completions, %d replica(s)\n", model.c_str(), strategy.c_str(), host.c_str(), bound, gpus);
@@ -75,6 +86,7 @@ int main(int argc, char** argv) {
   signal(SIGTERM, on_signal);
   while (!g_stop) usleep(200000);
   b200_server_destroy(srv);
+  if (tokenizer) b200_tokenizer_destroy(tokenizer);
   for (auto e : engines) b200_engine_destroy(e);
   return 0;
 }
