@@ -7,6 +7,8 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <time.h>
+
 #include <string>
 #include <utility>
 #include <vector>
