@@ -100,6 +100,31 @@ func NewServer(model string, strategy int, engines []*Engine) (*Server, error) {
 
 func (s *Server) Close() { C.b200_server_destroy(s.h) }
 
+// Tokenizer is the checkpoint's tokenizer.json (Llama-3 family) loaded on the host side of the ABI: what the backend pod does
+// with the model directory internal/modelcontroller/engine_vllm.go:34-41 hands it.
+type Tokenizer struct{ h *C.b200_tokenizer }
+
+func LoadTokenizer(tokenizerJSON string) (*Tokenizer, error) {
+	cp := C.CString(tokenizerJSON)
+	defer C.free(unsafe.Pointer(cp))
+	var t *C.b200_tokenizer
+	if rc := C.b200_tokenizer_load(cp, &t); rc != 0 {
+		return nil, errors.New(C.GoString(C.b200_last_error()))
+	}
+	return &Tokenizer{t}, nil
+}
+
+func (t *Tokenizer) Close() { C.b200_tokenizer_destroy(t.h) }
+
+// UseTokenizer makes the server render prompts with the Llama-3 chat template, stop at <|eot_id|> / <|end_of_text|> and
+// detokenise its stream incrementally.  The tokenizer must outlive the server.
+func (s *Server) UseTokenizer(t *Tokenizer) error {
+	if rc := C.b200_server_set_tokenizer(s.h, t.h); rc != 0 {
+		return errors.New(C.GoString(C.b200_last_error()))
+	}
+	return nil
+}
+
 //export goBegin
 func goBegin(ud unsafe.Pointer, status C.int, ctype *C.char) C.int {
 	w := cgo.Handle(uintptr(ud)).Value().(http.ResponseWriter)
