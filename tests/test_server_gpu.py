@@ -181,7 +181,7 @@ def test_destroy_with_idle_keepalive_client_returns_promptly(stack):
         socks.append(c)                                           # kept open: the server thread sits in recv()
     t0 = time.perf_counter()
     srv.close()
-    assert time.perf_counter() - t0 < 1.0
+    assert time.perf_counter() - t0 < 3.0                          # the old behaviour was a 5 s stall
     for c in socks:
         assert c.recv(16) == b""                                  # peer closed
         c.close()
