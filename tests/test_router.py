@@ -251,3 +251,40 @@ def test_hash_lookup_metrics_follow_the_reference_instruments():
     assert 'kubeai_inference_requests_hash_lookup_iterations_bucket{le="2"} 25' in m
     assert "kubeai_inference_requests_hash_lookup_iterations_sum 26" in m and "hash_lookup_default{" not in m
     [d() for d in dones]
+
+
+def test_closed_loop_least_load_is_sticky_and_prefix_hash_is_stickier():
+    """The routing experiment's side finding (profiles/r02_routing.md): in a closed-loop load generator a conversation's next
+    turn is issued when its previous turn finishes, i.e. on the endpoint that just lost one in-flight request — so LeastLoad
+    keeps most conversations where their KV prefix is, without looking at the prefix.  Event simulation on the native
+    router: 8 endpoints, 64 conversations of 12 turns, service times with jitter."""
+    import heapq
+    import random
+    from kubeai_b200.router import LEAST_LOAD, PREFIX_HASH, Router
+
+    def run(strategy):
+        rng = random.Random(5)
+        r = Router(replication=256)
+        r.reconcile_endpoints({f"pod-{i}": {"address": f"gpu:{i}"} for i in range(8)})
+        events, last, same, total = [], {}, 0, 0
+        for c in range(64):
+            heapq.heappush(events, (rng.random() * 0.01, c, 0, None))       # (time, conversation, turn, done of the previous turn)
+        while events:
+            t, c, turn, done = heapq.heappop(events)
+            if done is not None:
+                done()                                                      # the previous turn's request ends ...
+            if turn == 12:
+                continue
+            addr, d = r.await_best_address(strategy, prefix=f"conversation {c:04d} first user message", mean_load_pct=125)
+            if turn > 0:
+                total += 1
+                same += addr == last[c]
+            last[c] = addr
+            heapq.heappush(events, (t + 0.25 + 0.1 * rng.random(), c, turn + 1, d))    # ... and the next one starts at once
+        assert r.in_flight()[1] == 0
+        r.close()
+        return same / total
+
+    sticky_ll, sticky_ph = run(LEAST_LOAD), run(PREFIX_HASH)
+    assert sticky_ph >= 0.97, sticky_ph           # CHWBL moves a conversation only when its endpoint is over the load bound
+    assert 0.5 <= sticky_ll < sticky_ph, (sticky_ll, sticky_ph)   # far above the 1/8 of a prefix-blind uniform choice
