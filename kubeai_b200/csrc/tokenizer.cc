@@ -175,25 +175,46 @@ void b200_tokenizer::bpe(const char* s, size_t n, std::vector<int32_t>* out) con
       return;
     }
   }
-  std::vector<int> sym(n);
-  for (size_t i = 0; i < n; ++i) sym[i] = byte_symbol[static_cast<unsigned char>(s[i])];
-  // lowest rank first, leftmost among equals: the order tokenizers' merge queue pops (models/bpe/word.rs)
-  while (sym.size() > 1) {
-    int best_rank = INT32_MAX, best_id = -1;
-    size_t best_pos = 0;
-    for (size_t i = 0; i + 1 < sym.size(); ++i) {
-      auto it = merges.find((static_cast<uint64_t>(static_cast<uint32_t>(sym[i])) << 32) | static_cast<uint32_t>(sym[i + 1]));
-      if (it != merges.end() && it->second.first < best_rank) {
-        best_rank = it->second.first;
-        best_id = it->second.second;
-        best_pos = i;
-      }
-    }
-    if (best_id < 0) break;
-    sym[best_pos] = best_id;
-    sym.erase(sym.begin() + static_cast<long>(best_pos) + 1);
+  // Symbols as a doubly linked list over the byte positions; candidate merges in a min-heap ordered by (rank, position of the
+  // left symbol) — lowest rank first, leftmost among equals: the order tokenizers' merge queue pops (models/bpe/word.rs).  An
+  // entry is stale when either symbol has since been merged away or changed; O(n log n) for a pre-token of n bytes (a single
+  // "word" of a megabyte must not cost a quadratic scan).
+  std::vector<int> sym(n), prev(n), next(n);
+  for (size_t i = 0; i < n; ++i) {
+    sym[i] = byte_symbol[static_cast<unsigned char>(s[i])];
+    prev[i] = static_cast<int>(i) - 1;
+    next[i] = i + 1 < n ? static_cast<int>(i) + 1 : -1;
   }
-  for (int v : sym) out->push_back(v);
+  struct Cand {
+    int rank, pos, left, right, merged;
+  };
+  auto worse = [](const Cand& x, const Cand& y) { return x.rank != y.rank ? x.rank > y.rank : x.pos > y.pos; };
+  std::vector<Cand> heap;
+  auto push = [&](int pos) {
+    const int nx = next[static_cast<size_t>(pos)];
+    if (nx < 0) return;
+    auto it = merges.find((static_cast<uint64_t>(static_cast<uint32_t>(sym[static_cast<size_t>(pos)])) << 32) | static_cast<uint32_t>(sym[static_cast<size_t>(nx)]));
+    if (it == merges.end()) return;
+    heap.push_back(Cand{it->second.first, pos, sym[static_cast<size_t>(pos)], sym[static_cast<size_t>(nx)], it->second.second});
+    std::push_heap(heap.begin(), heap.end(), worse);
+  };
+  for (size_t i = 0; i + 1 < n; ++i) push(static_cast<int>(i));
+  while (!heap.empty()) {
+    std::pop_heap(heap.begin(), heap.end(), worse);
+    const Cand c = heap.back();
+    heap.pop_back();
+    const size_t p = static_cast<size_t>(c.pos);
+    if (sym[p] != c.left) continue;                       // the left symbol was merged away (-1) or has grown
+    const int nx = next[p];
+    if (nx < 0 || sym[static_cast<size_t>(nx)] != c.right) continue;
+    sym[p] = c.merged;
+    sym[static_cast<size_t>(nx)] = -1;
+    next[p] = next[static_cast<size_t>(nx)];
+    if (next[p] >= 0) prev[static_cast<size_t>(next[p])] = c.pos;
+    if (prev[p] >= 0) push(prev[p]);
+    push(c.pos);
+  }
+  for (int i = 0; i >= 0; i = next[static_cast<size_t>(i)]) out->push_back(sym[static_cast<size_t>(i)]);
 }
 
 void b200_tokenizer::encode_plain(const char* s, size_t n, std::vector<int32_t>* out) const {
